@@ -1,0 +1,168 @@
+/*
+ * spano.h -- C ABI of the B200-native compositing path for SimplePanorama.
+ *
+ * This is the drop-in boundary: the reference's unchanged C++ entry points in
+ * src/classes (stitch_parameters::return_full / get_preview / blend,
+ * src/classes/_panorama.cpp:161-354) keep calling their callees
+ *   proj::get_proj_parameters / projection::project   src/math/_projection.h:53-60,155-161
+ *   blnd::createSurroundingMask + cv::erode            src/math/_blending.h, _projection.cpp:441-443
+ *   imgs[i] / gain[i]                                  src/classes/_panorama.cpp:321-327
+ *   blnd::multi_blend                                  src/math/_blending.h:24
+ *   util::get_pan_dimension                            src/system/_util.cpp:204-231
+ * and those callee bodies forward to the functions below (shim/ shows the cv::Mat glue,
+ * INTEGRATION.md the build wiring).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no C++/torch/OpenCV types.
+ *   - every function returns 0 on success, <0 on error (SPANO_E_*); it never throws.
+ *     spano_last_error(ctx) gives the message of the last failure on that context.
+ *   - pointers are borrowed for the duration of the call; outputs are caller-allocated
+ *     after a size query (spano_warp_roi / spano_pan_dimension).
+ *   - images are row-major, interleaved BGR uint8 ("8UC3"), `step` = bytes per row.
+ *   - one spano_ctx per panorama object / thread; calls on one ctx are serialised by an
+ *     internal mutex, different contexts may be used concurrently.
+ *   - functions named spano_dev_* take DEVICE pointers and enqueue on the context's
+ *     stream without synchronising (the caller owns the stream, see spano_set_stream);
+ *     the others take HOST pointers and return when the result is in host memory.
+ *   - there is no CPU fallback: without a CUDA device spano_create fails.
+ */
+#ifndef SPANO_H
+#define SPANO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPANO_VERSION 100
+
+/* projection kinds == pan::Projection order used by the reference's projector classes */
+#define SPANO_SPHERICAL 0     /* proj::spherical_proj   -> cv::detail::SphericalWarper    */
+#define SPANO_CYLINDRICAL 1   /* proj::cylindrical_proj -> cv::detail::CylindricalWarper  */
+#define SPANO_STEREOGRAPHIC 2 /* proj::sten_proj        -> cv::detail::StereographicWarper */
+
+#define SPANO_OK 0
+#define SPANO_E_INVALID (-1)  /* bad argument (what the reference would CV_Assert / throw on) */
+#define SPANO_E_CUDA (-2)     /* CUDA runtime error                                            */
+#define SPANO_E_NOMEM (-3)    /* device or host allocation failed                              */
+#define SPANO_E_NODEVICE (-4) /* no usable CUDA device: the library has no CPU path            */
+#define SPANO_E_LIMIT (-5)    /* exceeds a limit of the reference path (e.g. remap's 32767 px) */
+
+#define SPANO_MAX_BANDS 10    /* UI caps bands at one digit; divisor 255/bands needs bands <= 255 */
+
+/* output kinds of the blend */
+#define SPANO_OUT_F32 0 /* CV_32FC3 as returned by blnd::multi_blend                          */
+#define SPANO_OUT_U8 1  /* CV_8UC3 as returned by stitch_parameters::blend (x255, convertTo)  */
+
+typedef struct spano_ctx spano_ctx;
+
+/* ---- lifetime --------------------------------------------------------------------- */
+int spano_version(void);
+int spano_create(spano_ctx **out, int device);
+void spano_destroy(spano_ctx *ctx);
+const char *spano_last_error(spano_ctx *ctx);
+/* Use an external CUDA stream (cudaStream_t as void*) for all work of this context;
+ * NULL restores the context's own stream. */
+int spano_set_stream(spano_ctx *ctx, void *cuda_stream);
+/* Block until everything enqueued on the context's stream has finished. */
+int spano_sync(spano_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+long long spano_launch_count(spano_ctx *ctx);
+
+/* ---- a3: projector geometry (host arithmetic, bit-exact with OpenCV's warpers) -----
+ * Replaces cv::detail::RotationWarperBase::detectResultRoi[ByBorder] and
+ * SphericalWarper::detectResultRoi as reached from projection::project
+ * (src/math/_projection.cpp:51,81,321).  K and R are the float32 3x3 matrices the
+ * reference hands to OpenCV, i.e. K is already K_adj (principal point flipped,
+ * _projection.cpp:41-44).  The warped tile is (roi + 1) in both dimensions and its
+ * corner is the truncated ROI top-left, exactly like RotationWarperBase::warp.
+ * Pure host arithmetic: ctx may be NULL.                                                 */
+int spano_warp_roi(spano_ctx *ctx, int proj, float scale, const float K[9], const float R[9], int src_w, int src_h,
+                   int *tl_x, int *tl_y, int *dst_w, int *dst_h);
+
+/* a9: util::get_pan_dimension (src/system/_util.cpp:204-231). */
+int spano_pan_dimension(int n, const int *tl_x, const int *tl_y, const int *w, const int *h, int *canvas_w,
+                        int *canvas_h, int *min_x, int *min_y);
+
+/* ---- a3 + a4 + a6: warp one image (HOST buffers) -------------------------------------
+ * = projection::project + createSurroundingMask(warped,true,1) + cv::erode(3 iterations)
+ *   + `warped / gain` (src/math/_projection.cpp:422-454, src/classes/_panorama.cpp:321-327).
+ * dst must be dst_w x dst_h from spano_warp_roi.  The validity mask is computed from the
+ * un-gained warp, as in the reference; gain is applied afterwards (gain = 1.0: none).
+ * dst_valid_mask may be NULL (get_masks = false).                                        */
+int spano_warp(spano_ctx *ctx, int proj, float scale, const float K[9], const float R[9], const uint8_t *src_bgr,
+               int src_w, int src_h, size_t src_step, double gain, uint8_t *dst_bgr, size_t dst_step,
+               uint8_t *dst_valid_mask, size_t mask_step);
+
+/* a4 alone: blnd::createSurroundingMask(img,true,1) followed by `erode_iters` 3x3 erosions. */
+int spano_surrounding_mask(spano_ctx *ctx, const uint8_t *bgr, int w, int h, size_t step, int erode_iters,
+                           uint8_t *mask, size_t mask_step);
+
+/* a6 alone: `img / gain` on CV_8UC3, in place. */
+int spano_apply_gain(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, double gain);
+
+/* ---- a7 + a8 + a10: blnd::multi_blend (+ the x255/convertTo tail of blend()) ----------
+ * tiles[j]  : CV_8UC3 w[j] x h[j]      (gain already applied)
+ * masks[j]  : CV_8UC1 mask_cut, 0..255 (seam mask resized to the tile, _panorama.cpp:329-335)
+ * masks_orig: CV_8UC1 validity mask {0,255}
+ * out       : canvas_w x canvas_h from spano_pan_dimension; float32x3 (SPANO_OUT_F32) or
+ *             uint8x3 (SPANO_OUT_U8); out_step in bytes.                                  */
+int spano_multiblend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps,
+                     const uint8_t *const *masks, const size_t *mask_steps, const uint8_t *const *masks_orig,
+                     const size_t *orig_steps, const int *tl_x, const int *tl_y, const int *w, const int *h,
+                     int bands, double sigma, int out_kind, void *out, size_t out_step);
+
+/* ---- a1: the fused path of stitch_parameters::return_full (MULTI_BLEND) --------------
+ * sources -> warp + validity masks + gain -> multi_blend -> 8-bit canvas, tiles stay on
+ * the device between the stages.  Geometry (tile corners/sizes, canvas size) must have been
+ * queried with spano_warp_roi / spano_pan_dimension; masks_cut[j] is w[j] x h[j].
+ * gains may be NULL (conf.gain_compensation == false).
+ * row0/row1 select a band of canvas rows [row0,row1) (row-band sharding, one band per GPU);
+ * `canvas` then receives only those rows (row 0 of `canvas` is canvas row row0).          */
+typedef struct spano_image_desc {
+    const uint8_t *src_bgr; /* source image, 8UC3 */
+    int src_w, src_h;
+    size_t src_step;
+    float K[9]; /* K_adj, float32 */
+    float R[9];
+    double gain;               /* 1.0 = none */
+    const uint8_t *mask_cut;   /* w x h, 8UC1 */
+    size_t mask_cut_step;
+    int tl_x, tl_y, w, h;      /* from spano_warp_roi */
+} spano_image_desc;
+
+int spano_composite(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *images, int bands,
+                    double sigma, int row0, int row1, uint8_t *canvas, size_t canvas_step);
+
+/* Same, with every pointer in `images` and `canvas` a DEVICE pointer; asynchronous on the
+ * context's stream.  src_step must be a multiple of 8 and src_bgr 8-byte aligned for the
+ * fast sampling path (any layout is accepted; others take the byte path).                */
+int spano_dev_composite(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *images, int bands,
+                        double sigma, int row0, int row1, uint8_t *canvas, size_t canvas_step);
+
+/* ---- device-pointer stage entry points (asynchronous on the context's stream) -------- */
+int spano_dev_warp(spano_ctx *ctx, int proj, float scale, const float K[9], const float R[9], const uint8_t *src_bgr,
+                   int src_w, int src_h, size_t src_step, double gain, int tl_x, int tl_y, int dst_w, int dst_h,
+                   uint8_t *dst_bgr, size_t dst_step, uint8_t *dst_valid_mask, size_t mask_step);
+int spano_dev_multiblend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps,
+                         const uint8_t *const *masks, const size_t *mask_steps, const uint8_t *const *masks_orig,
+                         const size_t *orig_steps, const int *tl_x, const int *tl_y, const int *w, const int *h,
+                         int bands, double sigma, int row0, int row1, int out_kind, void *out, size_t out_step);
+
+/* ---- measurement helpers ---------------------------------------------------------------
+ * Time (ms, CUDA events on the context's stream) spent in the kernels of each stage since
+ * the last spano_timers_reset: [0] warp  [1] validity mask  [2] blend  [3] normalise.
+ * Enabled with spano_timers_enable(ctx, 1); adds event records around each stage.         */
+int spano_timers_enable(spano_ctx *ctx, int on);
+int spano_timers_reset(spano_ctx *ctx);
+int spano_timers_read(spano_ctx *ctx, float ms[4], long long launches[4]);
+/* FP32 FMA-pipe microbenchmark (the blend kernel's roofline denominator; MEASURED_PEAKS.json
+ * carries no fp32 entry): returns achieved TFLOP/s of a register-resident FFMA loop.      */
+int spano_fp32_peak(spano_ctx *ctx, int variant, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPANO_H */

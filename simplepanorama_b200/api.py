@@ -1,0 +1,330 @@
+"""Host-side mirror of the reference's compositing interface, on top of the C ABI (include/spano.h).
+
+Function names, argument meaning and error behaviour follow the reference's C++ callees so the
+parity tests read like tests of the reference itself (paths relative to the upstream tree):
+
+    project / get_proj_parameters   proj::projection::project, proj::get_proj_parameters
+                                    (src/math/_projection.cpp:27-84,297-324,422-454)
+    create_surrounding_mask         blnd::createSurroundingMask  (src/math/_blending.cpp:278-324)
+    apply_gain                      `imgs[i] / gain[i]`          (src/classes/_panorama.cpp:321-327)
+    get_pan_dimension               util::get_pan_dimension      (src/system/_util.cpp:204-231)
+    multi_blend                     blnd::multi_blend            (src/math/_blending.cpp:186-252)
+    blend                           stitch_parameters::blend, MULTI_BLEND (src/classes/_panorama.cpp:242-249)
+    return_full                     stitch_parameters::return_full (src/classes/_panorama.cpp:259-354)
+
+All compute happens in libspano.so (hand-written CUDA, sm_100a).  Host arrays are numpy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from ._lib import (CYLINDRICAL, OUT_F32, OUT_U8, SPHERICAL, STEREOGRAPHIC, ImageDesc, SpanoError)
+
+__all__ = [
+    "SPHERICAL", "CYLINDRICAL", "STEREOGRAPHIC", "Context", "ProjData", "SpanoError", "adjusted_camera", "warp_roi",
+    "project", "get_proj_parameters", "create_surrounding_mask", "validity_mask", "apply_gain", "get_pan_dimension",
+    "multi_blend", "blend", "return_full", "default_context",
+]
+
+
+def _f9(a) -> np.ndarray:
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(9))
+    return a
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(_lib.c_f32p)
+
+
+def _ip(a: np.ndarray):
+    return a.ctypes.data_as(_lib.c_intp)
+
+
+def _u8img(a, channels: int, what: str) -> np.ndarray:
+    a = np.asarray(a)
+    if a.dtype != np.uint8:
+        raise SpanoError(_lib.E_INVALID, f"{what}: expected uint8, got {a.dtype}")
+    want = 3 if channels == 3 else 2
+    if a.ndim != want or (channels == 3 and a.shape[2] != 3):
+        raise SpanoError(_lib.E_INVALID, f"{what}: expected {'HxWx3' if channels == 3 else 'HxW'}, got {a.shape}")
+    if a.size == 0:
+        raise SpanoError(_lib.E_INVALID, f"{what}: empty image")
+    if a.strides[-1] != 1 or (channels == 3 and a.strides[1] != 3):
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class Context:
+    """One spano_ctx (one per panorama object / thread, like one pan::panorama per viewer window)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.spano_create(C.byref(h), int(device))
+        if rc != 0:
+            raise SpanoError(rc, {
+                _lib.E_NODEVICE: "no usable CUDA (sm_100) device; this library has no CPU path",
+                _lib.E_INVALID: f"invalid device ordinal {device}",
+            }.get(rc, "spano_create failed"))
+        self.h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.spano_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise SpanoError(rc, self.lib.spano_last_error(self.h).decode("utf-8", "replace"))
+
+    def set_stream(self, cuda_stream: int | None):
+        self.check(self.lib.spano_set_stream(self.h, C.c_void_p(cuda_stream or 0)))
+
+    def sync(self):
+        self.check(self.lib.spano_sync(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.spano_launch_count(self.h))
+
+    def timers_enable(self, on: bool = True):
+        self.check(self.lib.spano_timers_enable(self.h, int(on)))
+
+    def timers_reset(self):
+        self.check(self.lib.spano_timers_reset(self.h))
+
+    def timers_read(self):
+        ms = (C.c_float * 4)()
+        n = (C.c_longlong * 4)()
+        self.check(self.lib.spano_timers_read(self.h, ms, n))
+        names = ("warp", "mask", "blend", "normalise")
+        return {k: float(ms[i]) for i, k in enumerate(names)}, {k: int(n[i]) for i, k in enumerate(names)}
+
+    def fp32_peak(self, variant: int = 0) -> float:
+        v = C.c_double()
+        self.check(self.lib.spano_fp32_peak(self.h, int(variant), C.byref(v)))
+        return float(v.value)
+
+
+_default_ctx: Context | None = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+# ---------------------------------------------------------------------------------------------
+# geometry
+# ---------------------------------------------------------------------------------------------
+def adjusted_camera(K, R, w_ref: int, h_ref: int):
+    """K_adj / R as float32, the matrices projection::project hands to OpenCV
+    (principal point flipped to (w-cx, h-cy); src/math/_projection.cpp:36-49)."""
+    K = np.asarray(K, np.float64)
+    f_i = K[0, 0]
+    K_adj = np.array([[f_i, 0, w_ref - K[0, 2]], [0, f_i, h_ref - K[1, 2]], [0, 0, 1]], np.float64)
+    return K_adj.astype(np.float32), np.asarray(R, np.float64).astype(np.float32)
+
+
+def warp_roi(kind: int, focal: float, K32, R32, src_w: int, src_h: int, ctx: Context | None = None):
+    """Corner and size of the warped tile: ((tl_x, tl_y), (w, h)).  K32 is K_adj (float32).
+    Host arithmetic only: works without a context (and without a GPU)."""
+    k, r = _f9(K32), _f9(R32)
+    out = [C.c_int() for _ in range(4)]
+    lib = ctx.lib if ctx is not None else _lib.load()
+    rc = lib.spano_warp_roi(ctx.h if ctx is not None else None, int(kind), C.c_float(focal), _fp(k), _fp(r),
+                            int(src_w), int(src_h), *[C.byref(o) for o in out])
+    if rc != 0:
+        if ctx is not None:
+            ctx.check(rc)
+        raise SpanoError(rc, "spano_warp_roi failed (degenerate ROI or bad argument)")
+    return (out[0].value, out[1].value), (out[2].value, out[3].value)
+
+
+def project(kind: int, focal: float, R, K, img, gain: float = 1.0, get_mask: bool = False, ctx: Context | None = None):
+    """projection::project (+ optionally the validity mask and the 8-bit gain of the later stages).
+
+    Returns (corner(x, y), warped tile[, validity mask])."""
+    ctx = ctx or default_context()
+    img = _u8img(img, 3, "image")
+    h_ref, w_ref = img.shape[:2]
+    K32, R32 = adjusted_camera(K, R, w_ref, h_ref)
+    corner, (w, h) = warp_roi(kind, focal, K32, R32, w_ref, h_ref, ctx)
+    dst = np.empty((h, w, 3), np.uint8)
+    msk = np.empty((h, w), np.uint8) if get_mask else None
+    k, r = _f9(K32), _f9(R32)
+    ctx.check(ctx.lib.spano_warp(ctx.h, int(kind), C.c_float(focal), _fp(k), _fp(r), img.ctypes.data, w_ref, h_ref,
+                                 img.strides[0], float(gain), dst.ctypes.data, dst.strides[0],
+                                 msk.ctypes.data if get_mask else None, msk.strides[0] if get_mask else 0))
+    return (corner, dst, msk) if get_mask else (corner, dst)
+
+
+@dataclass
+class ProjData:
+    """proj::proj_data (src/math/_projection.h:15-19)."""
+    imgs: list = field(default_factory=list)
+    msks: list = field(default_factory=list)
+    corners: list = field(default_factory=list)
+
+
+def get_proj_parameters(images, R, K, con, kind: int, focal: float, get_masks: bool = True,
+                        ctx: Context | None = None) -> ProjData:
+    """proj::get_proj_parameters: warp every connected image, collect corners and validity masks."""
+    out = ProjData()
+    for i, img in enumerate(images):
+        if con[i] > 0:
+            res = project(kind, focal, R[i], K[i], img, 1.0, get_masks, ctx)
+            out.corners.append(res[0])
+            out.imgs.append(res[1])
+            if get_masks:
+                out.msks.append(res[2])
+    return out
+
+
+def create_surrounding_mask(img, erode_iters: int = 0, ctx: Context | None = None) -> np.ndarray:
+    """blnd::createSurroundingMask(img, true, 1), optionally followed by cv::erode(.., iterations)."""
+    ctx = ctx or default_context()
+    img = _u8img(img, 3, "image")
+    h, w = img.shape[:2]
+    m = np.empty((h, w), np.uint8)
+    ctx.check(ctx.lib.spano_surrounding_mask(ctx.h, img.ctypes.data, w, h, img.strides[0], int(erode_iters),
+                                             m.ctypes.data, m.strides[0]))
+    return m
+
+
+def validity_mask(img, ctx: Context | None = None) -> np.ndarray:
+    """createSurroundingMask + cv::erode(mask, Mat(), (-1,-1), 3)  (src/math/_projection.cpp:441-443)."""
+    return create_surrounding_mask(img, 3, ctx)
+
+
+def apply_gain(img, g: float, ctx: Context | None = None) -> np.ndarray:
+    """`img / g` on CV_8UC3: saturate(rint(float(v) * float(1/g)))."""
+    ctx = ctx or default_context()
+    out = np.array(_u8img(img, 3, "image"), copy=True, order="C")
+    h, w = out.shape[:2]
+    ctx.check(ctx.lib.spano_apply_gain(ctx.h, out.ctypes.data, w, h, out.strides[0], float(g)))
+    return out
+
+
+def get_pan_dimension(top_lefts, images):
+    """util::get_pan_dimension -> (width, height, min_x, min_y)."""
+    return pan_dimension(top_lefts, [(im.shape[1], im.shape[0]) for im in images])
+
+
+def pan_dimension(top_lefts, sizes):
+    """Canvas bounding box of tiles given as corners and (w, h) sizes."""
+    n = len(sizes)
+    if n == 0 or n != len(top_lefts):
+        raise SpanoError(_lib.E_INVALID, "Input consistency!")
+    tlx = np.array([c[0] for c in top_lefts], np.int32)
+    tly = np.array([c[1] for c in top_lefts], np.int32)
+    w = np.array([s[0] for s in sizes], np.int32)
+    h = np.array([s[1] for s in sizes], np.int32)
+    out = [C.c_int() for _ in range(4)]
+    rc = _lib.load().spano_pan_dimension(n, _ip(tlx), _ip(tly), _ip(w), _ip(h), *[C.byref(o) for o in out])
+    if rc != 0:
+        raise SpanoError(rc, "spano_pan_dimension failed")
+    return tuple(o.value for o in out)
+
+
+def _blend_call(images, masks, masks_orig, top_lefts, bands, sigma, out_kind, ctx):
+    ctx = ctx or default_context()
+    n = len(images)
+    if n == 0 or n != len(masks) or n != len(masks_orig) or n != len(top_lefts):
+        raise SpanoError(_lib.E_INVALID, "Input consistency!")
+    imgs = [_u8img(a, 3, f"images[{i}]") for i, a in enumerate(images)]
+    mc = [_u8img(a, 1, f"masks[{i}]") for i, a in enumerate(masks)]
+    mo = [_u8img(a, 1, f"masks_orig[{i}]") for i, a in enumerate(masks_orig)]
+    for i in range(n):
+        if mc[i].shape != imgs[i].shape[:2] or mo[i].shape != imgs[i].shape[:2]:
+            raise SpanoError(_lib.E_INVALID, f"mask {i} does not match its tile size")
+    W, H, _, _ = get_pan_dimension(top_lefts, imgs)
+    ptr = lambda arrs: (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    steps = lambda arrs: (C.c_size_t * n)(*[a.strides[0] for a in arrs])
+    tlx = np.array([c[0] for c in top_lefts], np.int32)
+    tly = np.array([c[1] for c in top_lefts], np.int32)
+    w = np.array([im.shape[1] for im in imgs], np.int32)
+    h = np.array([im.shape[0] for im in imgs], np.int32)
+    out = np.empty((H, W, 3), np.float32 if out_kind == OUT_F32 else np.uint8)
+    ctx.check(ctx.lib.spano_multiblend(ctx.h, n, ptr(imgs), steps(imgs), ptr(mc), steps(mc), ptr(mo), steps(mo),
+                                       _ip(tlx), _ip(tly), _ip(w), _ip(h), int(bands), float(sigma), out_kind,
+                                       out.ctypes.data, out.strides[0]))
+    return out
+
+
+def multi_blend(images, masks, masks_orig, top_lefts, bands: int, sigma: float, ctx: Context | None = None):
+    """blnd::multi_blend -> CV_32FC3 canvas."""
+    return _blend_call(images, masks, masks_orig, top_lefts, bands, sigma, OUT_F32, ctx)
+
+
+def blend(images, masks, masks_orig, top_lefts, bands: int, sigma: float, ctx: Context | None = None):
+    """stitch_parameters::blend with conf.blend == MULTI_BLEND -> CV_8UC3 canvas."""
+    return _blend_call(images, masks, masks_orig, top_lefts, bands, sigma, OUT_U8, ctx)
+
+
+def plan_tiles(images, R, K, kind: int, focal: float, ctx: Context | None = None):
+    """Geometry of every warped tile without warping: list of (K32, R32, (tl_x, tl_y), (w, h))."""
+    plan = []
+    for img, r, k in zip(images, R, K):
+        h_ref, w_ref = img.shape[:2]
+        K32, R32 = adjusted_camera(k, r, w_ref, h_ref)
+        corner, size = warp_roi(kind, focal, K32, R32, w_ref, h_ref, ctx)
+        plan.append((K32, R32, corner, size))
+    return plan
+
+
+def make_descs(images, plan, gains, masks_cut, ptr_of=lambda a: a.ctypes.data, step_of=lambda a: a.strides[0]):
+    """Array of spano_image_desc for spano_composite / spano_dev_composite."""
+    n = len(images)
+    descs = (ImageDesc * n)()
+    for j in range(n):
+        K32, R32, (tlx, tly), (w, h) = plan[j]
+        d = descs[j]
+        d.src_bgr = ptr_of(images[j])
+        d.src_h, d.src_w = int(images[j].shape[0]), int(images[j].shape[1])
+        d.src_step = step_of(images[j])
+        d.K[:] = [float(v) for v in np.asarray(K32, np.float32).reshape(9)]
+        d.R[:] = [float(v) for v in np.asarray(R32, np.float32).reshape(9)]
+        d.gain = float(gains[j]) if gains is not None else 1.0
+        d.mask_cut = ptr_of(masks_cut[j])
+        d.mask_cut_step = step_of(masks_cut[j])
+        d.tl_x, d.tl_y, d.w, d.h = int(tlx), int(tly), int(w), int(h)
+    return descs
+
+
+def return_full(images, R, K, kind: int, focal: float, gains, masks_cut, bands: int, sigma: float,
+                rows: tuple[int, int] | None = None, ctx: Context | None = None):
+    """stitch_parameters::return_full (MULTI_BLEND, gain optional): decoded sources + K/R + gains +
+    full-resolution mask_cut[] -> final CV_8UC3 canvas, through the fused device path.
+    `rows=(row0,row1)` restricts the result to a band of canvas rows (row-band sharding)."""
+    ctx = ctx or default_context()
+    n = len(images)
+    if n == 0 or n != len(R) or n != len(K) or n != len(masks_cut):
+        raise SpanoError(_lib.E_INVALID, "Input consistency!")
+    imgs = [_u8img(a, 3, f"images[{i}]") for i, a in enumerate(images)]
+    plan = plan_tiles(imgs, R, K, kind, focal, ctx)
+    cuts = [_u8img(a, 1, f"mask_cut[{i}]") for i, a in enumerate(masks_cut)]
+    for j in range(n):
+        w, h = plan[j][3]
+        if cuts[j].shape != (h, w):
+            raise SpanoError(_lib.E_INVALID, f"mask_cut[{j}] is {cuts[j].shape}, tile is {(h, w)}")
+    W, H, _, _ = pan_dimension([p[2] for p in plan], [p[3] for p in plan])
+    row0, row1 = rows if rows is not None else (0, H)
+    descs = make_descs(imgs, plan, gains, cuts)
+    canvas = np.empty((row1 - row0, W, 3), np.uint8)
+    ctx.check(ctx.lib.spano_composite(ctx.h, int(kind), C.c_float(focal), n, descs, int(bands), float(sigma),
+                                      int(row0), int(row1), canvas.ctypes.data, canvas.strides[0]))
+    return canvas

@@ -1,0 +1,511 @@
+// blend_kernels.cu -- the reference's multiband blend as fused separable-filter kernels (sm_100a).
+//
+// Replaces blnd::multi_blend (reference src/math/_blending.cpp:186-252), the per-pixel loops of
+// imgm::elementwiseOperation (src/math/_img_manipulation.cpp:31-84) and the x255/convertTo tail of
+// stitch_parameters::blend (src/classes/_panorama.cpp:242-249).
+//
+// What the reference computes (NOT a decimated Laplacian pyramid -- see SURVEY.md section 0.3):
+//   for band i in 0..B-1:  s_i = sqrt(2(B-i)+1)*sigma, kernel size 2*ceil(3 sigma)+1 for EVERY band
+//     for image j:         G_i = GaussianBlur(I_j, s_i),  W_i = GaussianBlur(mask_cut_j, s_i)/255
+//                          band = (i==B-1) ? I - G_i : (i>0 ? G_i - G_{i+1} : G_0)
+//                          W_i = 0 where validity mask != 255
+//                          color += band*W_i ; alpha += W_i          (in the tile's canvas ROI)
+//   out = color / clamp(alpha) / float(255/B)        [integer division]      (-> x255 -> u8)
+// BORDER_REFLECT applies at the borders of each warped TILE.
+//
+// Kernel structure: per tile, one CTA owns a 32 x BH block of tile pixels and runs four channel
+// phases (mask_cut, B, G, R).  Each phase stages the u8 channel (+ halo, reflect resolved) as
+// float in shared memory, runs the horizontal pass for ALL B sigmas at once (the symmetric
+// pair sums x[-k]+x[k] are shared by every sigma), keeps the B row-filtered planes in shared
+// memory, and runs the vertical pass from shared memory into registers (8 rows per thread, each
+// loaded value feeds up to 8 accumulators).  Band algebra, weights, validity zeroing and the
+// sum over bands happen in registers; the only HBM traffic is the u8 inputs (5 B/tile-px, halo
+// re-reads come from L2) and one float4 read-modify-write of the canvas accumulator per tile
+// pixel.  No level ever round-trips to HBM.
+//
+// This stage is bound by the FP32 FMA pipe, not by HBM (4 ch x B x 2 x 43 MACs per tile pixel
+// against ~37 B): see DESIGN.md.  Taps live in constant memory so the FMAs take them as
+// constant-bank operands.
+#include "spano_internal.h"
+#include <cmath>
+#include <cstdio>
+
+namespace {
+
+constexpr int MAXB = SPANO_MAX_BANDS;
+constexpr int MAXR = SPANO_BLUR_RADIUS_MAX;
+
+// c_taps[b][k] = tap at distance k from the centre for band b's sigma (k = 0..radius)
+__constant__ float c_taps[MAXB][MAXR + 1];
+
+struct BlendParams {
+    const uint8_t *tile;  size_t tile_step;
+    const uint8_t *cut;   size_t cut_step;
+    const uint8_t *valid; size_t valid_step;
+    int w, h;          // tile extent
+    int ty_begin, ty_end; // tile rows to produce
+    float4 *acc;       // canvas accumulator rows [row0, ...), pitch canvas_w
+    int canvas_w;
+    int ax, ay;        // tile corner relative to acc origin (canvas x, canvas y - row0)
+    int radius;
+};
+
+// cv::borderInterpolate(p, len, BORDER_REFLECT)
+__device__ __forceinline__ int reflect_idx(int p, int len)
+{
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        if (p < 0) p = -p - 1;
+        else p = len - 1 - (p - len);
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+// channel 0 = mask_cut, 1..3 = B,G,R of the tile
+__device__ __forceinline__ float load_channel(const BlendParams &P, int ch, int x, int y)
+{
+    if (ch == 0) return (float)__ldg(P.cut + (size_t)y * P.cut_step + x);
+    return (float)__ldg(P.tile + (size_t)y * P.tile_step + (size_t)x * 3 + (ch - 1));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path: radius 21 (sigma = 7, the reference default and every BASELINE config).
+// ---------------------------------------------------------------------------------------------
+constexpr int FR = 21;           // radius
+constexpr int FBW = 32;          // block width (one warp = one row of the block)
+constexpr int FINP = FBW + 2 * FR + 2;   // 76: staged row pitch (floats), multiple of 4 for LDS.128
+constexpr int FCH = 8;           // output rows per thread in the vertical pass
+
+// block height: the B row-filtered planes + the B weight planes must fit in 227 KB
+template <int B> struct FastCfg {
+    static constexpr int BH = (B <= 7) ? 64 : 32;
+    static constexpr int ROWS = BH + 2 * FR;          // staged / row-filtered rows
+    static constexpr int THREADS = FBW * (BH / FCH);  // 256 or 128
+};
+
+template <int B>
+struct FastSmem {
+    float in[FastCfg<B>::ROWS][FINP];
+    float row[B][FastCfg<B>::ROWS][FBW];
+    float wgt[B][FastCfg<B>::BH][FBW];   // W_b of the block's pixels, kept across the colour phases
+};
+
+template <int B>
+__global__ void __launch_bounds__(FastCfg<B>::THREADS, 1) blend_fast_kernel(const BlendParams P)
+{
+    constexpr int FBH = FastCfg<B>::BH, FROWS = FastCfg<B>::ROWS, FTHREADS = FastCfg<B>::THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FastSmem<B> &S = *reinterpret_cast<FastSmem<B> *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * FBW;                 // tile x of block column 0
+    const int ty0 = P.ty_begin + blockIdx.y * FBH;    // tile y of block row 0
+    const int cx = tid & 31;                          // my column in the vertical pass
+    const int cr0 = (tid >> 5) * FCH;                 // my first block row in the vertical pass
+
+    float contrib[3][FCH];
+    float wsum[FCH];
+
+    // validity of my output pixels
+    bool ok[FCH];
+#pragma unroll
+    for (int o = 0; o < FCH; ++o) {
+        const int x = tx0 + cx, y = ty0 + cr0 + o;
+        ok[o] = (x < P.w) && (y < P.ty_end);
+    }
+
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+        __syncthreads(); // previous phase's vertical pass is done with S
+        // ---- stage channel + halo as float, BORDER_REFLECT resolved against the tile ----
+        for (int i = tid; i < FROWS * (FBW + 2 * FR); i += FTHREADS) {
+            const int r = i / (FBW + 2 * FR), c = i - r * (FBW + 2 * FR);
+            const int y = reflect_idx(ty0 - FR + r, P.h);
+            const int x = reflect_idx(tx0 - FR + c, P.w);
+            S.in[r][c] = load_channel(P, ch, x, y);
+        }
+        __syncthreads();
+        // ---- horizontal pass, all sigmas at once: item = (row, group of 4 columns) ----
+#pragma unroll 1
+        for (int item = tid; item < FROWS * (FBW / 4); item += FTHREADS) {
+            const int r = item >> 3, g = item & 7;
+            float v[48];
+            const float4 *src = reinterpret_cast<const float4 *>(&S.in[r][4 * g]);
+#pragma unroll
+            for (int q = 0; q < 12; ++q) {
+                const float4 t = src[q];
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+            float out[B][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float pair[FR + 1];
+                pair[0] = v[j + FR];
+#pragma unroll
+                for (int k = 1; k <= FR; ++k) pair[k] = v[j + FR - k] + v[j + FR + k];
+#pragma unroll
+                for (int b = 0; b < B; ++b) {
+                    float a = c_taps[b][0] * pair[0];
+#pragma unroll
+                    for (int k = 1; k <= FR; ++k) a = fmaf(c_taps[b][k], pair[k], a);
+                    out[b][j] = a;
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < B; ++b)
+                *reinterpret_cast<float4 *>(&S.row[b][r][4 * g]) = make_float4(out[b][0], out[b][1], out[b][2], out[b][3]);
+        }
+        __syncthreads();
+        // ---- vertical pass from shared memory + band algebra in registers ----
+        float cur[FCH]; // G_b of the previous sigma (colour phases)
+#pragma unroll 1
+        for (int b = 0; b < B; ++b) {
+            float a[FCH];
+#pragma unroll
+            for (int o = 0; o < FCH; ++o) a[o] = 0.f;
+            const float *tp = c_taps[b];
+#pragma unroll
+            for (int i = 0; i < FCH + 2 * FR; ++i) {
+                const float val = S.row[b][cr0 + i][cx];
+#pragma unroll
+                for (int o = 0; o < FCH; ++o) {
+                    const int k = i - o; // tap index 0..42
+                    if (k >= 0 && k <= 2 * FR) a[o] = fmaf(tp[k < FR ? FR - k : k - FR], val, a[o]);
+                }
+            }
+            if (ch == 0) {
+#pragma unroll
+                for (int o = 0; o < FCH; ++o) {
+                    bool keep = false;
+                    if (ok[o]) keep = __ldg(P.valid + (size_t)(ty0 + cr0 + o) * P.valid_step + (tx0 + cx)) == 255;
+                    const float wv = keep ? a[o] * (float)(1.0 / 255.0) : 0.f;
+                    S.wgt[b][cr0 + o][cx] = wv;   // only this thread ever touches this element
+                    wsum[o] = (b == 0) ? wv : wsum[o] + wv;
+                }
+            } else {
+                float *cc = contrib[ch - 1];
+#pragma unroll
+                for (int o = 0; o < FCH; ++o) {
+                    if (b == 0) cc[o] = (B > 1) ? a[o] * S.wgt[0][cr0 + o][cx] : 0.f;
+                    else if (b >= 2) cc[o] = fmaf(cur[o] - a[o], S.wgt[b - 1][cr0 + o][cx], cc[o]); // band b-1 = G_{b-1} - G_b
+                    if (b == B - 1) {
+                        const float I = S.in[cr0 + o + FR][cx + FR];
+                        cc[o] = fmaf(I - a[o], S.wgt[B - 1][cr0 + o][cx], cc[o]);                 // band B-1 = I - G_{B-1}
+                    }
+                    cur[o] = a[o];
+                }
+            }
+        }
+    }
+    // ---- accumulate into the canvas (one float4 read-modify-write per tile pixel) ----
+#pragma unroll
+    for (int o = 0; o < FCH; ++o) {
+        if (!ok[o]) continue;
+        const int x = tx0 + cx, y = ty0 + cr0 + o;
+        float4 *q = P.acc + (size_t)(P.ay + y) * P.canvas_w + (P.ax + x);
+        float4 t = *q;
+        t.x += contrib[0][o]; t.y += contrib[1][o]; t.z += contrib[2][o]; t.w += wsum[o];
+        *q = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic path: any radius <= 32 (other sigma values).  Same arithmetic, runtime loops,
+// 32x32 block, one sigma at a time.  Also the on-device cross-check of the fast kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int GB = 32;
+constexpr int GTHREADS = 256;
+
+template <int B>
+__global__ void __launch_bounds__(GTHREADS) blend_generic_kernel(const BlendParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = P.radius;
+    const int IW = GB + 2 * R;           // staged width / height
+    const int IP = IW + 1;               // pitch
+    float *s_in = reinterpret_cast<float *>(smem_raw);   // [IW][IP]
+    float *s_tmp = s_in + (size_t)IW * IP;               // [IW][GB]
+
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * GB;
+    const int ty0 = P.ty_begin + blockIdx.y * GB;
+    const int cx = tid & 31, cy = tid >> 5; // my pixels: (cx, cy + 8 j), j = 0..3
+
+    float wgt[B][4], contrib[3][4], wsum[4], cur[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        ok[j] = (tx0 + cx < P.w) && (ty0 + cy + 8 * j < P.ty_end);
+        wsum[j] = 0.f;
+        cur[j] = 0.f;
+        contrib[0][j] = contrib[1][j] = contrib[2][j] = 0.f;
+    }
+
+    for (int ch = 0; ch < 4; ++ch) {
+        __syncthreads();
+        for (int i = tid; i < IW * IW; i += GTHREADS) {
+            const int r = i / IW, c = i - r * IW;
+            s_in[r * IP + c] = load_channel(P, ch, reflect_idx(tx0 - R + c, P.w), reflect_idx(ty0 - R + r, P.h));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            for (int i = tid; i < IW * GB; i += GTHREADS) {
+                const int r = i >> 5, c = i & 31;
+                const float *p = s_in + r * IP + c + R;
+                float a = c_taps[b][0] * p[0];
+                for (int k = 1; k <= R; ++k) a = fmaf(c_taps[b][k], p[-k] + p[k], a);
+                s_tmp[r * GB + c] = a;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ry = cy + 8 * j + R;
+                const float *p = s_tmp + ry * GB + cx;
+                float a = 0.f;
+                for (int k = -R; k <= R; ++k) a = fmaf(c_taps[b][k < 0 ? -k : k], p[k * GB], a);
+                if (ch == 0) {
+                    bool keep = false;
+                    if (ok[j]) keep = __ldg(P.valid + (size_t)(ty0 + cy + 8 * j) * P.valid_step + (tx0 + cx)) == 255;
+                    const float wv = keep ? a * (float)(1.0 / 255.0) : 0.f;
+                    wgt[b][j] = wv;
+                    wsum[j] += wv;
+                } else {
+                    float *cc = contrib[ch - 1];
+                    if (b == 0) { if (B > 1) cc[j] = a * wgt[0][j]; }
+                    else if (b >= 2) cc[j] = fmaf(cur[j] - a, wgt[b - 1][j], cc[j]);
+                    if (b == B - 1) {
+                        const float I = s_in[ry * IP + cx + R];
+                        cc[j] = fmaf(I - a, wgt[B - 1][j], cc[j]);
+                    }
+                    cur[j] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (!ok[j]) continue;
+        const int x = tx0 + cx, y = ty0 + cy + 8 * j;
+        float4 *q = P.acc + (size_t)(P.ay + y) * P.canvas_w + (P.ax + x);
+        float4 t = *q;
+        t.x += contrib[0][j]; t.y += contrib[1][j]; t.z += contrib[2][j]; t.w += wsum[j];
+        *q = t;
+    }
+}
+
+// out = color / clamp(alpha) / float(255/B)  [ -> *255 -> u8 ]
+__global__ void normalise_kernel(const float4 *acc, int canvas_w, int rows, float inv_div, int out_kind, void *out,
+                                 size_t out_step)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= canvas_w || y >= rows) return;
+    const float4 t = acc[(size_t)y * canvas_w + x];
+    float d = t.w;
+    d = copysignf(fmaxf(fabsf(d), 1e-6f), d);
+    const float s = __fdiv_rn(1.f, d);
+    const float c0 = __fmul_rn(__fmul_rn(t.x, s), inv_div);
+    const float c1 = __fmul_rn(__fmul_rn(t.y, s), inv_div);
+    const float c2 = __fmul_rn(__fmul_rn(t.z, s), inv_div);
+    if (out_kind == SPANO_OUT_F32) {
+        float *o = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(out) + (size_t)y * out_step) + 3 * (size_t)x;
+        o[0] = c0; o[1] = c1; o[2] = c2;
+    } else {
+        unsigned char *o = reinterpret_cast<unsigned char *>(out) + (size_t)y * out_step + 3 * (size_t)x;
+        o[0] = (unsigned char)min(255, max(0, __float2int_rn(__fmul_rn(c0, 255.f))));
+        o[1] = (unsigned char)min(255, max(0, __float2int_rn(__fmul_rn(c1, 255.f))));
+        o[2] = (unsigned char)min(255, max(0, __float2int_rn(__fmul_rn(c2, 255.f))));
+    }
+}
+
+// ---- FP32 pipe microbenchmark (roofline denominator of the blend kernels) ----
+template <int VARIANT>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *sink, int iters, float seed)
+{
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + (float)(threadIdx.x + i);
+    const float m = 1.0000001f * seed, c = 1e-9f;
+    for (int it = 0; it < iters; ++it) {
+        if (VARIANT == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
+        } else if (VARIANT == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], c_taps[i & 7][i], a[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                float2 d;
+                asm volatile("{ .reg .b64 ra, rb, rc, rd;\n"
+                             "  mov.b64 ra, {%2, %3};\n"
+                             "  mov.b64 rb, {%4, %4};\n"
+                             "  mov.b64 rc, {%5, %5};\n"
+                             "  fma.rn.f32x2 rd, ra, rb, rc;\n"
+                             "  mov.b64 {%0, %1}, rd; }\n"
+                             : "=f"(d.x), "=f"(d.y)
+                             : "f"(a[i]), "f"(a[i + 1]), "f"(m), "f"(c));
+                a[i] = d.x;
+                a[i + 1] = d.y;
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456f) sink[0] = s;
+}
+
+template <int B>
+int launch_fast(spano_ctx *ctx, const BlendParams &P, dim3 grid)
+{
+    static bool configured[64] = {false};
+    const size_t smem = sizeof(FastSmem<B>);
+    int dev = ctx->device & 63;
+    if (!configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(blend_fast_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return spano_fail(ctx, SPANO_E_CUDA, "cudaFuncSetAttribute(blend_fast<%d>, %zu B): %s", B, smem, cudaGetErrorString(e));
+        configured[dev] = true;
+    }
+    blend_fast_kernel<B><<<grid, FastCfg<B>::THREADS, smem, ctx->stream>>>(P);
+    return 0;
+}
+
+template <int B>
+int launch_generic(spano_ctx *ctx, const BlendParams &P, dim3 grid)
+{
+    static bool configured[64] = {false};
+    const int IW = GB + 2 * P.radius;
+    const size_t smem = ((size_t)IW * (IW + 1) + (size_t)IW * GB) * sizeof(float);
+    int dev = ctx->device & 63;
+    if (!configured[dev]) {
+        const int IWm = GB + 2 * MAXR;
+        const size_t smem_max = ((size_t)IWm * (IWm + 1) + (size_t)IWm * GB) * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(blend_generic_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e != cudaSuccess) return spano_fail(ctx, SPANO_E_CUDA, "cudaFuncSetAttribute(blend_generic<%d>): %s", B, cudaGetErrorString(e));
+        configured[dev] = true;
+    }
+    blend_generic_kernel<B><<<grid, GTHREADS, smem, ctx->stream>>>(P);
+    return 0;
+}
+
+} // namespace
+
+// Gaussian taps for every band into constant memory (cv::getGaussianKernel, see projector_host.cpp).
+int launch_blend_setup(spano_ctx *ctx, int bands, double sigma)
+{
+    if (bands < 1 || bands > MAXB) return spano_fail(ctx, SPANO_E_INVALID, "bands %d not in [1,%d]", bands, MAXB);
+    if (!(sigma > 0)) return spano_fail(ctx, SPANO_E_INVALID, "sigma must be > 0");
+    const int radius = (int)std::ceil(3 * sigma);
+    if (radius < 1 || radius > MAXR)
+        return spano_fail(ctx, SPANO_E_LIMIT, "blur radius ceil(3*sigma)=%d exceeds %d", radius, MAXR);
+    float host[MAXB][MAXR + 1] = {};
+    float full[2 * MAXR + 1];
+    const int n = 2 * radius + 1;
+    for (int i = 0; i < bands; ++i) {
+        const double sb = std::sqrt((double)(2 * (bands - i) + 1)) * sigma;
+        spano_host_gaussian_taps(n, sb, full);
+        for (int k = 0; k <= radius; ++k) host[i][k] = full[radius + k];
+    }
+    SPANO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_taps, host, sizeof(host), 0, cudaMemcpyHostToDevice, ctx->stream));
+    return radius;
+}
+
+int launch_blend_clear(spano_ctx *ctx, float4 *acc, int canvas_w, int rows)
+{
+    SPANO_CUDA(ctx, cudaMemsetAsync(acc, 0, (size_t)canvas_w * rows * sizeof(float4), ctx->stream));
+    return 0;
+}
+
+static int g_force_generic = 0;
+extern "C" void spano_debug_force_generic(int on) { g_force_generic = on; }
+
+int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius, float4 *acc, int canvas_w, int row0,
+                      int row1)
+{
+    // tile rows that fall into canvas rows [row0,row1)
+    int ty_begin = row0 - t.cy, ty_end = row1 - t.cy;
+    if (ty_begin < 0) ty_begin = 0;
+    if (ty_end > t.h) ty_end = t.h;
+    if (ty_end <= ty_begin || t.w <= 0) return 0;
+    BlendParams P;
+    P.tile = t.tile;  P.tile_step = t.tile_step;
+    P.cut = t.cut;  P.cut_step = t.cut_step;
+    P.valid = t.valid;  P.valid_step = t.valid_step;
+    P.w = t.w;  P.h = t.h;
+    P.ty_begin = ty_begin;  P.ty_end = ty_end;
+    P.acc = acc;  P.canvas_w = canvas_w;
+    P.ax = t.cx;  P.ay = t.cy - row0;
+    P.radius = radius;
+    int rc = 0;
+    const bool fast = (radius == FR) && !g_force_generic;
+    if (fast) {
+        const int fbh = bands <= 7 ? 64 : 32; // FastCfg<B>::BH
+        dim3 grid((t.w + FBW - 1) / FBW, (ty_end - ty_begin + fbh - 1) / fbh);
+        switch (bands) {
+#define CASE(B) case B: rc = launch_fast<B>(ctx, P, grid); break;
+            CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
+#undef CASE
+        default: return spano_fail(ctx, SPANO_E_INVALID, "bands %d unsupported", bands);
+        }
+    } else {
+        dim3 grid((t.w + GB - 1) / GB, (ty_end - ty_begin + GB - 1) / GB);
+        switch (bands) {
+#define CASE(B) case B: rc = launch_generic<B>(ctx, P, grid); break;
+            CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
+#undef CASE
+        default: return spano_fail(ctx, SPANO_E_INVALID, "bands %d unsupported", bands);
+        }
+    }
+    if (rc) return rc;
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return 1;
+}
+
+int launch_normalise(spano_ctx *ctx, const float4 *acc, int canvas_w, int rows, int bands, int out_kind, void *out,
+                     size_t out_step)
+{
+    if (rows <= 0 || canvas_w <= 0) return 0;
+    const float divisor = (float)(255 / bands); // integer division, as in the reference
+    const float inv_div = (float)(1.0 / (double)divisor);
+    dim3 block(256), grid((canvas_w + 255) / 256, rows);
+    normalise_kernel<<<grid, block, 0, ctx->stream>>>(acc, canvas_w, rows, inv_div, out_kind, out, out_step);
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return 1;
+}
+
+int launch_fp32_peak(spano_ctx *ctx, int variant, double *tflops)
+{
+    float *sink = nullptr;
+    int rc = spano_reserve(ctx, spano_ctx::BUF_MISC, 256, (void **)&sink);
+    if (rc) return rc;
+    int sms = 0;
+    SPANO_CUDA(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    const int iters = 20000, blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    SPANO_CUDA(ctx, cudaEventCreate(&e0));
+    SPANO_CUDA(ctx, cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        SPANO_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        if (variant == 0) fp32_peak_kernel<0><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 1.0f);
+        else if (variant == 1) fp32_peak_kernel<1><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 1.0f);
+        else fp32_peak_kernel<2><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 1.0f);
+        SPANO_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        SPANO_CUDA(ctx, cudaEventSynchronize(e1));
+        float ms = 0;
+        SPANO_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctx->launches += 4;
+    const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return 0;
+}

@@ -1,0 +1,579 @@
+// capi.cu -- C ABI of the compositing library (include/spano.h) and the host orchestration of
+// the fused path.  No exceptions cross this boundary; every entry point returns a status code.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <algorithm>
+
+#include "spano_internal.h"
+
+// ---------------------------------------------------------------------------------------------
+// context plumbing
+// ---------------------------------------------------------------------------------------------
+int spano_fail(spano_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+int spano_reserve(spano_ctx *ctx, int which, size_t bytes, void **out)
+{
+    DeviceBuffer &b = ctx->buf[which];
+    if (b.bytes < bytes) {
+        if (b.ptr) {
+            // the old buffer may still be in use by work queued on the stream
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(b.ptr);
+            b.ptr = nullptr;
+            b.bytes = 0;
+        }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&b.ptr, want);
+        if (e != cudaSuccess) {
+            b.ptr = nullptr;
+            return spano_fail(ctx, SPANO_E_NOMEM, "cudaMalloc(%zu B) failed: %s", want, cudaGetErrorString(e));
+        }
+        b.bytes = want;
+    }
+    *out = b.ptr;
+    return 0;
+}
+
+namespace {
+
+struct Guard {
+    spano_ctx *c;
+    explicit Guard(spano_ctx *ctx) : c(ctx) { c->mu.lock(); cudaSetDevice(c->device); }
+    ~Guard() { c->mu.unlock(); }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct StageTimer {
+    spano_ctx *ctx;
+    int stage;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    StageTimer(spano_ctx *c, int s) : ctx(c), stage(s)
+    {
+        if (!ctx->timers_on) return;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, ctx->stream);
+    }
+    void stop(int launches)
+    {
+        if (!ctx->timers_on) return;
+        cudaEventRecord(e1, ctx->stream);
+        ctx->pending_events.push_back({stage, {e0, e1}});
+        ctx->stage_launches[stage] += launches;
+    }
+};
+
+void drain_timers(spano_ctx *ctx)
+{
+    for (auto &p : ctx->pending_events) {
+        float ms = 0.f;
+        cudaEventSynchronize(p.second.second);
+        cudaEventElapsedTime(&ms, p.second.first, p.second.second);
+        ctx->stage_ms[p.first] += ms;
+        cudaEventDestroy(p.second.first);
+        cudaEventDestroy(p.second.second);
+    }
+    ctx->pending_events.clear();
+}
+
+int check_image_args(spano_ctx *ctx, const void *p, int w, int h, size_t step, int cn, const char *what)
+{
+    if (!p) return spano_fail(ctx, SPANO_E_INVALID, "%s: null pointer", what);
+    if (w <= 0 || h <= 0) return spano_fail(ctx, SPANO_E_INVALID, "%s: empty image %dx%d", what, w, h);
+    if (step < (size_t)w * cn) return spano_fail(ctx, SPANO_E_INVALID, "%s: step %zu < row bytes %zu", what, step, (size_t)w * cn);
+    return 0;
+}
+
+// cv::remap asserts every dimension < SHRT_MAX
+int check_remap_limits(spano_ctx *ctx, int sw, int sh, int dw, int dh)
+{
+    if (sw >= 32767 || sh >= 32767 || dw >= 32767 || dh >= 32767)
+        return spano_fail(ctx, SPANO_E_LIMIT, "remap dimension >= 32767 (src %dx%d dst %dx%d): the reference's cv::remap rejects this", sw, sh, dw, dh);
+    return 0;
+}
+
+int valid_proj(spano_ctx *ctx, int proj, float scale)
+{
+    if (proj < SPANO_SPHERICAL || proj > SPANO_STEREOGRAPHIC) return spano_fail(ctx, SPANO_E_INVALID, "unknown projection %d", proj);
+    if (!(scale > 0.f)) return spano_fail(ctx, SPANO_E_INVALID, "scale must be > 0");
+    return 0;
+}
+
+// warp + dark flags + validity mask of one full tile, all on device
+int dev_warp_tile(spano_ctx *ctx, const SpanoProjector &P, const uint8_t *d_src, int src_w, int src_h, size_t src_step,
+                  double gain, int tl_x, int tl_y, int w, int h, uint8_t *d_tile, size_t tile_step, uint8_t *d_mask,
+                  size_t mask_step)
+{
+    uint8_t *dark = nullptr;
+    size_t dark_step = 0;
+    if (d_mask) {
+        dark_step = align_up((size_t)w, 16);
+        int rc = spano_reserve(ctx, spano_ctx::BUF_DARK, dark_step * h, (void **)&dark);
+        if (rc) return rc;
+    }
+    StageTimer t0(ctx, 0);
+    int n = launch_warp(ctx, P, d_src, src_w, src_h, src_step, gain, tl_x, tl_y, w, h, 0, h, d_tile, tile_step, dark, dark_step);
+    if (n < 0) return n;
+    t0.stop(n);
+    if (d_mask) {
+        StageTimer t1(ctx, 1);
+        n = launch_valid_mask(ctx, dark, w, h, dark_step, 3, d_mask, mask_step);
+        if (n < 0) return n;
+        t1.stop(n);
+    }
+    return 0;
+}
+
+int dev_multiblend(spano_ctx *ctx, int n, const BlendTile *tiles, int canvas_w, int canvas_h, int bands, double sigma,
+                   int row0, int row1, int out_kind, void *d_out, size_t out_step)
+{
+    if (row0 < 0) row0 = 0;
+    if (row1 > canvas_h) row1 = canvas_h;
+    const int rows = row1 - row0;
+    if (rows <= 0) return 0;
+    int radius = launch_blend_setup(ctx, bands, sigma);
+    if (radius < 0) return radius;
+    float4 *acc = nullptr;
+    int rc = spano_reserve(ctx, spano_ctx::BUF_ACC, (size_t)canvas_w * rows * sizeof(float4), (void **)&acc);
+    if (rc) return rc;
+    StageTimer t2(ctx, 2);
+    rc = launch_blend_clear(ctx, acc, canvas_w, rows);
+    if (rc) return rc;
+    int launches = 0;
+    for (int j = 0; j < n; ++j) {
+        int k = launch_blend_tile(ctx, tiles[j], bands, radius, acc, canvas_w, row0, row1);
+        if (k < 0) return k;
+        launches += k;
+    }
+    t2.stop(launches);
+    StageTimer t3(ctx, 3);
+    int k = launch_normalise(ctx, acc, canvas_w, rows, bands, out_kind, d_out, out_step);
+    if (k < 0) return k;
+    t3.stop(k);
+    return 0;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------
+extern "C" int spano_version(void) { return SPANO_VERSION; }
+
+extern "C" int spano_create(spano_ctx **out, int device)
+{
+    if (!out) return SPANO_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) return SPANO_E_NODEVICE;
+    if (device < 0 || device >= count) return SPANO_E_INVALID;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SPANO_E_CUDA;
+    if (prop.major != 10) return SPANO_E_NODEVICE; // built for sm_100a only
+    spano_ctx *ctx = new (std::nothrow) spano_ctx();
+    if (!ctx) return SPANO_E_NOMEM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return SPANO_E_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return SPANO_OK;
+}
+
+extern "C" void spano_destroy(spano_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    drain_timers(ctx);
+    for (auto &b : ctx->buf)
+        if (b.ptr) cudaFree(b.ptr);
+    for (void *p : ctx->owned) cudaFree(p);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char *spano_last_error(spano_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int spano_set_stream(spano_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SPANO_OK;
+}
+
+extern "C" int spano_sync(spano_ctx *ctx)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}
+
+extern "C" long long spano_launch_count(spano_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int spano_timers_enable(spano_ctx *ctx, int on)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    ctx->timers_on = on != 0;
+    return SPANO_OK;
+}
+
+extern "C" int spano_timers_reset(spano_ctx *ctx)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    drain_timers(ctx);
+    for (int i = 0; i < 4; ++i) { ctx->stage_ms[i] = 0.f; ctx->stage_launches[i] = 0; }
+    return SPANO_OK;
+}
+
+extern "C" int spano_timers_read(spano_ctx *ctx, float ms[4], long long launches[4])
+{
+    if (!ctx || !ms) return SPANO_E_INVALID;
+    Guard g(ctx);
+    drain_timers(ctx);
+    for (int i = 0; i < 4; ++i) {
+        ms[i] = ctx->stage_ms[i];
+        if (launches) launches[i] = ctx->stage_launches[i];
+    }
+    return SPANO_OK;
+}
+
+extern "C" int spano_fp32_peak(spano_ctx *ctx, int variant, double *tflops)
+{
+    if (!ctx || !tflops) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return launch_fp32_peak(ctx, variant, tflops);
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------
+extern "C" int spano_warp_roi(spano_ctx *ctx, int proj, float scale, const float K[9], const float R[9], int src_w,
+                              int src_h, int *tl_x, int *tl_y, int *dst_w, int *dst_h)
+{
+    // pure host arithmetic: ctx may be NULL (then no error message is recorded)
+    if (!K || !R || !tl_x || !tl_y || !dst_w || !dst_h) return spano_fail(ctx, SPANO_E_INVALID, "spano_warp_roi: null argument");
+    if (int rc = valid_proj(ctx, proj, scale)) return rc;
+    if (src_w <= 0 || src_h <= 0) return spano_fail(ctx, SPANO_E_INVALID, "spano_warp_roi: empty source %dx%d", src_w, src_h);
+    SpanoProjector P;
+    spano_host_set_camera(&P, proj, scale, K, R);
+    int roi[4];
+    spano_host_roi(&P, src_w, src_h, roi);
+    *tl_x = roi[0];
+    *tl_y = roi[1];
+    // RotationWarperBase::warp: dst.create(roi.height + 1, roi.width + 1), roi = Rect(tl, br)
+    const long long w = (long long)roi[2] - roi[0] + 1, h = (long long)roi[3] - roi[1] + 1;
+    if (w <= 0 || h <= 0 || w > 0x7fffffffLL || h > 0x7fffffffLL)
+        return spano_fail(ctx, SPANO_E_LIMIT, "degenerate result ROI (%d,%d)-(%d,%d)", roi[0], roi[1], roi[2], roi[3]);
+    *dst_w = (int)w;
+    *dst_h = (int)h;
+    return SPANO_OK;
+}
+
+extern "C" int spano_pan_dimension(int n, const int *tl_x, const int *tl_y, const int *w, const int *h, int *canvas_w,
+                                   int *canvas_h, int *min_x, int *min_y)
+{
+    if (n <= 0 || !tl_x || !tl_y || !w || !h) return SPANO_E_INVALID;
+    int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
+    for (int i = 0; i < n; ++i) {
+        x0 = std::min(x0, tl_x[i]);
+        y0 = std::min(y0, tl_y[i]);
+        x1 = std::max(x1, tl_x[i] + w[i]);
+        y1 = std::max(y1, tl_y[i] + h[i]);
+    }
+    if (canvas_w) *canvas_w = x1 - x0;
+    if (canvas_h) *canvas_h = y1 - y0;
+    if (min_x) *min_x = x0;
+    if (min_y) *min_y = y0;
+    return SPANO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-pointer stage entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" int spano_dev_warp(spano_ctx *ctx, int proj, float scale, const float K[9], const float R[9],
+                              const uint8_t *src_bgr, int src_w, int src_h, size_t src_step, double gain, int tl_x,
+                              int tl_y, int dst_w, int dst_h, uint8_t *dst_bgr, size_t dst_step,
+                              uint8_t *dst_valid_mask, size_t mask_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (!K || !R) return spano_fail(ctx, SPANO_E_INVALID, "spano_dev_warp: null K/R");
+    if (int rc = valid_proj(ctx, proj, scale)) return rc;
+    if (int rc = check_image_args(ctx, src_bgr, src_w, src_h, src_step, 3, "source")) return rc;
+    if (int rc = check_image_args(ctx, dst_bgr, dst_w, dst_h, dst_step, 3, "destination")) return rc;
+    if (dst_valid_mask && mask_step < (size_t)dst_w) return spano_fail(ctx, SPANO_E_INVALID, "mask step too small");
+    if (!(gain > 0.0)) return spano_fail(ctx, SPANO_E_INVALID, "gain must be > 0");
+    if (int rc = check_remap_limits(ctx, src_w, src_h, dst_w, dst_h)) return rc;
+    SpanoProjector P;
+    spano_host_set_camera(&P, proj, scale, K, R);
+    return dev_warp_tile(ctx, P, src_bgr, src_w, src_h, src_step, gain, tl_x, tl_y, dst_w, dst_h, dst_bgr, dst_step,
+                         dst_valid_mask, mask_step);
+}
+
+extern "C" int spano_dev_multiblend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps,
+                                    const uint8_t *const *masks, const size_t *mask_steps,
+                                    const uint8_t *const *masks_orig, const size_t *orig_steps, const int *tl_x,
+                                    const int *tl_y, const int *w, const int *h, int bands, double sigma, int row0,
+                                    int row1, int out_kind, void *out, size_t out_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (n <= 0 || !tiles || !tile_steps || !masks || !mask_steps || !masks_orig || !orig_steps || !tl_x || !tl_y || !w || !h || !out)
+        return spano_fail(ctx, SPANO_E_INVALID, "spano_dev_multiblend: null/empty argument");
+    if (out_kind != SPANO_OUT_F32 && out_kind != SPANO_OUT_U8) return spano_fail(ctx, SPANO_E_INVALID, "unknown out_kind %d", out_kind);
+    int cw, chh, mx, my;
+    spano_pan_dimension(n, tl_x, tl_y, w, h, &cw, &chh, &mx, &my);
+    if (out_step < (size_t)cw * (out_kind == SPANO_OUT_F32 ? 12 : 3)) return spano_fail(ctx, SPANO_E_INVALID, "out_step too small");
+    std::vector<BlendTile> bt(n);
+    for (int j = 0; j < n; ++j) {
+        if (int rc = check_image_args(ctx, tiles[j], w[j], h[j], tile_steps[j], 3, "tile")) return rc;
+        if (int rc = check_image_args(ctx, masks[j], w[j], h[j], mask_steps[j], 1, "mask_cut")) return rc;
+        if (int rc = check_image_args(ctx, masks_orig[j], w[j], h[j], orig_steps[j], 1, "mask_orig")) return rc;
+        bt[j] = BlendTile{tiles[j], tile_steps[j], masks[j], mask_steps[j], masks_orig[j], orig_steps[j], w[j], h[j], tl_x[j] - mx, tl_y[j] - my};
+    }
+    return dev_multiblend(ctx, n, bt.data(), cw, chh, bands, sigma, row0, row1, out_kind, out, out_step);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" int spano_warp(spano_ctx *ctx, int proj, float scale, const float K[9], const float R[9],
+                          const uint8_t *src_bgr, int src_w, int src_h, size_t src_step, double gain, uint8_t *dst_bgr,
+                          size_t dst_step, uint8_t *dst_valid_mask, size_t mask_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    int tl_x, tl_y, w, h;
+    if (int rc = spano_warp_roi(ctx, proj, scale, K, R, src_w, src_h, &tl_x, &tl_y, &w, &h)) return rc;
+    Guard g(ctx);
+    if (int rc = check_image_args(ctx, src_bgr, src_w, src_h, src_step, 3, "source")) return rc;
+    if (int rc = check_image_args(ctx, dst_bgr, w, h, dst_step, 3, "destination")) return rc;
+    if (dst_valid_mask && mask_step < (size_t)w) return spano_fail(ctx, SPANO_E_INVALID, "mask step too small");
+    if (!(gain > 0.0)) return spano_fail(ctx, SPANO_E_INVALID, "gain must be > 0");
+    if (int rc = check_remap_limits(ctx, src_w, src_h, w, h)) return rc;
+    SpanoProjector P;
+    spano_host_set_camera(&P, proj, scale, K, R);
+    const size_t s_step = align_up((size_t)src_w * 3, 16), t_step = align_up((size_t)w * 3, 16), m_step = align_up((size_t)w, 16);
+    uint8_t *d_src, *d_tile, *d_mask = nullptr;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC, s_step * src_h + 16, (void **)&d_src)) return rc;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, t_step * h, (void **)&d_tile)) return rc;
+    if (dst_valid_mask)
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILEMASK, m_step * h, (void **)&d_mask)) return rc;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_src, s_step, src_bgr, src_step, (size_t)src_w * 3, src_h, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = dev_warp_tile(ctx, P, d_src, src_w, src_h, s_step, gain, tl_x, tl_y, w, h, d_tile, t_step, d_mask, m_step)) return rc;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(dst_bgr, dst_step, d_tile, t_step, (size_t)w * 3, h, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dst_valid_mask)
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(dst_valid_mask, mask_step, d_mask, m_step, (size_t)w, h, cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}
+
+extern "C" int spano_surrounding_mask(spano_ctx *ctx, const uint8_t *bgr, int w, int h, size_t step, int erode_iters,
+                                      uint8_t *mask, size_t mask_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (int rc = check_image_args(ctx, bgr, w, h, step, 3, "image")) return rc;
+    if (int rc = check_image_args(ctx, mask, w, h, mask_step, 1, "mask")) return rc;
+    const size_t t_step = align_up((size_t)w * 3, 16), m_step = align_up((size_t)w, 16);
+    uint8_t *d_img, *d_dark, *d_mask;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, t_step * h, (void **)&d_img)) return rc;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_DARK, m_step * h, (void **)&d_dark)) return rc;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILEMASK, m_step * h, (void **)&d_mask)) return rc;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_img, t_step, bgr, step, (size_t)w * 3, h, cudaMemcpyHostToDevice, ctx->stream));
+    int n = launch_dark_flags(ctx, d_img, w, h, t_step, d_dark, m_step);
+    if (n < 0) return n;
+    n = launch_valid_mask(ctx, d_dark, w, h, m_step, erode_iters, d_mask, m_step);
+    if (n < 0) return n;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(mask, mask_step, d_mask, m_step, (size_t)w, h, cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}
+
+extern "C" int spano_apply_gain(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, double gain)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (int rc = check_image_args(ctx, bgr, w, h, step, 3, "image")) return rc;
+    if (!(gain > 0.0)) return spano_fail(ctx, SPANO_E_INVALID, "gain must be > 0");
+    const size_t t_step = align_up((size_t)w * 3, 16);
+    uint8_t *d_img;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, t_step * h, (void **)&d_img)) return rc;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_img, t_step, bgr, step, (size_t)w * 3, h, cudaMemcpyHostToDevice, ctx->stream));
+    int n = launch_gain(ctx, d_img, w, h, t_step, gain);
+    if (n < 0) return n;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(bgr, step, d_img, t_step, (size_t)w * 3, h, cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}
+
+extern "C" int spano_multiblend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps,
+                                const uint8_t *const *masks, const size_t *mask_steps,
+                                const uint8_t *const *masks_orig, const size_t *orig_steps, const int *tl_x,
+                                const int *tl_y, const int *w, const int *h, int bands, double sigma, int out_kind,
+                                void *out, size_t out_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (n <= 0 || !tiles || !tile_steps || !masks || !mask_steps || !masks_orig || !orig_steps || !tl_x || !tl_y || !w || !h || !out)
+        return spano_fail(ctx, SPANO_E_INVALID, "spano_multiblend: null/empty argument (the reference throws \"Input consistency!\")");
+    if (out_kind != SPANO_OUT_F32 && out_kind != SPANO_OUT_U8) return spano_fail(ctx, SPANO_E_INVALID, "unknown out_kind %d", out_kind);
+    int cw, chh, mx, my;
+    spano_pan_dimension(n, tl_x, tl_y, w, h, &cw, &chh, &mx, &my);
+    const size_t px_bytes = out_kind == SPANO_OUT_F32 ? 12 : 3;
+    if (out_step < (size_t)cw * px_bytes) return spano_fail(ctx, SPANO_E_INVALID, "out_step too small");
+    // upload every tile + masks into one arena
+    size_t total = 0;
+    std::vector<size_t> off_t(n), off_c(n), off_v(n), st_t(n), st_m(n);
+    for (int j = 0; j < n; ++j) {
+        if (int rc = check_image_args(ctx, tiles[j], w[j], h[j], tile_steps[j], 3, "tile")) return rc;
+        if (int rc = check_image_args(ctx, masks[j], w[j], h[j], mask_steps[j], 1, "mask_cut")) return rc;
+        if (int rc = check_image_args(ctx, masks_orig[j], w[j], h[j], orig_steps[j], 1, "mask_orig")) return rc;
+        st_t[j] = align_up((size_t)w[j] * 3, 16);
+        st_m[j] = align_up((size_t)w[j], 16);
+        off_t[j] = total; total += st_t[j] * h[j];
+        off_c[j] = total; total += st_m[j] * h[j];
+        off_v[j] = total; total += st_m[j] * h[j];
+    }
+    uint8_t *arena;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, total, (void **)&arena)) return rc;
+    std::vector<BlendTile> bt(n);
+    for (int j = 0; j < n; ++j) {
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(arena + off_t[j], st_t[j], tiles[j], tile_steps[j], (size_t)w[j] * 3, h[j], cudaMemcpyHostToDevice, ctx->stream));
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(arena + off_c[j], st_m[j], masks[j], mask_steps[j], (size_t)w[j], h[j], cudaMemcpyHostToDevice, ctx->stream));
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(arena + off_v[j], st_m[j], masks_orig[j], orig_steps[j], (size_t)w[j], h[j], cudaMemcpyHostToDevice, ctx->stream));
+        bt[j] = BlendTile{arena + off_t[j], st_t[j], arena + off_c[j], st_m[j], arena + off_v[j], st_m[j], w[j], h[j], tl_x[j] - mx, tl_y[j] - my};
+    }
+    const size_t o_step = align_up((size_t)cw * px_bytes, 16);
+    uint8_t *d_out;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_CANVAS, o_step * chh, (void **)&d_out)) return rc;
+    if (int rc = dev_multiblend(ctx, n, bt.data(), cw, chh, bands, sigma, 0, chh, out_kind, d_out, o_step)) return rc;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(out, out_step, d_out, o_step, (size_t)cw * px_bytes, chh, cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused path (return_full): sources -> canvas
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *im, int bands, double sigma,
+                   int row0, int row1, uint8_t *canvas, size_t canvas_step, bool host)
+{
+    if (n <= 0 || !im || !canvas) return spano_fail(ctx, SPANO_E_INVALID, "spano_composite: null/empty argument");
+    if (int rc = valid_proj(ctx, proj, scale)) return rc;
+    std::vector<int> tlx(n), tly(n), ww(n), hh(n);
+    for (int j = 0; j < n; ++j) { tlx[j] = im[j].tl_x; tly[j] = im[j].tl_y; ww[j] = im[j].w; hh[j] = im[j].h; }
+    int cw, chh, mx, my;
+    spano_pan_dimension(n, tlx.data(), tly.data(), ww.data(), hh.data(), &cw, &chh, &mx, &my);
+    if (row0 < 0) row0 = 0;
+    if (row1 > chh) row1 = chh;
+    if (row1 <= row0) return spano_fail(ctx, SPANO_E_INVALID, "empty row band [%d,%d)", row0, row1);
+    if (canvas_step < (size_t)cw * 3) return spano_fail(ctx, SPANO_E_INVALID, "canvas_step too small");
+    int radius = (int)std::ceil(3 * sigma);
+
+    // tiles that touch canvas rows [row0 - radius, row1 + radius) take part (halo recomputed locally)
+    std::vector<int> use;
+    size_t tiles_bytes = 0, src_bytes_max = 0, cut_bytes_max = 0;
+    std::vector<size_t> off_t(n), off_v(n), st_t(n), st_m(n);
+    for (int j = 0; j < n; ++j) {
+        if (int rc = check_image_args(ctx, im[j].src_bgr, im[j].src_w, im[j].src_h, im[j].src_step, 3, "source")) return rc;
+        if (int rc = check_image_args(ctx, im[j].mask_cut, im[j].w, im[j].h, im[j].mask_cut_step, 1, "mask_cut")) return rc;
+        if (!(im[j].gain > 0.0)) return spano_fail(ctx, SPANO_E_INVALID, "gain[%d] must be > 0", j);
+        if (int rc = check_remap_limits(ctx, im[j].src_w, im[j].src_h, im[j].w, im[j].h)) return rc;
+        const int cy = im[j].tl_y - my;
+        if (cy + im[j].h <= row0 || cy >= row1) continue; // blur support never crosses tile borders (reflect)
+        use.push_back(j);
+        st_t[j] = align_up((size_t)im[j].w * 3, 16);
+        st_m[j] = align_up((size_t)im[j].w, 16);
+        off_t[j] = tiles_bytes; tiles_bytes += st_t[j] * im[j].h;
+        off_v[j] = tiles_bytes; tiles_bytes += st_m[j] * im[j].h;
+        src_bytes_max = std::max(src_bytes_max, align_up((size_t)im[j].src_w * 3, 16) * im[j].src_h + 16);
+        cut_bytes_max = std::max(cut_bytes_max, st_m[j] * im[j].h);
+    }
+    (void)radius;
+    uint8_t *arena = nullptr, *d_src = nullptr, *d_cut_all = nullptr;
+    if (!use.empty())
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, tiles_bytes, (void **)&arena)) return rc;
+    size_t cut_total = 0;
+    std::vector<size_t> off_c(n);
+    if (host) {
+        for (int j : use) { off_c[j] = cut_total; cut_total += st_m[j] * im[j].h; }
+        if (!use.empty()) {
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC, src_bytes_max, (void **)&d_src)) return rc;
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTMASK, cut_total, (void **)&d_cut_all)) return rc;
+        }
+    }
+    std::vector<BlendTile> bt;
+    for (int j : use) {
+        SpanoProjector P;
+        spano_host_set_camera(&P, proj, scale, im[j].K, im[j].R);
+        const uint8_t *src = im[j].src_bgr;
+        size_t s_step = im[j].src_step;
+        const uint8_t *cut = im[j].mask_cut;
+        size_t c_step = im[j].mask_cut_step;
+        if (host) {
+            s_step = align_up((size_t)im[j].src_w * 3, 16);
+            SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_src, s_step, im[j].src_bgr, im[j].src_step, (size_t)im[j].src_w * 3, im[j].src_h, cudaMemcpyHostToDevice, ctx->stream));
+            src = d_src;
+            c_step = st_m[j];
+            SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_cut_all + off_c[j], c_step, im[j].mask_cut, im[j].mask_cut_step, (size_t)im[j].w, im[j].h, cudaMemcpyHostToDevice, ctx->stream));
+            cut = d_cut_all + off_c[j];
+        }
+        if (int rc = dev_warp_tile(ctx, P, src, im[j].src_w, im[j].src_h, s_step, im[j].gain, im[j].tl_x, im[j].tl_y, im[j].w, im[j].h,
+                                   arena + off_t[j], st_t[j], arena + off_v[j], st_m[j]))
+            return rc;
+        bt.push_back(BlendTile{arena + off_t[j], st_t[j], cut, c_step, arena + off_v[j], st_m[j], im[j].w, im[j].h, im[j].tl_x - mx, im[j].tl_y - my});
+    }
+    uint8_t *d_canvas = canvas;
+    size_t d_step = canvas_step;
+    if (host) {
+        d_step = align_up((size_t)cw * 3, 16);
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_CANVAS, d_step * (row1 - row0), (void **)&d_canvas)) return rc;
+    }
+    if (int rc = dev_multiblend(ctx, (int)bt.size(), bt.data(), cw, chh, bands, sigma, row0, row1, SPANO_OUT_U8, d_canvas, d_step)) return rc;
+    if (host) {
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(canvas, canvas_step, d_canvas, d_step, (size_t)cw * 3, row1 - row0, cudaMemcpyDeviceToHost, ctx->stream));
+        SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SPANO_OK;
+}
+
+} // namespace
+
+extern "C" int spano_composite(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *images, int bands,
+                               double sigma, int row0, int row1, uint8_t *canvas, size_t canvas_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return composite_impl(ctx, proj, scale, n, images, bands, sigma, row0, row1, canvas, canvas_step, true);
+}
+
+extern "C" int spano_dev_composite(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *images,
+                                   int bands, double sigma, int row0, int row1, uint8_t *canvas, size_t canvas_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return composite_impl(ctx, proj, scale, n, images, bands, sigma, row0, row1, canvas, canvas_step, false);
+}

@@ -1,0 +1,87 @@
+// spano_internal.h -- shared declarations of the sm_100a compositing library (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/spano.h"
+
+#define SPANO_BLUR_RADIUS_MAX 32 /* ceil(3*sigma) supported by the blend kernels (sigma <= 10) */
+
+// Derived projector state handed to kernels (== cv::detail::ProjectorBase after setCameraParams).
+struct SpanoProjector {
+    int kind;
+    float scale;
+    float k[9], rinv[9], r_kinv[9], k_rinv[9];
+};
+
+// host, bit-exact with OpenCV (projector_host.cpp; compiled with -ffp-contract=off)
+void spano_host_set_camera(SpanoProjector *p, int kind, float scale, const float *K, const float *R);
+void spano_host_map_forward(const SpanoProjector *p, float x, float y, float *u, float *v);
+void spano_host_roi(const SpanoProjector *p, int src_w, int src_h, int roi[4]);
+// finish a ROI from float extremes found elsewhere (stereographic GPU scan + exact host refinement)
+void spano_host_gaussian_taps(int n, double sigma, float *taps);
+
+struct DeviceBuffer {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct spano_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    long long launches = 0;
+    // grow-only scratch buffers, indexed by role
+    enum { BUF_LABELS = 0, BUF_DARK, BUF_MASK0, BUF_TABLES, BUF_ACC, BUF_TILE, BUF_TILEMASK, BUF_CUTMASK, BUF_SRC,
+           BUF_CANVAS, BUF_MISC, BUF_COUNT };
+    DeviceBuffer buf[BUF_COUNT];
+    std::vector<void *> owned; // extra allocations freed at destroy / end of call
+    // timers
+    bool timers_on = false;
+    float stage_ms[4] = {0, 0, 0, 0};
+    long long stage_launches[4] = {0, 0, 0, 0};
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
+};
+
+int spano_fail(spano_ctx *ctx, int code, const char *fmt, ...);
+int spano_reserve(spano_ctx *ctx, int which, size_t bytes, void **out);
+
+#define SPANO_CUDA(ctx, call)                                                                      \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return spano_fail(ctx, SPANO_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                              __LINE__);                                                           \
+    } while (0)
+
+// ---- kernel launchers (each returns the number of kernels launched, or <0) -------------
+// warp_kernels.cu
+int launch_warp(spano_ctx *ctx, const SpanoProjector &P, const uint8_t *src, int src_w, int src_h, size_t src_step,
+                double gain, int tl_x, int tl_y, int dst_w, int dst_h, int row_begin, int row_end, uint8_t *dst,
+                size_t dst_step, uint8_t *dark, size_t dark_step);
+int launch_gain(spano_ctx *ctx, uint8_t *img, int w, int h, size_t step, double gain);
+int launch_dark_flags(spano_ctx *ctx, const uint8_t *bgr, int w, int h, size_t step, uint8_t *dark, size_t dark_step);
+// mask_kernels.cu
+int launch_valid_mask(spano_ctx *ctx, const uint8_t *dark, int w, int h, size_t dark_step, int erode_iters,
+                      uint8_t *mask, size_t mask_step);
+// blend_kernels.cu
+struct BlendTile {
+    const uint8_t *tile;   size_t tile_step;   // 8UC3, gain applied
+    const uint8_t *cut;    size_t cut_step;    // mask_cut 8UC1
+    const uint8_t *valid;  size_t valid_step;  // validity mask 8UC1
+    int w, h;                                  // full tile extent (reflect borders refer to it)
+    int cx, cy;                                // tile corner in canvas coordinates
+};
+int launch_blend_setup(spano_ctx *ctx, int bands, double sigma);
+int launch_blend_clear(spano_ctx *ctx, float4 *acc, int canvas_w, int rows);
+int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius, float4 *acc, int canvas_w, int row0,
+                      int row1);
+int launch_normalise(spano_ctx *ctx, const float4 *acc, int canvas_w, int rows, int bands, int out_kind, void *out,
+                     size_t out_step);
+int launch_fp32_peak(spano_ctx *ctx, int variant, double *tflops);

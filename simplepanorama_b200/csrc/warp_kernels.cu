@@ -1,0 +1,341 @@
+// warp_kernels.cu -- fused inverse-projection remap + bilinear sampling + dark flag + exposure gain (sm_100a).
+//
+// Replaces, per warped tile, the reference's
+//   cv::detail::{Spherical,Cylindrical,Stereographic}Warper::warp   (src/math/_projection.cpp:51,81,321)
+//     = buildMaps (projector mapBackward per destination pixel) + cv::remap(INTER_LINEAR, BORDER_CONSTANT)
+//   the gray<=1 test at the head of blnd::createSurroundingMask      (src/math/_blending.cpp:283-287)
+//   `imgs[i] / gain[i]` on CV_8UC3                                   (src/classes/_panorama.cpp:321-327)
+// in ONE pass: the float maps are never materialised, the warped tile is written once.
+//
+// Arithmetic contract (what makes the result match OpenCV):
+//   * mapBackward in float32 with IEEE mul/add/div (no FMA contraction: __fmul_rn/__fadd_rn/__fdiv_rn)
+//     and CUDA's accurate sinf/cosf/atan2f/atanf/sqrtf (<= 2 ulp; glibc's differ in the last ulp
+//     for a small fraction of arguments, which can move a sample by one 1/32-px bin).
+//   * sampling is OpenCV's 8-bit fixed point: sx = cvRound(32 x), weights (32-fy)(32-fx)*32,
+//     D = (sum + 2^14) >> 15.  Evaluated separably with exact integers:
+//     h = (32-fx) p0 + fx p1 (one dp4a per channel and row), D = ((32-fy) h_top + fy h_bot + 512) >> 10.
+//   * gray = (3735 B + 19235 G + 9798 R + 2^14) >> 15 on the UN-gained sample; dark = gray <= 1.
+//   * gain: rint(float(v) * float(1/g)) saturated (cv::Mat::convertTo with alpha).
+//
+// HBM traffic per tile pixel: 3 B source read (each source pixel is touched ~once, neighbours hit
+// L1/L2) + 3 B tile write + 1 B dark-flag write = 7 B.
+// For spherical / cylindrical the trigonometry is separable (u depends on the column, v on the
+// row): sin/cos are evaluated once per tile column / row into small tables, so the per-pixel work
+// is 9 mul/add + 2 div + the integer sampler.
+#include "spano_internal.h"
+
+namespace {
+
+constexpr float kPiF = 3.14159265358979323846f; // (float)CV_PI
+
+struct WarpParams {
+    float m[9]; // k_rinv
+    float scale;
+    int tl_x, tl_y;
+    int dst_w, dst_h;
+    int row_begin, row_end;
+    const uint8_t *src;
+    int src_w, src_h;
+    size_t src_step;
+    uint8_t *dst;
+    size_t dst_step;
+    uint8_t *dark;
+    size_t dark_step;
+    float inv_gain;
+    int apply_gain;
+    int src_aligned8; // src pointer and step are multiples of 8: 64-bit window loads allowed
+    const float *colA, *colB, *rowA, *rowB;
+};
+
+// per-column / per-row trigonometry tables
+template <int KIND>
+__global__ void warp_tables_kernel(float scale, int tl_x, int tl_y, int w, int h, float *colA, float *colB,
+                                   float *rowA, float *rowB)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < w) {
+        float u = __fdiv_rn((float)(i + tl_x), scale);
+        colA[i] = sinf(u);
+        colB[i] = cosf(u);
+    }
+    if (i < h) {
+        float v = __fdiv_rn((float)(i + tl_y), scale);
+        if (KIND == SPANO_SPHERICAL) {
+            float t = __fsub_rn(kPiF, v);
+            rowA[i] = sinf(t);
+            rowB[i] = cosf(t);
+        } else {
+            rowA[i] = v;
+            rowB[i] = 0.f;
+        }
+    }
+}
+
+// cvRound(32*v) with x86 cvtss2si semantics: INT_MIN for NaN / out of range
+__device__ __forceinline__ int fixed_coord(float v)
+{
+    float s = v * 32.f;
+    if (!(s > -2147483648.f && s < 2147483648.f)) return (int)0x80000000;
+    return __float2int_rn(s);
+}
+
+__device__ __forceinline__ int sat_short(int v) { return max(-32768, min(32767, v)); }
+
+// Bilinear sample of one destination pixel -> packed 0x00RRGGBB (un-gained).
+__device__ __forceinline__ uint32_t sample_bilinear(const WarpParams &P, float x, float y)
+{
+    const int fx = fixed_coord(x), fy = fixed_coord(y);
+    const int sx = sat_short(fx >> 5), sy = sat_short(fy >> 5);
+    const int ax = fx & 31, ay = fy & 31;
+    const uint32_t wx = (uint32_t)(32 - ax) | ((uint32_t)ax << 24); // bytes {32-ax,0,0,ax}
+    uint32_t hb[2], hg[2], hr[2];
+    if ((unsigned)sx < (unsigned)(P.src_w - 1) && (unsigned)sy < (unsigned)(P.src_h - 1)) {
+        const uint8_t *row = P.src + (size_t)sy * P.src_step;
+        const int o = 3 * sx;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            uint64_t win;
+            if (P.src_aligned8) {
+                const int a = o & ~7, sh = (o & 7) * 8;
+                uint64_t lo = __ldg(reinterpret_cast<const unsigned long long *>(row + a));
+                win = lo >> sh;
+                if (sh > 16) { // the 6 bytes cross into the next aligned word
+                    uint64_t hi = __ldg(reinterpret_cast<const unsigned long long *>(row + a + 8));
+                    win |= hi << (64 - sh);
+                }
+            } else {
+                win = 0;
+#pragma unroll
+                for (int b = 0; b < 6; ++b) win |= (uint64_t)__ldg(row + o + b) << (8 * b);
+            }
+            hb[r] = __dp4a((uint32_t)win, wx, 0u);
+            hg[r] = __dp4a((uint32_t)(win >> 8), wx, 0u);
+            hr[r] = __dp4a((uint32_t)(win >> 16), wx, 0u);
+            row += P.src_step;
+        }
+    } else {
+        // BORDER_CONSTANT(0): every tap outside the source contributes 0
+        if (sx >= P.src_w || sx + 1 < 0 || sy >= P.src_h || sy + 1 < 0) return 0u;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int yy = sy + r;
+            uint32_t p0[3] = {0, 0, 0}, p1[3] = {0, 0, 0};
+            if (yy >= 0 && yy < P.src_h) {
+                const uint8_t *row = P.src + (size_t)yy * P.src_step;
+                if (sx >= 0 && sx < P.src_w) {
+                    p0[0] = __ldg(row + 3 * sx); p0[1] = __ldg(row + 3 * sx + 1); p0[2] = __ldg(row + 3 * sx + 2);
+                }
+                if (sx + 1 >= 0 && sx + 1 < P.src_w) {
+                    p1[0] = __ldg(row + 3 * sx + 3); p1[1] = __ldg(row + 3 * sx + 4); p1[2] = __ldg(row + 3 * sx + 5);
+                }
+            }
+            hb[r] = (32 - ax) * p0[0] + ax * p1[0];
+            hg[r] = (32 - ax) * p0[1] + ax * p1[1];
+            hr[r] = (32 - ax) * p0[2] + ax * p1[2];
+        }
+    }
+    const uint32_t wy0 = 32 - ay, wy1 = ay;
+    const uint32_t B = (wy0 * hb[0] + wy1 * hb[1] + 512u) >> 10;
+    const uint32_t G = (wy0 * hg[0] + wy1 * hg[1] + 512u) >> 10;
+    const uint32_t R = (wy0 * hr[0] + wy1 * hr[1] + 512u) >> 10;
+    return B | (G << 8) | (R << 16);
+}
+
+__device__ __forceinline__ uint32_t is_dark(uint32_t bgr)
+{
+    const uint32_t B = bgr & 255u, G = (bgr >> 8) & 255u, R = (bgr >> 16) & 255u;
+    const uint32_t gray = (3735u * B + 19235u * G + 9798u * R + (1u << 14)) >> 15;
+    return gray <= 1u ? 1u : 0u;
+}
+
+__device__ __forceinline__ uint32_t gain_u8(uint32_t v, float a)
+{
+    int r = __float2int_rn(__fmul_rn((float)v, a));
+    return (uint32_t)min(255, max(0, r));
+}
+
+__device__ __forceinline__ uint32_t gain_bgr(uint32_t bgr, float a)
+{
+    return gain_u8(bgr & 255u, a) | (gain_u8((bgr >> 8) & 255u, a) << 8) | (gain_u8((bgr >> 16) & 255u, a) << 16);
+}
+
+// mapBackward, OpenCV expression order, no contraction.
+template <int KIND>
+__device__ __forceinline__ void map_backward(const WarpParams &P, int u_i, int v_i, float &x, float &y)
+{
+    float x_, y_, z_;
+    if (KIND == SPANO_SPHERICAL) {
+        const float sinv = __ldg(P.rowA + v_i), cosv = __ldg(P.rowB + v_i);
+        x_ = __fmul_rn(sinv, __ldg(P.colA + u_i));
+        y_ = cosv;
+        z_ = __fmul_rn(sinv, __ldg(P.colB + u_i));
+    } else if (KIND == SPANO_CYLINDRICAL) {
+        x_ = __ldg(P.colA + u_i);
+        y_ = __ldg(P.rowA + v_i);
+        z_ = __ldg(P.colB + u_i);
+    } else {
+        const float u = __fdiv_rn((float)(u_i + P.tl_x), P.scale);
+        const float v = __fdiv_rn((float)(v_i + P.tl_y), P.scale);
+        const float az = atan2f(v, u);
+        const float r = sqrtf(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)));
+        const float pol = __fmul_rn(2.f, atanf(__fdiv_rn(1.f, r)));
+        const float t = __fsub_rn(kPiF, pol);
+        const float sinv = sinf(t);
+        x_ = __fmul_rn(sinv, sinf(az));
+        y_ = cosf(t);
+        z_ = __fmul_rn(sinv, cosf(az));
+    }
+    const float *m = P.m;
+    x = __fadd_rn(__fadd_rn(__fmul_rn(m[0], x_), __fmul_rn(m[1], y_)), __fmul_rn(m[2], z_));
+    y = __fadd_rn(__fadd_rn(__fmul_rn(m[3], x_), __fmul_rn(m[4], y_)), __fmul_rn(m[5], z_));
+    const float z = __fadd_rn(__fadd_rn(__fmul_rn(m[6], x_), __fmul_rn(m[7], y_)), __fmul_rn(m[8], z_));
+    if (z > 0.f) {
+        x = __fdiv_rn(x, z);
+        y = __fdiv_rn(y, z);
+    } else {
+        x = y = -1.f;
+    }
+}
+
+constexpr int WARP_PX_PER_THREAD = 4;
+constexpr int WARP_BLOCK_X = 32, WARP_BLOCK_Y = 8;
+
+template <int KIND>
+__global__ void __launch_bounds__(WARP_BLOCK_X *WARP_BLOCK_Y) warp_kernel(const WarpParams P)
+{
+    const int x0 = (blockIdx.x * WARP_BLOCK_X + threadIdx.x) * WARP_PX_PER_THREAD;
+    const int v = P.row_begin + blockIdx.y * WARP_BLOCK_Y + threadIdx.y;
+    if (x0 >= P.dst_w || v >= P.row_end) return;
+
+    uint32_t px[WARP_PX_PER_THREAD];
+    uint32_t dark = 0;
+#pragma unroll
+    for (int i = 0; i < WARP_PX_PER_THREAD; ++i) {
+        const int u = x0 + i;
+        uint32_t s = 0, d = 1;
+        if (u < P.dst_w) {
+            float x, y;
+            map_backward<KIND>(P, u, v, x, y);
+            s = sample_bilinear(P, x, y);
+            d = is_dark(s);
+            if (P.apply_gain) s = gain_bgr(s, P.inv_gain);
+        }
+        px[i] = s;
+        dark |= d << (8 * i);
+    }
+    uint8_t *drow = P.dst + (size_t)v * P.dst_step + (size_t)x0 * 3;
+    const bool full = x0 + WARP_PX_PER_THREAD <= P.dst_w;
+    if (full && (((uintptr_t)drow) & 3) == 0) {
+        // 4 px = 12 B = three 32-bit words; a warp writes 384 contiguous bytes
+        uint32_t *q = reinterpret_cast<uint32_t *>(drow);
+        q[0] = px[0] | (px[1] << 24);
+        q[1] = (px[1] >> 8) | (px[2] << 16);
+        q[2] = (px[2] >> 16) | (px[3] << 8);
+    } else {
+        for (int i = 0; i < WARP_PX_PER_THREAD && x0 + i < P.dst_w; ++i) {
+            drow[3 * i] = (uint8_t)px[i];
+            drow[3 * i + 1] = (uint8_t)(px[i] >> 8);
+            drow[3 * i + 2] = (uint8_t)(px[i] >> 16);
+        }
+    }
+    if (P.dark) {
+        uint8_t *krow = P.dark + (size_t)v * P.dark_step + x0;
+        if (full && (((uintptr_t)krow) & 3) == 0) *reinterpret_cast<uint32_t *>(krow) = dark;
+        else
+            for (int i = 0; i < WARP_PX_PER_THREAD && x0 + i < P.dst_w; ++i) krow[i] = (uint8_t)(dark >> (8 * i));
+    }
+}
+
+__global__ void gain_kernel(uint8_t *img, int w3, int h, size_t step, float a)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w3 || y >= h) return;
+    uint8_t *p = img + (size_t)y * step + x;
+    *p = (uint8_t)gain_u8(*p, a);
+}
+
+__global__ void dark_flags_kernel(const uint8_t *bgr, int w, int h, size_t step, uint8_t *dark, size_t dark_step)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t *p = bgr + (size_t)y * step + (size_t)x * 3;
+    const uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
+    dark[(size_t)y * dark_step + x] = (uint8_t)is_dark(v);
+}
+
+} // namespace
+
+int launch_warp(spano_ctx *ctx, const SpanoProjector &proj, const uint8_t *src, int src_w, int src_h, size_t src_step,
+                double gain, int tl_x, int tl_y, int dst_w, int dst_h, int row_begin, int row_end, uint8_t *dst,
+                size_t dst_step, uint8_t *dark, size_t dark_step)
+{
+    if (row_end <= row_begin) return 0;
+    int launches = 0;
+    float *tables = nullptr;
+    const size_t tab_floats = 2 * (size_t)dst_w + 2 * (size_t)dst_h;
+    int rc = spano_reserve(ctx, spano_ctx::BUF_TABLES, tab_floats * sizeof(float), (void **)&tables);
+    if (rc) return rc;
+    WarpParams P;
+    for (int i = 0; i < 9; ++i) P.m[i] = proj.k_rinv[i];
+    P.scale = proj.scale;
+    P.tl_x = tl_x;  P.tl_y = tl_y;
+    P.dst_w = dst_w;  P.dst_h = dst_h;
+    P.row_begin = row_begin;  P.row_end = row_end;
+    P.src = src;  P.src_w = src_w;  P.src_h = src_h;  P.src_step = src_step;
+    P.dst = dst;  P.dst_step = dst_step;
+    P.dark = dark;  P.dark_step = dark_step;
+    P.inv_gain = (float)(1.0 / gain);
+    P.apply_gain = (gain != 1.0);
+    P.src_aligned8 = ((((uintptr_t)src) | src_step) & 7) == 0;
+    P.colA = tables;
+    P.colB = tables + dst_w;
+    P.rowA = tables + 2 * (size_t)dst_w;
+    P.rowB = tables + 2 * (size_t)dst_w + dst_h;
+
+    if (proj.kind != SPANO_STEREOGRAPHIC) {
+        const int n = dst_w > dst_h ? dst_w : dst_h;
+        const int tb = 256;
+        if (proj.kind == SPANO_SPHERICAL)
+            warp_tables_kernel<SPANO_SPHERICAL><<<(n + tb - 1) / tb, tb, 0, ctx->stream>>>(
+                proj.scale, tl_x, tl_y, dst_w, dst_h, tables, tables + dst_w, tables + 2 * (size_t)dst_w,
+                tables + 2 * (size_t)dst_w + dst_h);
+        else
+            warp_tables_kernel<SPANO_CYLINDRICAL><<<(n + tb - 1) / tb, tb, 0, ctx->stream>>>(
+                proj.scale, tl_x, tl_y, dst_w, dst_h, tables, tables + dst_w, tables + 2 * (size_t)dst_w,
+                tables + 2 * (size_t)dst_w + dst_h);
+        ++launches;
+    }
+    dim3 block(WARP_BLOCK_X, WARP_BLOCK_Y);
+    dim3 grid((dst_w + WARP_BLOCK_X * WARP_PX_PER_THREAD - 1) / (WARP_BLOCK_X * WARP_PX_PER_THREAD),
+              (row_end - row_begin + WARP_BLOCK_Y - 1) / WARP_BLOCK_Y);
+    switch (proj.kind) {
+    case SPANO_SPHERICAL: warp_kernel<SPANO_SPHERICAL><<<grid, block, 0, ctx->stream>>>(P); break;
+    case SPANO_CYLINDRICAL: warp_kernel<SPANO_CYLINDRICAL><<<grid, block, 0, ctx->stream>>>(P); break;
+    default: warp_kernel<SPANO_STEREOGRAPHIC><<<grid, block, 0, ctx->stream>>>(P); break;
+    }
+    ++launches;
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += launches;
+    return launches;
+}
+
+int launch_gain(spano_ctx *ctx, uint8_t *img, int w, int h, size_t step, double gain)
+{
+    if (gain == 1.0 || w <= 0 || h <= 0) return 0;
+    dim3 block(256), grid((3 * w + 255) / 256, h);
+    gain_kernel<<<grid, block, 0, ctx->stream>>>(img, 3 * w, h, step, (float)(1.0 / gain));
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return 1;
+}
+
+int launch_dark_flags(spano_ctx *ctx, const uint8_t *bgr, int w, int h, size_t step, uint8_t *dark, size_t dark_step)
+{
+    dim3 block(256), grid((w + 255) / 256, h);
+    dark_flags_kernel<<<grid, block, 0, ctx->stream>>>(bgr, w, h, step, dark, dark_step);
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return 1;
+}
