@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- composited output Mpx/s of the warp + gain + multiband path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            our arm (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...   the reference's CPU path (cv2), host cores
+
+One "step" = one full pass of the hot path over the synthetic image set: every source image is
+warped (inverse projection + fixed-point bilinear + gain), its validity mask is built, all tiles are
+multiband-blended and the canvas is normalised to 8 bit.  At N > 1 the canvas is cut into row bands
+(one per GPU) and the finished 8-bit bands are gathered to rank 0 inside the timed region.
+
+`value`  : canvas Mpx / step time with sources, K/R, gains and mask_cut already resident in HBM.
+`e2e`    : the same through the host-buffer C-ABI call a user makes (spano_composite): pinned host
+           sources + masks copied H2D and the 8-bit canvas copied D2H inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "composited output Mpx/s (warp+gain+multiband)"
+UNIT = "Mpx/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--scale", type=float, default=1.0, help="debug: shrink the workload (not a valid bench number)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU time budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.stop = threading.Event()
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------
+# workload
+# ----------------------------------------------------------------------------------------------
+def build_workload(args):
+    from simplepanorama_b200 import api, synth
+    cfg = synth.config(args.workload, args.scale)
+    K, R, gains = synth.cameras(cfg)
+    images = synth.make_images(cfg, gains)
+    plan = api.plan_tiles(images, R, K, cfg.kind, cfg.focal)   # host geometry only
+    corners = [p[2] for p in plan]
+    sizes = [p[3] for p in plan]
+    cuts = synth.seam_masks(corners, sizes)
+    W, H, mx, my = api.pan_dimension(corners, sizes)
+    T = sum(w * h for w, h in sizes)
+    return dict(cfg=cfg, K=K, R=R, gains=gains, images=images, plan=plan, corners=corners, sizes=sizes, cuts=cuts,
+                W=W, H=H, min_y=my, T=T)
+
+
+def config_json(wl, args, world):
+    cfg = wl["cfg"]
+    return {"workload": f"{cfg.name}: {cfg.description}", "images": cfg.n, "image_size": [cfg.width, cfg.height],
+            "projection": ["spherical", "cylindrical", "stereographic"][cfg.kind], "focal": cfg.focal, "bands": cfg.bands,
+            "sigma": cfg.sigma, "canvas": [wl["W"], wl["H"]], "tile_mpx": round(wl["T"] / 1e6, 1),
+            "sharding": f"row-bands x{world}" if world > 1 else "single GPU",
+            "l2": "inputs larger than L2 (sources+masks > 2 GB vs 126 MB)", "scale": args.scale}
+
+
+# ----------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle/cv2_ref.py) on a bounded sample
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_sample(wl, seconds: float, steps: int = 1, warmup: int = 0):
+    """Times the reference's CPU implementation (same OpenCV kernels, all host threads) on a bounded
+    sample of the workload: image 0 cropped to a horizontal strip whose height is calibrated so that
+    one pass costs about `seconds`.  Returns (canvas-equivalent Mpx/s, description, ms per step)."""
+    import cv2
+    from oracle import cv2_ref
+    cfg = wl["cfg"]
+    cores = os.cpu_count() or 1
+    cv2.setNumThreads(cores)
+
+    def run(rows):
+        y0 = (cfg.height - rows) // 2
+        img = np.ascontiguousarray(wl["images"][0][y0:y0 + rows])
+        K = wl["K"][0].copy(); K[1, 2] = rows / 2.0
+        t0 = time.perf_counter()
+        corner, tile = cv2_ref.project(cfg.kind, cfg.focal, wl["R"][0], K, img)
+        msk = cv2_ref.validity_mask(tile)
+        tile = cv2_ref.apply_gain(tile, wl["gains"][0])
+        cut = np.full(tile.shape[:2], 255, np.uint8)
+        out = cv2_ref.blend_to_u8(cv2_ref.multi_blend([tile], [cut], [msk], [corner], cfg.bands, cfg.sigma))
+        return time.perf_counter() - t0, tile.shape[0] * tile.shape[1], out
+
+    pilot_rows = max(64, min(cfg.height, 256))
+    t, px, _ = run(pilot_rows)
+    rows = int(max(pilot_rows, min(cfg.height, pilot_rows * seconds / max(t, 1e-3))))
+    times = []
+    for i in range(warmup + steps):
+        t, px, _ = run(rows)
+        if i >= warmup:
+            times.append(t)
+    t = float(np.mean(times))
+    tile_mpx_s = px / t / 1e6
+    canvas_mpx_s = tile_mpx_s * (wl["W"] * wl["H"]) / wl["T"]   # whole job: T tile-px for C canvas-px
+    desc = (f"image 0 of {cfg.n}, central {rows}-row strip ({px / 1e6:.2f} tile-Mpx): warp+mask+gain+{cfg.bands}-band "
+            f"multi_blend+convert via cv2 {cv2.__version__}, {cores} threads; scaled to the whole job by tile pixels "
+            f"(T={wl['T'] / 1e6:.0f} Mpx for C={wl['W'] * wl['H'] / 1e6:.0f} canvas-Mpx)")
+    return canvas_mpx_s, desc, t * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = build_workload(args)
+    budget = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    v, desc, ms, cores = cpu_reference_sample(wl, budget, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_json(wl, args, 1),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as tdist
+    from simplepanorama_b200 import api, dist as sdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: simplepanorama_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        tdist.init_process_group("nccl", device_id=dev)
+
+    wl = build_workload(args)
+    cfg = wl["cfg"]
+    ctx = api.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    bands = sdist.plan_row_bands(list(zip(wl["corners"], wl["sizes"])), world, wl["min_y"], wl["H"])
+    row0, row1 = bands[rank]
+
+    # host (pinned) and device copies of the inputs
+    h_img = [torch.from_numpy(a).pin_memory() for a in wl["images"]]
+    h_cut = [torch.from_numpy(a).pin_memory() for a in wl["cuts"]]
+    d_img = [t.to(dev, non_blocking=True) for t in h_img]
+    d_cut = [t.to(dev, non_blocking=True) for t in h_cut]
+    d_canvas = torch.empty((max(1, row1 - row0), wl["W"], 3), dtype=torch.uint8, device=dev)
+    h_canvas = torch.empty((max(1, row1 - row0), wl["W"], 3), dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+    ptr = lambda t: t.data_ptr()
+    step_of = lambda t: t.stride(0)
+    descs_dev = api.make_descs(d_img, wl["plan"], wl["gains"], d_cut, ptr, step_of)
+    descs_host = api.make_descs(h_img, wl["plan"], wl["gains"], h_cut, ptr, step_of)
+    lib = ctx.lib
+    import ctypes as C
+
+    def step_dev():
+        if row1 > row0:
+            ctx.check(lib.spano_dev_composite(ctx.h, cfg.kind, C.c_float(cfg.focal), cfg.n, descs_dev, cfg.bands, cfg.sigma,
+                                              row0, row1, d_canvas.data_ptr(), d_canvas.stride(0)))
+        if world > 1:
+            return sdist.gather_bands(d_canvas[: row1 - row0], bands, wl["W"], rank, world)
+        return d_canvas
+
+    def step_host():
+        if row1 > row0:
+            ctx.check(lib.spano_composite(ctx.h, cfg.kind, C.c_float(cfg.focal), cfg.n, descs_host, cfg.bands, cfg.sigma,
+                                          row0, row1, h_canvas.data_ptr(), h_canvas.stride(0)))
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, with_timers=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if with_timers:
+            ctx.timers_enable(True)
+            ctx.timers_reset()
+        l0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        stage = None
+        if with_timers:
+            stage = ctx.timers_read()
+            ctx.timers_enable(False)
+        launches = ctx.launch_count - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, stage
+
+    canvas_mpx = wl["W"] * wl["H"] / 1e6
+    with ClockSampler(local) as clk:
+        ms, launches, stage = timed(step_dev, args.steps, args.warmup, with_timers=True)
+    clocks = clk.summary()
+    value = canvas_mpx / (ms * 1e-3)
+
+    # roofline of the dominant kernel (the blend) and of the warp kernel, from the live stage timers
+    stage_ms, stage_n = stage
+    my_T = 0   # tile pixels this rank blended / warped
+    for (tlx, tly), (w, h) in zip(wl["corners"], wl["sizes"]):
+        cy = tly - wl["min_y"]
+        a, b = max(row0, cy), min(row1, cy + h)
+        if b > a:
+            my_T += w * (b - a)
+    warp_T = sum(w * h for ((tlx, tly), (w, h)) in zip(wl["corners"], wl["sizes"])
+                 if (tly - wl["min_y"]) < row1 and (tly - wl["min_y"] + h) > row0)
+    fp32_peak = max(ctx.fp32_peak(0), ctx.fp32_peak(1), ctx.fp32_peak(2))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    blend_s = stage_ms["blend"] * 1e-3 / args.steps
+    warp_s = stage_ms["warp"] * 1e-3 / args.steps
+    blend_flops = 688.0 * cfg.bands * my_T            # 4 ch x B sigmas x 2 passes x 43 MACs per tile pixel
+    n_blend = max(1, stage_n["blend"] // args.steps)
+    n_warp = max(1, stage_n["warp"] // args.steps)
+    roofline = {
+        "kernel": f"blend_fast_kernel<{cfg.bands}>", "bound": "fp32",
+        "achieved": blend_flops / blend_s / 1e12 if blend_s > 0 else None, "peak": fp32_peak, "unit": "TFLOP/s",
+        "frac": (blend_flops / blend_s / 1e12 / fp32_peak) if blend_s > 0 else None, "traffic": None,
+        "peak_source": "FFMA microbenchmark run by this bench (MEASURED_PEAKS.json has no fp32 entry)",
+        "launches_per_step": n_blend, "avg_launch_ms": blend_s * 1e3 / n_blend,
+        "algorithmic_flop_per_tile_px": 688 * cfg.bands,
+        "hbm": {"achieved": (37.0 * my_T) / blend_s / 1e9 if blend_s > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                "bytes_per_tile_px": 37, "note": "5 B u8 inputs + 32 B float4 accumulator read-modify-write; not the binding roof"},
+    }
+    roofline_warp = {
+        "kernel": "warp_kernel", "bound": "hbm", "achieved": 7.0 * warp_T / warp_s / 1e9 if warp_s > 0 else None,
+        "peak": hbm_peak, "unit": "GB/s", "frac": (7.0 * warp_T / warp_s / 1e9 / hbm_peak) if warp_s > 0 else None,
+        "traffic": None, "peak_source": hbm_src, "launches_per_step": n_warp, "avg_launch_ms": warp_s * 1e3 / n_warp,
+        "algorithmic_bytes_per_tile_px": 7,
+    }
+
+    e2e = None
+    if not args.no_e2e:
+        ms_e, _, _ = timed(step_host, max(1, min(args.steps, 3)), 1)
+        h2d = sum(a.numel() for a in h_img) + sum(a.numel() for a in h_cut)
+        d2h = (row1 - row0) * wl["W"] * 3
+        e2e = {"value": canvas_mpx / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": ms_e, "api": "spano_composite (host buffers, pinned)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, desc, cms, cores = cpu_reference_sample(wl, args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config_json(wl, args, world), "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu,
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+                "tile_mpx_per_s": wl["T"] / 1e6 / (ms * 1e-3)}
+        print(json.dumps(line))
+    if world > 1:
+        tdist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -96,6 +96,16 @@ int spano_warp(spano_ctx *ctx, int proj, float scale, const float K[9], const fl
                int src_w, int src_h, size_t src_step, double gain, uint8_t *dst_bgr, size_t dst_step,
                uint8_t *dst_valid_mask, size_t mask_step);
 
+/* The two halves of the warp on their own (HOST buffers), for unit parity and for callers that
+ * use them directly: cv::detail::RotationWarperBase::buildMaps (float maps of a w x h tile whose
+ * corner is (tl_x, tl_y)) and cv::remap(src, dst, xmap, ymap, INTER_LINEAR, BORDER_CONSTANT)
+ * with OpenCV's 8-bit fixed-point sampler (the reference calls cv::remap itself at
+ * src/math/_projection.cpp:278).                                                         */
+int spano_build_maps(spano_ctx *ctx, int proj, float scale, const float K[9], const float R[9], int tl_x, int tl_y,
+                     int w, int h, float *xmap, float *ymap);
+int spano_remap(spano_ctx *ctx, const uint8_t *src_bgr, int src_w, int src_h, size_t src_step, const float *xmap,
+                const float *ymap, int dst_w, int dst_h, uint8_t *dst_bgr, size_t dst_step);
+
 /* a4 alone: blnd::createSurroundingMask(img,true,1) followed by `erode_iters` 3x3 erosions. */
 int spano_surrounding_mask(spano_ctx *ctx, const uint8_t *bgr, int w, int h, size_t step, int erode_iters,
                            uint8_t *mask, size_t mask_step);

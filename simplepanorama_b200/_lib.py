@@ -43,6 +43,8 @@ SYMBOLS = {
     "spano_pan_dimension": (C.c_int, [C.c_int, c_intp, c_intp, c_intp, c_intp, c_intp, c_intp, c_intp, c_intp]),
     "spano_warp": (C.c_int, [C.c_void_p, C.c_int, C.c_float, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
                              C.c_double, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "spano_build_maps": (C.c_int, [C.c_void_p, C.c_int, C.c_float, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "spano_remap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_surrounding_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_apply_gain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double]),
     "spano_multiblend": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_u8pp, c_sizep, c_u8pp, c_sizep, c_intp, c_intp,

@@ -172,6 +172,33 @@ def project(kind: int, focal: float, R, K, img, gain: float = 1.0, get_mask: boo
     return (corner, dst, msk) if get_mask else (corner, dst)
 
 
+def build_maps(kind: int, focal: float, K32, R32, corner, size, ctx: Context | None = None):
+    """cv::detail::RotationWarperBase::buildMaps -> (xmap, ymap) float32 of a (w, h) tile at `corner`."""
+    ctx = ctx or default_context()
+    w, h = size
+    xm = np.empty((h, w), np.float32)
+    ym = np.empty((h, w), np.float32)
+    k, r = _f9(K32), _f9(R32)
+    ctx.check(ctx.lib.spano_build_maps(ctx.h, int(kind), C.c_float(focal), _fp(k), _fp(r), int(corner[0]), int(corner[1]),
+                                       int(w), int(h), xm.ctypes.data, ym.ctypes.data))
+    return xm, ym
+
+
+def remap(img, xmap, ymap, ctx: Context | None = None) -> np.ndarray:
+    """cv::remap(img, xmap, ymap, INTER_LINEAR, BORDER_CONSTANT) on CV_8UC3."""
+    ctx = ctx or default_context()
+    img = _u8img(img, 3, "image")
+    xm = np.ascontiguousarray(xmap, np.float32)
+    ym = np.ascontiguousarray(ymap, np.float32)
+    if xm.ndim != 2 or xm.shape != ym.shape or xm.size == 0:
+        raise SpanoError(_lib.E_INVALID, "maps must be equal-sized non-empty 2-D float32 arrays")
+    h, w = xm.shape
+    dst = np.empty((h, w, 3), np.uint8)
+    ctx.check(ctx.lib.spano_remap(ctx.h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], xm.ctypes.data,
+                                  ym.ctypes.data, w, h, dst.ctypes.data, dst.strides[0]))
+    return dst
+
+
 @dataclass
 class ProjData:
     """proj::proj_data (src/math/_projection.h:15-19)."""

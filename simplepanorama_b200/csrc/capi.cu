@@ -388,6 +388,52 @@ extern "C" int spano_warp(spano_ctx *ctx, int proj, float scale, const float K[9
     return SPANO_OK;
 }
 
+extern "C" int spano_build_maps(spano_ctx *ctx, int proj, float scale, const float K[9], const float R[9], int tl_x,
+                                int tl_y, int w, int h, float *xmap, float *ymap)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (!K || !R || !xmap || !ymap) return spano_fail(ctx, SPANO_E_INVALID, "spano_build_maps: null argument");
+    if (int rc = valid_proj(ctx, proj, scale)) return rc;
+    if (w <= 0 || h <= 0) return spano_fail(ctx, SPANO_E_INVALID, "spano_build_maps: empty map %dx%d", w, h);
+    SpanoProjector P;
+    spano_host_set_camera(&P, proj, scale, K, R);
+    float *d_maps;
+    const size_t n = (size_t)w * h;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_MISC, 2 * n * sizeof(float), (void **)&d_maps)) return rc;
+    int k = launch_warp(ctx, P, nullptr, 1, 1, 0, 1.0, tl_x, tl_y, w, h, 0, h, nullptr, 0, nullptr, 0, d_maps, d_maps + n);
+    if (k < 0) return k;
+    SPANO_CUDA(ctx, cudaMemcpyAsync(xmap, d_maps, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaMemcpyAsync(ymap, d_maps + n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}
+
+extern "C" int spano_remap(spano_ctx *ctx, const uint8_t *src_bgr, int src_w, int src_h, size_t src_step,
+                           const float *xmap, const float *ymap, int dst_w, int dst_h, uint8_t *dst_bgr, size_t dst_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (!xmap || !ymap) return spano_fail(ctx, SPANO_E_INVALID, "spano_remap: null map");
+    if (int rc = check_image_args(ctx, src_bgr, src_w, src_h, src_step, 3, "source")) return rc;
+    if (int rc = check_image_args(ctx, dst_bgr, dst_w, dst_h, dst_step, 3, "destination")) return rc;
+    if (int rc = check_remap_limits(ctx, src_w, src_h, dst_w, dst_h)) return rc;
+    const size_t s_step = align_up((size_t)src_w * 3, 16), t_step = align_up((size_t)dst_w * 3, 16), n = (size_t)dst_w * dst_h;
+    uint8_t *d_src, *d_tile;
+    float *d_maps;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC, s_step * src_h + 16, (void **)&d_src)) return rc;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, t_step * dst_h, (void **)&d_tile)) return rc;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_MISC, 2 * n * sizeof(float), (void **)&d_maps)) return rc;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_src, s_step, src_bgr, src_step, (size_t)src_w * 3, src_h, cudaMemcpyHostToDevice, ctx->stream));
+    SPANO_CUDA(ctx, cudaMemcpyAsync(d_maps, xmap, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    SPANO_CUDA(ctx, cudaMemcpyAsync(d_maps + n, ymap, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    int k = launch_remap(ctx, d_src, src_w, src_h, s_step, d_maps, d_maps + n, dst_w, dst_h, d_tile, t_step);
+    if (k < 0) return k;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(dst_bgr, dst_step, d_tile, t_step, (size_t)dst_w * 3, dst_h, cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}
+
 extern "C" int spano_surrounding_mask(spano_ctx *ctx, const uint8_t *bgr, int w, int h, size_t step, int erode_iters,
                                       uint8_t *mask, size_t mask_step)
 {

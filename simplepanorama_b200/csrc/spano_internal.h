@@ -64,7 +64,9 @@ int spano_reserve(spano_ctx *ctx, int which, size_t bytes, void **out);
 // warp_kernels.cu
 int launch_warp(spano_ctx *ctx, const SpanoProjector &P, const uint8_t *src, int src_w, int src_h, size_t src_step,
                 double gain, int tl_x, int tl_y, int dst_w, int dst_h, int row_begin, int row_end, uint8_t *dst,
-                size_t dst_step, uint8_t *dark, size_t dark_step);
+                size_t dst_step, uint8_t *dark, size_t dark_step, float *xmap = nullptr, float *ymap = nullptr);
+int launch_remap(spano_ctx *ctx, const uint8_t *src, int src_w, int src_h, size_t src_step, const float *xmap,
+                 const float *ymap, int dst_w, int dst_h, uint8_t *dst, size_t dst_step);
 int launch_gain(spano_ctx *ctx, uint8_t *img, int w, int h, size_t step, double gain);
 int launch_dark_flags(spano_ctx *ctx, const uint8_t *bgr, int w, int h, size_t step, uint8_t *dark, size_t dark_step);
 // mask_kernels.cu

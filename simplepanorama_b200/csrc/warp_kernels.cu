@@ -246,6 +246,30 @@ __global__ void __launch_bounds__(WARP_BLOCK_X *WARP_BLOCK_Y) warp_kernel(const 
     }
 }
 
+// buildMaps alone (float maps, as cv::detail::RotationWarperBase::buildMaps returns them)
+template <int KIND>
+__global__ void build_maps_kernel(const WarpParams P, float *xmap, float *ymap)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (u >= P.dst_w || v >= P.dst_h) return;
+    float x, y;
+    map_backward<KIND>(P, u, v, x, y);
+    xmap[(size_t)v * P.dst_w + u] = x;
+    ymap[(size_t)v * P.dst_w + u] = y;
+}
+
+// cv::remap(INTER_LINEAR, BORDER_CONSTANT) on explicit float maps
+__global__ void remap_kernel(const WarpParams P, const float *xmap, const float *ymap)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (u >= P.dst_w || v >= P.dst_h) return;
+    const uint32_t s = sample_bilinear(P, xmap[(size_t)v * P.dst_w + u], ymap[(size_t)v * P.dst_w + u]);
+    uint8_t *d = P.dst + (size_t)v * P.dst_step + (size_t)u * 3;
+    d[0] = (uint8_t)s; d[1] = (uint8_t)(s >> 8); d[2] = (uint8_t)(s >> 16);
+}
+
 __global__ void gain_kernel(uint8_t *img, int w3, int h, size_t step, float a)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,9 +291,24 @@ __global__ void dark_flags_kernel(const uint8_t *bgr, int w, int h, size_t step,
 
 } // namespace
 
+int launch_remap(spano_ctx *ctx, const uint8_t *src, int src_w, int src_h, size_t src_step, const float *xmap,
+                 const float *ymap, int dst_w, int dst_h, uint8_t *dst, size_t dst_step)
+{
+    WarpParams P = {};
+    P.dst_w = dst_w;  P.dst_h = dst_h;
+    P.src = src;  P.src_w = src_w;  P.src_h = src_h;  P.src_step = src_step;
+    P.dst = dst;  P.dst_step = dst_step;
+    P.src_aligned8 = ((((uintptr_t)src) | src_step) & 7) == 0;
+    dim3 block(256), grid((dst_w + 255) / 256, dst_h);
+    remap_kernel<<<grid, block, 0, ctx->stream>>>(P, xmap, ymap);
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return 1;
+}
+
 int launch_warp(spano_ctx *ctx, const SpanoProjector &proj, const uint8_t *src, int src_w, int src_h, size_t src_step,
                 double gain, int tl_x, int tl_y, int dst_w, int dst_h, int row_begin, int row_end, uint8_t *dst,
-                size_t dst_step, uint8_t *dark, size_t dark_step)
+                size_t dst_step, uint8_t *dark, size_t dark_step, float *xmap, float *ymap)
 {
     if (row_end <= row_begin) return 0;
     int launches = 0;
@@ -306,6 +345,18 @@ int launch_warp(spano_ctx *ctx, const SpanoProjector &proj, const uint8_t *src, 
                 proj.scale, tl_x, tl_y, dst_w, dst_h, tables, tables + dst_w, tables + 2 * (size_t)dst_w,
                 tables + 2 * (size_t)dst_w + dst_h);
         ++launches;
+    }
+    if (xmap) { // maps only
+        dim3 mb(256), mg((dst_w + 255) / 256, dst_h);
+        switch (proj.kind) {
+        case SPANO_SPHERICAL: build_maps_kernel<SPANO_SPHERICAL><<<mg, mb, 0, ctx->stream>>>(P, xmap, ymap); break;
+        case SPANO_CYLINDRICAL: build_maps_kernel<SPANO_CYLINDRICAL><<<mg, mb, 0, ctx->stream>>>(P, xmap, ymap); break;
+        default: build_maps_kernel<SPANO_STEREOGRAPHIC><<<mg, mb, 0, ctx->stream>>>(P, xmap, ymap); break;
+        }
+        ++launches;
+        SPANO_CUDA(ctx, cudaGetLastError());
+        ctx->launches += launches;
+        return launches;
     }
     dim3 block(WARP_BLOCK_X, WARP_BLOCK_Y);
     dim3 grid((dst_w + WARP_BLOCK_X * WARP_PX_PER_THREAD - 1) / (WARP_BLOCK_X * WARP_PX_PER_THREAD),
