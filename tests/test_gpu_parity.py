@@ -93,11 +93,17 @@ def test_warp_vs_oracle_band_limited(ctx, oracle, name, scale):
         img = synth.make_image(cfg, j, gains[j])
         K32, R32 = api.adjusted_camera(K[j], R[j], cfg.width, cfg.height)
         tl_o, tile_o = oracle.warp(cfg.kind, np.float32(cfg.focal), K32, R32, img)
-        corner, tile, mask = api.project(cfg.kind, cfg.focal, R[j], K[j], img, gains[j], True, ctx)
+        corner, tile, mask = api.project(cfg.kind, cfg.focal, R[j], K[j], img, 1.0, True, ctx)
         assert corner == tl_o
-        ref = oracle.apply_gain(tile_o, gains[j])
-        assert np.abs(tile.astype(int) - ref.astype(int)).max() <= U8_TOL
+        diff = np.abs(tile.astype(int) - tile_o.astype(int))
+        assert diff.max() <= U8_TOL, (diff.max(), (diff > 0).mean())
+        assert (diff > 0).mean() <= 5 * BIN_SLIP_FRAC
         assert np.array_equal(mask, oracle.surrounding_mask(tile_o, 3))
+        # the fused gain is exactly the 8-bit gain applied to the un-gained warp (a 1-LSB bin slip can
+        # grow to 2 LSB after a gain of 1/0.8, in the reference as well: compare like with like)
+        _, gained, mask2 = api.project(cfg.kind, cfg.focal, R[j], K[j], img, gains[j], True, ctx)
+        assert np.array_equal(gained, oracle.apply_gain(tile, gains[j]))
+        assert np.array_equal(mask2, mask)
 
 
 # ------------------------------------------------------------------ a4 / a6: masks and gain
