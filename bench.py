@@ -97,11 +97,13 @@ def build_workload(args):
     from simplepanorama_b200 import api, synth
     cfg = synth.config(args.workload, args.scale)
     K, R, gains = synth.cameras(cfg)
-    images = synth.make_images(cfg, gains)
-    plan = api.plan_tiles(images, R, K, cfg.kind, cfg.focal)   # host geometry only
-    corners = [p[2] for p in plan]
-    sizes = [p[3] for p in plan]
-    cuts = synth.seam_masks(corners, sizes)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:   # numpy releases the GIL
+        images = list(ex.map(lambda j: synth.make_image(cfg, j, gains[j]), range(cfg.n)))
+        plan = api.plan_tiles(images, R, K, cfg.kind, cfg.focal)   # host geometry only
+        corners = [p[2] for p in plan]
+        sizes = [p[3] for p in plan]
+        cuts = list(ex.map(lambda j: synth.seam_masks(corners, sizes, only=j), range(cfg.n)))
     W, H, mx, my = api.pan_dimension(corners, sizes)
     T = sum(w * h for w, h in sizes)
     return dict(cfg=cfg, K=K, R=R, gains=gains, images=images, plan=plan, corners=corners, sizes=sizes, cuts=cuts,
@@ -195,15 +197,20 @@ def run_ours(args):
     wl = build_workload(args)
     cfg = wl["cfg"]
     ctx = api.Context(local)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream shared by torch and the library, so that torch.cuda.Event
+    # brackets exactly the kernels the library launches (the legacy default stream has handle 0,
+    # which spano_set_stream reads as "use the context's own stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     bands = sdist.plan_row_bands(list(zip(wl["corners"], wl["sizes"])), world, wl["min_y"], wl["H"])
     row0, row1 = bands[rank]
 
     # host (pinned) and device copies of the inputs
-    h_img = [torch.from_numpy(a).pin_memory() for a in wl["images"]]
-    h_cut = [torch.from_numpy(a).pin_memory() for a in wl["cuts"]]
+    h_img = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in wl["images"]]
+    h_cut = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in wl["cuts"]]
     d_img = [t.to(dev, non_blocking=True) for t in h_img]
     d_cut = [t.to(dev, non_blocking=True) for t in h_cut]
     d_canvas = torch.empty((max(1, row1 - row0), wl["W"], 3), dtype=torch.uint8, device=dev)

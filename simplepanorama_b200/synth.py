@@ -111,7 +111,7 @@ def make_images(cfg: Config, gains, noise: int = 0):
     return [make_image(cfg, j, gains[j], noise) for j in range(cfg.n)]
 
 
-def seam_masks(corners, sizes, soft: int = 8):
+def seam_masks(corners, sizes, soft: int = 8, only: int | None = None):
     """Soft-edged 0..255 seam masks (uint8, one per tile): pixel p of tile j is 255 when j's
     centre is the nearest among the tiles whose rectangle contains p (a Voronoi seam), computed on
     a coarse grid and bilinearly up-sampled to tile size like the reference's preview->full resize."""
@@ -121,7 +121,7 @@ def seam_masks(corners, sizes, soft: int = 8):
     x0 = np.array([c[0] for c in corners]); y0 = np.array([c[1] for c in corners])
     x1 = x0 + np.array([s[0] for s in sizes]); y1 = y0 + np.array([s[1] for s in sizes])
     out = []
-    for j in range(n):
+    for j in (range(n) if only is None else [only]):
         w, h = sizes[j]
         gw, gh = max(2, w // soft + 1), max(2, h // soft + 1)
         gx = corners[j][0] + (np.arange(gw) + 0.5) * (w / gw)
@@ -136,7 +136,7 @@ def seam_masks(corners, sizes, soft: int = 8):
             di = (GX - cx[i]) ** 2 + (GY - cy[i]) ** 2
             keep &= ~(inside & ((di < dj) | ((di == dj) & (i < j))))
         out.append(_upsample_u8(keep.astype(np.float32) * 255.0, w, h))
-    return out
+    return out if only is None else out[0]
 
 
 def _upsample_u8(coarse: np.ndarray, w: int, h: int) -> np.ndarray:
@@ -149,4 +149,4 @@ def _upsample_u8(coarse: np.ndarray, w: int, h: int) -> np.ndarray:
     rows0 = coarse[iy][:, ix] * (1 - ax) + coarse[iy][:, ix + 1] * ax
     rows1 = coarse[iy + 1][:, ix] * (1 - ax) + coarse[iy + 1][:, ix + 1] * ax
     v = rows0 * (1 - ay)[:, None] + rows1 * ay[:, None]
-    return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(np.clip(np.rint(v), 0, 255).astype(np.uint8))
