@@ -210,6 +210,8 @@ __global__ void __launch_bounds__(FastCfg<B>::THREADS, 1) blend_fast_kernel(cons
     }
 }
 
+#include "blend_march.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // Generic path: any radius <= 32 (other sigma values).  Same arithmetic, runtime loops,
 // 32x32 block, one sigma at a time.  Also the on-device cross-check of the fast kernel.
@@ -375,6 +377,43 @@ int launch_fast(spano_ctx *ctx, const BlendParams &P, dim3 grid)
 }
 
 template <int B>
+int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
+{
+    constexpr int SW = (B <= 6) ? 32 : 16;
+    using C = march::Cfg<B, SW>;
+    static bool configured[64] = {false};
+    int dev = ctx->device & 63;
+    if (!configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(march::blend_march_kernel<B, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return spano_fail(ctx, SPANO_E_CUDA, "cudaFuncSetAttribute(blend_march<%d>, %zu B): %s", B, C::SMEM, cudaGetErrorString(e));
+        configured[dev] = true;
+    }
+    march::Params P;
+    P.tile = Q.tile;  P.tile_step = Q.tile_step;
+    P.cut = Q.cut;  P.cut_step = Q.cut_step;
+    P.valid = Q.valid;  P.valid_step = Q.valid_step;
+    P.w = Q.w;  P.h = Q.h;
+    P.ty_begin = Q.ty_begin;  P.ty_end = Q.ty_end;
+    P.acc = Q.acc;  P.canvas_w = Q.canvas_w;  P.ax = Q.ax;  P.ay = Q.ay;
+    // segment height: minimise waves x (rows per CTA + the ~21 row-equivalents the prologue costs)
+    const int rows = Q.ty_end - Q.ty_begin, strips = (Q.w + SW - 1) / SW;
+    int best_seg = (rows + 7) / 8 * 8;
+    double best_cost = 1e30;
+    for (int nseg = 1; nseg <= 64; ++nseg) {
+        int seg = ((rows + nseg - 1) / nseg + 7) / 8 * 8;
+        if (seg < 64 && nseg > 1) break;
+        int n = (rows + seg - 1) / seg;
+        double waves = std::ceil((double)strips * n / sms);
+        double cost = waves * (seg + 40.0);
+        if (cost < best_cost) { best_cost = cost; best_seg = seg; }
+    }
+    P.seg_rows = best_seg;
+    dim3 grid(strips, (rows + best_seg - 1) / best_seg);
+    march::blend_march_kernel<B, SW><<<grid, march::THREADS, C::SMEM, ctx->stream>>>(P);
+    return 0;
+}
+
+template <int B>
 int launch_generic(spano_ctx *ctx, const BlendParams &P, dim3 grid)
 {
     static bool configured[64] = {false};
@@ -420,6 +459,7 @@ int launch_blend_clear(spano_ctx *ctx, float4 *acc, int canvas_w, int rows)
     return 0;
 }
 
+// debug / cross-check switch: 0 = default (marching kernel), 1 = generic-radius kernel, 2 = block-tiled kernel
 static int g_force_generic = 0;
 extern "C" void spano_debug_force_generic(int on) { g_force_generic = on; }
 
@@ -441,8 +481,17 @@ int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius,
     P.ax = t.cx;  P.ay = t.cy - row0;
     P.radius = radius;
     int rc = 0;
-    const bool fast = (radius == FR) && !g_force_generic;
-    if (fast) {
+    const bool fast = (radius == FR) && g_force_generic != 1;
+    if (fast && g_force_generic == 0) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        switch (bands) {
+#define CASE(B) case B: rc = launch_march<B>(ctx, P, sms); break;
+            CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
+#undef CASE
+        default: return spano_fail(ctx, SPANO_E_INVALID, "bands %d unsupported", bands);
+        }
+    } else if (fast) {
         const int fbh = bands <= 7 ? 64 : 32; // FastCfg<B>::BH
         dim3 grid((t.w + FBW - 1) / FBW, (ty_end - ty_begin + fbh - 1) / fbh);
         switch (bands) {

@@ -1,0 +1,301 @@
+// blend_march.cuh -- marching-strip multiband blend kernel (sm_100a), radius 21 (sigma = 7).
+//
+// Same arithmetic as the block-tiled kernel in blend_kernels.cu (see the header there for what the
+// reference's blnd::multi_blend computes, src/math/_blending.cpp:186-252); different schedule:
+//
+//   one CTA (256 threads, 1 CTA per SM) owns a strip of SW tile columns and marches down a segment
+//   of tile rows 8 rows at a time.  The horizontally filtered rows of ALL 4 channels x B sigmas live
+//   in a 56-row (7 chunks of 8) circular buffer in shared memory, so every input row is filtered
+//   horizontally exactly once: no halo recomputation in y.  In x only loads are redundant (the
+//   21-px halo is staged, not filtered).
+//
+//   Every thread runs the same schedule per 8-row step s (2 CTA barriers):
+//     A | stage: raw chunk s+7 (prefetched last step) -> shared; prefetch chunk s+8; early-issue the
+//       | global loads of the combine of step s-1 (validity, centre pixel, canvas accumulator)
+//       | vertical pass of step s: thread = (sigma group, channel, column); per sigma 50 LDS feed
+//       |   8 accumulators each (344 FFMA); taps are compile-time constant-bank operands
+//       | combine of step s-1: weights, validity zeroing, band algebra, one float4 RMW of the canvas
+//     B | publish the vertical results of step s to shared (G)
+//       | horizontal pass of chunk s+7 for all B sigmas at once (shared pair sums) -> circular buffer
+//   Per tile pixel: 4*(21 + 22B) + 4*43B FMA-pipe instructions (B = 6: 1644), 37 B of HBM traffic.
+#pragma once
+
+namespace march {
+
+constexpr int R = 21;              // blur radius
+constexpr int STEP = 8;            // rows per step == rows per chunk
+constexpr int NCHUNK = 7;          // chunks in the circular buffer (50 rows live = 6.25 chunks)
+constexpr int NBUF = NCHUNK * STEP; // 56 rows
+constexpr int THREADS = 256;
+
+template <int B, int SW>
+struct Cfg {
+    static constexpr int PLANES = 4 * B;                       // plane = b * 4 + channel
+    static constexpr int PLANE_STRIDE = NBUF * SW + (SW == 16 ? 16 : 0); // floats; pad keeps half-warps on distinct banks
+    static constexpr int NC = SW + 2 * R;                      // staged columns
+    static constexpr int RAW_PITCH = (SW == 32) ? 76 : 80;     // floats, multiple of 4 (LDS.128)
+    static constexpr int GROUPS = SW / 4;                      // 4-column groups per row
+    static constexpr int ROW_ITEMS = STEP * 4 * GROUPS;        // horizontal-pass items per chunk (<= THREADS)
+    static constexpr int STAGE_ELEMS = STEP * NC * 4;          // raw elements per chunk
+    static constexpr int PRE = (STAGE_ELEMS + THREADS - 1) / THREADS; // prefetch registers per thread
+    static constexpr int NG = THREADS / (4 * SW);              // sigma groups in the vertical pass
+    static constexpr int HB = (B + NG - 1) / NG;               // sigmas per group
+    static constexpr int NPX = STEP * SW;                      // pixels per step (<= THREADS)
+    static constexpr size_t SMEM = sizeof(float) * ((size_t)PLANES * PLANE_STRIDE + (size_t)PLANES * STEP * SW + 4 * STEP * RAW_PITCH) +
+                                   sizeof(int) * NC;
+};
+
+struct Params {
+    const uint8_t *tile;  size_t tile_step;
+    const uint8_t *cut;   size_t cut_step;
+    const uint8_t *valid; size_t valid_step;
+    int w, h;               // tile extent
+    int ty_begin, ty_end;   // tile rows to produce
+    int seg_rows;           // rows per CTA segment (multiple of STEP)
+    float4 *acc;
+    int canvas_w;
+    int ax, ay;
+};
+
+__device__ __forceinline__ int reflect_idx(int p, int len)
+{
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        if (p < 0) p = -p - 1;
+        else p = len - 1 - (p - len);
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+// raw element e of the chunk whose first row is tile row yrow0: (ch, i, c), c fastest
+template <int B, int SW>
+__device__ __forceinline__ float fetch_raw(const Params &P, const int *xtab, int e, int yrow0)
+{
+    using C = Cfg<B, SW>;
+    const int c = e % C::NC;
+    const int t = e / C::NC;
+    const int i = t & (STEP - 1), ch = t >> 3;
+    const int y = reflect_idx(yrow0 + i, P.h);
+    const int x = xtab[c];
+    if (ch == 0) return (float)__ldg(P.cut + (size_t)y * P.cut_step + x);
+    return (float)__ldg(P.tile + (size_t)y * P.tile_step + (size_t)x * 3 + (ch - 1));
+}
+
+// horizontal pass of one item (row i of channel ch, 4 columns) of the staged chunk -> circular buffer slot
+template <int B, int SW>
+__device__ __forceinline__ void row_pass_item(const float *raw, float *rowbuf, int item, int slot_row0)
+{
+    using C = Cfg<B, SW>;
+    const int g = item % C::GROUPS;
+    const int rc = item / C::GROUPS;
+    const int i = rc & (STEP - 1), ch = rc >> 3;
+    float v[48];
+    const float4 *src = reinterpret_cast<const float4 *>(raw + (ch * STEP + i) * C::RAW_PITCH + 4 * g);
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+        const float4 s = src[q];
+        v[4 * q] = s.x; v[4 * q + 1] = s.y; v[4 * q + 2] = s.z; v[4 * q + 3] = s.w;
+    }
+    float out[B][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float pair[R + 1];
+        pair[0] = v[j + R];
+#pragma unroll
+        for (int k = 1; k <= R; ++k) pair[k] = v[j + R - k] + v[j + R + k];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            float a = c_taps[b][0] * pair[0];
+#pragma unroll
+            for (int k = 1; k <= R; ++k) a = fmaf(c_taps[b][k], pair[k], a);
+            out[b][j] = a;
+        }
+    }
+    float *dst = rowbuf + (size_t)ch * C::PLANE_STRIDE + (slot_row0 + i) * SW + 4 * g;
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+        *reinterpret_cast<float4 *>(dst + (size_t)(b * 4) * C::PLANE_STRIDE) = make_float4(out[b][0], out[b][1], out[b][2], out[b][3]);
+}
+
+// vertical pass of one sigma (compile-time b): 50 rows of one plane column -> 8 outputs
+template <int B, int SW, int BIDX>
+__device__ __forceinline__ void vertical_one(const float *col /* plane + x */, int chunk0, float (&res)[STEP])
+{
+#pragma unroll
+    for (int o = 0; o < STEP; ++o) res[o] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+        int slot = chunk0 + c;
+        if (slot >= NCHUNK) slot -= NCHUNK;
+        const float *p = col + slot * STEP * SW;
+#pragma unroll
+        for (int j = 0; j < STEP; ++j) {
+            const int i = c * STEP + j;                 // relative row 0..55 (only 0..49 are used)
+            if (i < STEP + 2 * R) {
+                const float val = p[j * SW];
+#pragma unroll
+                for (int o = 0; o < STEP; ++o) {
+                    const int d = i - o;                // tap index 0..42
+                    if (d >= 0 && d <= 2 * R) res[o] = fmaf(c_taps[BIDX][d < R ? R - d : d - R], val, res[o]);
+                }
+            }
+        }
+    }
+}
+
+template <int B, int SW, int GRP>
+__device__ __forceinline__ void vertical_group(const float *rowbuf, int ch, int x, int chunk0, float (&res)[Cfg<B, SW>::HB][STEP])
+{
+    using C = Cfg<B, SW>;
+#pragma unroll
+    for (int k = 0; k < C::HB; ++k) {
+        const int b = GRP * C::HB + k;
+        if (b < B) {
+            const float *col = rowbuf + (size_t)(b * 4 + ch) * C::PLANE_STRIDE + x;
+            // BIDX must be a compile-time constant: dispatch on k (unrolled) via a small switch
+            switch (k) {
+            case 0: vertical_one<B, SW, (GRP * C::HB + 0 < B ? GRP * C::HB + 0 : 0)>(col, chunk0, res[k]); break;
+            case 1: vertical_one<B, SW, (GRP * C::HB + 1 < B ? GRP * C::HB + 1 : 0)>(col, chunk0, res[k]); break;
+            case 2: vertical_one<B, SW, (GRP * C::HB + 2 < B ? GRP * C::HB + 2 : 0)>(col, chunk0, res[k]); break;
+            case 3: vertical_one<B, SW, (GRP * C::HB + 3 < B ? GRP * C::HB + 3 : 0)>(col, chunk0, res[k]); break;
+            default: vertical_one<B, SW, (GRP * C::HB + 4 < B ? GRP * C::HB + 4 : 0)>(col, chunk0, res[k]); break;
+            }
+        }
+    }
+}
+
+template <int B, int SW>
+__global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
+{
+    using C = Cfg<B, SW>;
+    static_assert(C::ROW_ITEMS <= THREADS && C::NPX <= THREADS && C::HB <= 5, "thread mapping");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *rowbuf = reinterpret_cast<float *>(smem_raw);                  // [PLANES][PLANE_STRIDE]
+    float *G = rowbuf + (size_t)C::PLANES * C::PLANE_STRIDE;              // [PLANES][STEP][SW]
+    float *raw = G + (size_t)C::PLANES * STEP * SW;                       // [4][STEP][RAW_PITCH]
+    int *xtab = reinterpret_cast<int *>(raw + 4 * STEP * C::RAW_PITCH);   // [NC] reflected tile x of staged column c
+
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * SW;
+    const int y0 = P.ty_begin + blockIdx.y * P.seg_rows;
+    const int y1 = min(P.ty_end, y0 + P.seg_rows);
+    const int nsteps = (y1 - y0 + STEP - 1) / STEP;
+    const int ybase = y0 - R;   // tile row of relative row 0
+
+    // vertical-pass role
+    const int vx = tid % SW, vch = (tid / SW) & 3, vg = tid / (4 * SW);
+    // combine role
+    const int po = tid / SW, px = tid % SW;
+
+    for (int c = tid; c < C::NC; c += THREADS) xtab[c] = reflect_idx(tx0 - R + c, P.w);
+
+    // ---------------- prologue: chunks 0..6 (relative rows 0..55) through the horizontal pass -------------
+#pragma unroll 1
+    for (int q = 0; q < NCHUNK; ++q) {
+        __syncthreads();
+        for (int e = tid; e < C::STAGE_ELEMS; e += THREADS)
+            raw[(size_t)(e / C::NC) * C::RAW_PITCH + (e % C::NC)] = fetch_raw<B, SW>(P, xtab, e, ybase + q * STEP);
+        __syncthreads();
+        if (tid < C::ROW_ITEMS) row_pass_item<B, SW>(raw, rowbuf, tid, q * STEP);
+    }
+
+    // prefetch registers: chunk 7 (consumed in step 0)
+    float pre[C::PRE];
+#pragma unroll
+    for (int k = 0; k < C::PRE; ++k) {
+        const int e = tid + k * THREADS;
+        pre[k] = (e < C::STAGE_ELEMS && nsteps > 1) ? fetch_raw<B, SW>(P, xtab, e, ybase + NCHUNK * STEP) : 0.f;
+    }
+
+    float res[C::HB][STEP];
+    int chunk0 = 0;                                        // circular slot of chunk s
+
+#pragma unroll 1
+    for (int s = 0; s <= nsteps; ++s) {
+        __syncthreads();                                   // A: chunk s..s+6 filtered, G(s-1) published, raw free
+        const bool more_rows = s + 1 < nsteps;             // chunk s+7 is needed by step s+1
+        if (more_rows) {
+#pragma unroll
+            for (int k = 0; k < C::PRE; ++k) {
+                const int e = tid + k * THREADS;
+                if (e < C::STAGE_ELEMS) raw[(size_t)(e / C::NC) * C::RAW_PITCH + (e % C::NC)] = pre[k];
+            }
+            if (s + 2 < nsteps) {
+#pragma unroll
+                for (int k = 0; k < C::PRE; ++k) {
+                    const int e = tid + k * THREADS;
+                    pre[k] = (e < C::STAGE_ELEMS) ? fetch_raw<B, SW>(P, xtab, e, ybase + (s + 1 + NCHUNK) * STEP) : 0.f;
+                }
+            }
+        }
+        // early loads for the combine of step s-1
+        const int cty = y0 + (s - 1) * STEP + po, ctx_ = tx0 + px;
+        const bool cdo = (s > 0) && (tid < C::NPX) && (ctx_ < P.w) && (cty < y1);
+        bool keep = false;
+        float I0 = 0.f, I1 = 0.f, I2 = 0.f;
+        float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 *accp = nullptr;
+        if (cdo) {
+            keep = __ldg(P.valid + (size_t)cty * P.valid_step + ctx_) == 255;
+            const uint8_t *pp = P.tile + (size_t)cty * P.tile_step + (size_t)ctx_ * 3;
+            I0 = (float)__ldg(pp); I1 = (float)__ldg(pp + 1); I2 = (float)__ldg(pp + 2);
+            accp = P.acc + (size_t)(P.ay + cty) * P.canvas_w + (P.ax + ctx_);
+            accv = *accp;
+        }
+        // ---- vertical pass of step s ----
+        if (s < nsteps) {
+            if constexpr (C::NG == 2) {
+                if (vg == 0) vertical_group<B, SW, 0>(rowbuf, vch, vx, chunk0, res);
+                else vertical_group<B, SW, 1>(rowbuf, vch, vx, chunk0, res);
+            } else {
+                static_assert(C::NG == 4, "sigma groups");
+                switch (vg) {
+                case 0: vertical_group<B, SW, 0>(rowbuf, vch, vx, chunk0, res); break;
+                case 1: vertical_group<B, SW, 1>(rowbuf, vch, vx, chunk0, res); break;
+                case 2: vertical_group<B, SW, 2>(rowbuf, vch, vx, chunk0, res); break;
+                default: vertical_group<B, SW, 3>(rowbuf, vch, vx, chunk0, res); break;
+                }
+            }
+        }
+        // ---- combine of step s-1 ----
+        if (cdo) {
+            const float *g = G + po * SW + px;              // + plane * STEP * SW
+            float wsum = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, wprev = 0.f;
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const float *gb = g + (size_t)(b * 4) * STEP * SW;
+                const float wv = keep ? gb[0] * (float)(1.0 / 255.0) : 0.f;
+                const float g0 = gb[STEP * SW], g1 = gb[2 * STEP * SW], g2 = gb[3 * STEP * SW];
+                wsum += wv;
+                if (b == 0) {
+                    if (B > 1) { c0 = g0 * wv; c1 = g1 * wv; c2 = g2 * wv; }
+                } else if (b >= 2) {                        // band b-1 = G_{b-1} - G_b
+                    c0 = fmaf(p0 - g0, wprev, c0); c1 = fmaf(p1 - g1, wprev, c1); c2 = fmaf(p2 - g2, wprev, c2);
+                }
+                if (b == B - 1) {                           // band B-1 = I - G_{B-1}
+                    c0 = fmaf(I0 - g0, wv, c0); c1 = fmaf(I1 - g1, wv, c1); c2 = fmaf(I2 - g2, wv, c2);
+                }
+                p0 = g0; p1 = g1; p2 = g2; wprev = wv;
+            }
+            accv.x += c0; accv.y += c1; accv.z += c2; accv.w += wsum;
+            *accp = accv;
+        }
+        __syncthreads();                                   // B: raw visible, G(s-1) consumed, vertical(s) done with the buffer
+        if (s < nsteps) {
+#pragma unroll
+            for (int k = 0; k < C::HB; ++k) {
+                const int b = vg * C::HB + k;
+                if (b < B) {
+#pragma unroll
+                    for (int o = 0; o < STEP; ++o) G[((size_t)(b * 4 + vch) * STEP + o) * SW + vx] = res[k][o];
+                }
+            }
+        }
+        if (more_rows && tid < C::ROW_ITEMS) row_pass_item<B, SW>(raw, rowbuf, tid, chunk0 * STEP);   // chunk s+7 reuses chunk s's slot
+        chunk0 = (chunk0 + 1 == NCHUNK) ? 0 : chunk0 + 1;
+    }
+}
+
+} // namespace march

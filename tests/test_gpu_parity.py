@@ -225,17 +225,26 @@ def test_multi_blend_other_sigmas(ctx, oracle, sigma):
     _assert_float_close(api.multi_blend(tiles, cuts, ones, corners, 3, sigma, ctx), ref)
 
 
-def test_fast_and_generic_kernels_agree(ctx, spano_lib, golden):
+@pytest.mark.parametrize("bands", [1, 2, 5, 6, 7, 10])
+def test_three_blend_kernels_agree(ctx, spano_lib, oracle, bands):
+    """Marching-strip kernel (default), block-tiled kernel and generic-radius kernel: same numbers."""
     from simplepanorama_b200 import api
-    g, tiles, cuts, valids, corners = _blend_inputs(golden)
-    fast = api.multi_blend(tiles, cuts, valids, corners, 5, 7.0, ctx)
-    spano_lib.spano_debug_force_generic(1)
-    try:
-        gen = api.multi_blend(tiles, cuts, valids, corners, 5, 7.0, ctx)
-    finally:
-        spano_lib.spano_debug_force_generic(0)
-    _assert_float_close(fast, gen)
-    _assert_float_close(gen, g["blend_f32_B5"])
+    rng = np.random.default_rng(40 + bands)
+    sizes = [(233, 310), (75, 40), (19, 300)]          # taller than a segment, smaller than the radius, narrow
+    corners = [(0, 0), (200, 100), (120, 5)]
+    tiles = [rng.integers(16, 240, (h, w, 3), dtype=np.uint8) for (w, h) in sizes]
+    cuts = [(rng.random((h, w)) * 255).astype(np.uint8) for (w, h) in sizes]
+    valids = [np.where(rng.random((h, w)) < 0.9, 255, 0).astype(np.uint8) for (w, h) in sizes]
+    outs = []
+    for mode in (0, 2, 1):
+        spano_lib.spano_debug_force_generic(mode)
+        try:
+            outs.append(api.multi_blend(tiles, cuts, valids, corners, bands, 7.0, ctx))
+        finally:
+            spano_lib.spano_debug_force_generic(0)
+    _assert_float_close(outs[0], outs[1])
+    _assert_float_close(outs[0], outs[2])
+    _assert_float_close(outs[0], oracle.multi_blend(tiles, cuts, valids, corners, bands, 7.0))
 
 
 def test_single_tile_closed_form(ctx, oracle):

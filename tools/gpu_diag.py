@@ -1,7 +1,7 @@
 """Diagnostics run on the GPU box (not a test): prints parity statistics and micro-benchmarks."""
 import json, sys, time, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from simplepanorama_b200 import api, synth, build as sb
 from oracle import oracle as orc
 sb.build(); orc.build()
