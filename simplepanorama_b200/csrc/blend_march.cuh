@@ -9,14 +9,16 @@
 //   horizontally exactly once: no halo recomputation in y.  In x only loads are redundant (the
 //   21-px halo is staged, not filtered).
 //
-//   Every thread runs the same schedule per 8-row step s (2 CTA barriers):
-//     A | stage: raw chunk s+7 (prefetched last step) -> shared; prefetch chunk s+8; early-issue the
-//       | global loads of the combine of step s-1 (validity, centre pixel, canvas accumulator)
-//       | vertical pass of step s: thread = (sigma group, channel, column); per sigma 50 LDS feed
-//       |   8 accumulators each (344 FFMA); taps are compile-time constant-bank operands
-//       | combine of step s-1: weights, validity zeroing, band algebra, one float4 RMW of the canvas
-//     B | publish the vertical results of step s to shared (G)
-//       | horizontal pass of chunk s+7 for all B sigmas at once (shared pair sums) -> circular buffer
+//   Every thread runs the same schedule per 8-row step s (3 CTA barriers; the loop body is kept small
+//   enough -- one copy of each pass -- to stay resident in the instruction cache):
+//     A  | stage: raw chunk s+7 (bytes prefetched last step) -> shared as float; prefetch chunk s+8
+//        | combine of step s-1: weights, validity zeroing, band algebra, one float4 RMW of the canvas
+//        |   (its global loads -- validity, centre pixel, accumulator -- were issued one step earlier)
+//     A2 | vertical pass of step s: thread = (sigma group, channel, column); per sigma 50 LDS feed
+//        |   8 accumulators each (344 FFMA, taps in registers); results published to shared (G)
+//     B  | issue the global loads of the combine of step s
+//        | horizontal pass of chunk s+7 for all B sigmas at once (shared pair sums) -> circular buffer
+//   Steps -7..-1 run the same loop with the vertical pass and combine skipped (they fill the buffer).
 //   Per tile pixel: 4*(21 + 22B) + 4*43B FMA-pipe instructions (B = 6: 1644), 37 B of HBM traffic.
 #pragma once
 
@@ -70,7 +72,7 @@ __device__ __forceinline__ int reflect_idx(int p, int len)
 
 // raw element e of the chunk whose first row is tile row yrow0: (ch, i, c), c fastest
 template <int B, int SW>
-__device__ __forceinline__ float fetch_raw(const Params &P, const int *xtab, int e, int yrow0)
+__device__ __forceinline__ uint32_t fetch_raw(const Params &P, const int *xtab, int e, int yrow0)
 {
     using C = Cfg<B, SW>;
     const int c = e % C::NC;
@@ -78,8 +80,8 @@ __device__ __forceinline__ float fetch_raw(const Params &P, const int *xtab, int
     const int i = t & (STEP - 1), ch = t >> 3;
     const int y = reflect_idx(yrow0 + i, P.h);
     const int x = xtab[c];
-    if (ch == 0) return (float)__ldg(P.cut + (size_t)y * P.cut_step + x);
-    return (float)__ldg(P.tile + (size_t)y * P.tile_step + (size_t)x * 3 + (ch - 1));
+    if (ch == 0) return __ldg(P.cut + (size_t)y * P.cut_step + x);
+    return __ldg(P.tile + (size_t)y * P.tile_step + (size_t)x * 3 + (ch - 1));
 }
 
 // horizontal pass of one item (row i of channel ch, 4 columns) of the staged chunk -> circular buffer slot
@@ -118,10 +120,14 @@ __device__ __forceinline__ void row_pass_item(const float *raw, float *rowbuf, i
         *reinterpret_cast<float4 *>(dst + (size_t)(b * 4) * C::PLANE_STRIDE) = make_float4(out[b][0], out[b][1], out[b][2], out[b][3]);
 }
 
-// vertical pass of one sigma (compile-time b): 50 rows of one plane column -> 8 outputs
-template <int B, int SW, int BIDX>
-__device__ __forceinline__ void vertical_one(const float *col /* plane + x */, int chunk0, float (&res)[STEP])
+// vertical pass of one sigma (run-time b, taps in registers so the code exists once and stays in the
+// instruction cache): 50 rows of one plane column -> 8 outputs
+template <int SW>
+__device__ __forceinline__ void vertical_one(const float *col /* plane + x */, const float *tp, int chunk0, float (&res)[STEP])
 {
+    float tap[R + 1];
+#pragma unroll
+    for (int j = 0; j <= R; ++j) tap[j] = tp[j];
 #pragma unroll
     for (int o = 0; o < STEP; ++o) res[o] = 0.f;
 #pragma unroll
@@ -137,29 +143,8 @@ __device__ __forceinline__ void vertical_one(const float *col /* plane + x */, i
 #pragma unroll
                 for (int o = 0; o < STEP; ++o) {
                     const int d = i - o;                // tap index 0..42
-                    if (d >= 0 && d <= 2 * R) res[o] = fmaf(c_taps[BIDX][d < R ? R - d : d - R], val, res[o]);
+                    if (d >= 0 && d <= 2 * R) res[o] = fmaf(tap[d < R ? R - d : d - R], val, res[o]);
                 }
-            }
-        }
-    }
-}
-
-template <int B, int SW, int GRP>
-__device__ __forceinline__ void vertical_group(const float *rowbuf, int ch, int x, int chunk0, float (&res)[Cfg<B, SW>::HB][STEP])
-{
-    using C = Cfg<B, SW>;
-#pragma unroll
-    for (int k = 0; k < C::HB; ++k) {
-        const int b = GRP * C::HB + k;
-        if (b < B) {
-            const float *col = rowbuf + (size_t)(b * 4 + ch) * C::PLANE_STRIDE + x;
-            // BIDX must be a compile-time constant: dispatch on k (unrolled) via a small switch
-            switch (k) {
-            case 0: vertical_one<B, SW, (GRP * C::HB + 0 < B ? GRP * C::HB + 0 : 0)>(col, chunk0, res[k]); break;
-            case 1: vertical_one<B, SW, (GRP * C::HB + 1 < B ? GRP * C::HB + 1 : 0)>(col, chunk0, res[k]); break;
-            case 2: vertical_one<B, SW, (GRP * C::HB + 2 < B ? GRP * C::HB + 2 : 0)>(col, chunk0, res[k]); break;
-            case 3: vertical_one<B, SW, (GRP * C::HB + 3 < B ? GRP * C::HB + 3 : 0)>(col, chunk0, res[k]); break;
-            default: vertical_one<B, SW, (GRP * C::HB + 4 < B ? GRP * C::HB + 4 : 0)>(col, chunk0, res[k]); break;
             }
         }
     }
@@ -189,77 +174,46 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
     const int po = tid / SW, px = tid % SW;
 
     for (int c = tid; c < C::NC; c += THREADS) xtab[c] = reflect_idx(tx0 - R + c, P.w);
+    __syncthreads();
 
-    // ---------------- prologue: chunks 0..6 (relative rows 0..55) through the horizontal pass -------------
-#pragma unroll 1
-    for (int q = 0; q < NCHUNK; ++q) {
-        __syncthreads();
-        for (int e = tid; e < C::STAGE_ELEMS; e += THREADS)
-            raw[(size_t)(e / C::NC) * C::RAW_PITCH + (e % C::NC)] = fetch_raw<B, SW>(P, xtab, e, ybase + q * STEP);
-        __syncthreads();
-        if (tid < C::ROW_ITEMS) row_pass_item<B, SW>(raw, rowbuf, tid, q * STEP);
-    }
-
-    // prefetch registers: chunk 7 (consumed in step 0)
-    float pre[C::PRE];
+    // prefetch registers (raw bytes): chunk 0, consumed in step -7
+    uint32_t pre[C::PRE];
 #pragma unroll
     for (int k = 0; k < C::PRE; ++k) {
         const int e = tid + k * THREADS;
-        pre[k] = (e < C::STAGE_ELEMS && nsteps > 1) ? fetch_raw<B, SW>(P, xtab, e, ybase + NCHUNK * STEP) : 0.f;
+        pre[k] = (e < C::STAGE_ELEMS) ? fetch_raw<B, SW>(P, xtab, e, ybase) : 0u;
     }
 
-    float res[C::HB][STEP];
-    int chunk0 = 0;                                        // circular slot of chunk s
+    int chunk0 = 0;                                        // circular slot of chunk s (== slot chunk s+7 will reuse)
+    // registers of the combine of the previous step (loaded one step ahead so their latency is hidden)
+    uint32_t vraw = 0, i0 = 0, i1 = 0, i2 = 0;
+    float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 *accp = nullptr;
+    bool cdo = false;
 
+    // steps -7..-1 only fill the circular buffer (chunks 0..6); step s >= 0 produces tile rows y0+8s..y0+8s+7
 #pragma unroll 1
-    for (int s = 0; s <= nsteps; ++s) {
-        __syncthreads();                                   // A: chunk s..s+6 filtered, G(s-1) published, raw free
+    for (int s = -NCHUNK; s <= nsteps; ++s) {
+        __syncthreads();                                   // A: chunks s..s+6 filtered, G(s-1) published, raw free
         const bool more_rows = s + 1 < nsteps;             // chunk s+7 is needed by step s+1
         if (more_rows) {
 #pragma unroll
             for (int k = 0; k < C::PRE; ++k) {
                 const int e = tid + k * THREADS;
-                if (e < C::STAGE_ELEMS) raw[(size_t)(e / C::NC) * C::RAW_PITCH + (e % C::NC)] = pre[k];
+                if (e < C::STAGE_ELEMS) raw[(size_t)(e / C::NC) * C::RAW_PITCH + (e % C::NC)] = (float)pre[k];
             }
             if (s + 2 < nsteps) {
 #pragma unroll
                 for (int k = 0; k < C::PRE; ++k) {
                     const int e = tid + k * THREADS;
-                    pre[k] = (e < C::STAGE_ELEMS) ? fetch_raw<B, SW>(P, xtab, e, ybase + (s + 1 + NCHUNK) * STEP) : 0.f;
+                    pre[k] = (e < C::STAGE_ELEMS) ? fetch_raw<B, SW>(P, xtab, e, ybase + (s + 1 + NCHUNK) * STEP) : 0u;
                 }
             }
         }
-        // early loads for the combine of step s-1
-        const int cty = y0 + (s - 1) * STEP + po, ctx_ = tx0 + px;
-        const bool cdo = (s > 0) && (tid < C::NPX) && (ctx_ < P.w) && (cty < y1);
-        bool keep = false;
-        float I0 = 0.f, I1 = 0.f, I2 = 0.f;
-        float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 *accp = nullptr;
+        // ---- combine of step s-1 (its global loads were issued during step s-1) ----
         if (cdo) {
-            keep = __ldg(P.valid + (size_t)cty * P.valid_step + ctx_) == 255;
-            const uint8_t *pp = P.tile + (size_t)cty * P.tile_step + (size_t)ctx_ * 3;
-            I0 = (float)__ldg(pp); I1 = (float)__ldg(pp + 1); I2 = (float)__ldg(pp + 2);
-            accp = P.acc + (size_t)(P.ay + cty) * P.canvas_w + (P.ax + ctx_);
-            accv = *accp;
-        }
-        // ---- vertical pass of step s ----
-        if (s < nsteps) {
-            if constexpr (C::NG == 2) {
-                if (vg == 0) vertical_group<B, SW, 0>(rowbuf, vch, vx, chunk0, res);
-                else vertical_group<B, SW, 1>(rowbuf, vch, vx, chunk0, res);
-            } else {
-                static_assert(C::NG == 4, "sigma groups");
-                switch (vg) {
-                case 0: vertical_group<B, SW, 0>(rowbuf, vch, vx, chunk0, res); break;
-                case 1: vertical_group<B, SW, 1>(rowbuf, vch, vx, chunk0, res); break;
-                case 2: vertical_group<B, SW, 2>(rowbuf, vch, vx, chunk0, res); break;
-                default: vertical_group<B, SW, 3>(rowbuf, vch, vx, chunk0, res); break;
-                }
-            }
-        }
-        // ---- combine of step s-1 ----
-        if (cdo) {
+            const bool keep = vraw == 255u;
+            const float I0 = (float)i0, I1 = (float)i1, I2 = (float)i2;
             const float *g = G + po * SW + px;              // + plane * STEP * SW
             float wsum = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
             float p0 = 0.f, p1 = 0.f, p2 = 0.f, wprev = 0.f;
@@ -282,18 +236,36 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
             accv.x += c0; accv.y += c1; accv.z += c2; accv.w += wsum;
             *accp = accv;
         }
-        __syncthreads();                                   // B: raw visible, G(s-1) consumed, vertical(s) done with the buffer
-        if (s < nsteps) {
-#pragma unroll
+        __syncthreads();                                   // A2: G(s-1) consumed
+        // ---- vertical pass of step s, results straight into G ----
+        const bool vdo = s >= 0 && s < nsteps;
+        if (vdo) {
+#pragma unroll 1
             for (int k = 0; k < C::HB; ++k) {
                 const int b = vg * C::HB + k;
                 if (b < B) {
+                    float res[STEP];
+                    vertical_one<SW>(rowbuf + (size_t)(b * 4 + vch) * C::PLANE_STRIDE + vx, c_taps[b], chunk0, res);
+                    float *gp = G + (size_t)(b * 4 + vch) * STEP * SW + vx;
 #pragma unroll
-                    for (int o = 0; o < STEP; ++o) G[((size_t)(b * 4 + vch) * STEP + o) * SW + vx] = res[k][o];
+                    for (int o = 0; o < STEP; ++o) gp[o * SW] = res[o];
                 }
             }
         }
-        if (more_rows && tid < C::ROW_ITEMS) row_pass_item<B, SW>(raw, rowbuf, tid, chunk0 * STEP);   // chunk s+7 reuses chunk s's slot
+        __syncthreads();                                   // B: raw visible; vertical(s) done with the circular buffer
+        // issue the global loads of the combine of step s (consumed after the next barrier A)
+        {
+            const int cty = y0 + s * STEP + po, ctx_ = tx0 + px;
+            cdo = vdo && (tid < C::NPX) && (ctx_ < P.w) && (cty < y1);
+            if (cdo) {
+                vraw = __ldg(P.valid + (size_t)cty * P.valid_step + ctx_);
+                const uint8_t *pp = P.tile + (size_t)cty * P.tile_step + (size_t)ctx_ * 3;
+                i0 = __ldg(pp); i1 = __ldg(pp + 1); i2 = __ldg(pp + 2);
+                accp = P.acc + (size_t)(P.ay + cty) * P.canvas_w + (P.ax + ctx_);
+                accv = *accp;
+            }
+        }
+        if (more_rows && tid < C::ROW_ITEMS) row_pass_item<B, SW>(raw, rowbuf, tid, chunk0 * STEP);   // chunk s+7 takes the slot chunk s vacates
         chunk0 = (chunk0 + 1 == NCHUNK) ? 0 : chunk0 + 1;
     }
 }
