@@ -61,6 +61,7 @@ def _run(cmd: list[str], verbose: bool, log_name: str | None = None) -> None:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    hdrs += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     jobs = []
     objs = []
     for s in CU_SOURCES:

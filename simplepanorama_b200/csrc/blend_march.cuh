@@ -59,6 +59,15 @@ struct Params {
     int ax, ay;
 };
 
+// u8 global load that lands zero-extended in a 32-bit register: no dependent instruction (mask /
+// convert) is scheduled behind the load, so its latency can be hidden behind the next phase
+__device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ int reflect_idx(int p, int len)
 {
     if ((unsigned)p < (unsigned)len) return p;
@@ -80,8 +89,8 @@ __device__ __forceinline__ uint32_t fetch_raw(const Params &P, const int *xtab, 
     const int i = t & (STEP - 1), ch = t >> 3;
     const int y = reflect_idx(yrow0 + i, P.h);
     const int x = xtab[c];
-    if (ch == 0) return __ldg(P.cut + (size_t)y * P.cut_step + x);
-    return __ldg(P.tile + (size_t)y * P.tile_step + (size_t)x * 3 + (ch - 1));
+    if (ch == 0) return ldg_u8(P.cut + (size_t)y * P.cut_step + x);
+    return ldg_u8(P.tile + (size_t)y * P.tile_step + (size_t)x * 3 + (ch - 1));
 }
 
 // horizontal pass of one item (row i of channel ch, 4 columns) of the staged chunk -> circular buffer slot
@@ -240,10 +249,11 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
         // ---- vertical pass of step s, results straight into G ----
         const bool vdo = s >= 0 && s < nsteps;
         if (vdo) {
+            // the loop counter b is uniform, so the taps c_taps[b][..] become uniform-register operands
+            // (2 vector-register sources per FFMA); each thread group takes the sigmas of its share
 #pragma unroll 1
-            for (int k = 0; k < C::HB; ++k) {
-                const int b = vg * C::HB + k;
-                if (b < B) {
+            for (int b = 0; b < B; ++b) {
+                if (b / C::HB == vg) {
                     float res[STEP];
                     vertical_one<SW>(rowbuf + (size_t)(b * 4 + vch) * C::PLANE_STRIDE + vx, c_taps[b], chunk0, res);
                     float *gp = G + (size_t)(b * 4 + vch) * STEP * SW + vx;
@@ -258,9 +268,9 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
             const int cty = y0 + s * STEP + po, ctx_ = tx0 + px;
             cdo = vdo && (tid < C::NPX) && (ctx_ < P.w) && (cty < y1);
             if (cdo) {
-                vraw = __ldg(P.valid + (size_t)cty * P.valid_step + ctx_);
+                vraw = ldg_u8(P.valid + (size_t)cty * P.valid_step + ctx_);
                 const uint8_t *pp = P.tile + (size_t)cty * P.tile_step + (size_t)ctx_ * 3;
-                i0 = __ldg(pp); i1 = __ldg(pp + 1); i2 = __ldg(pp + 2);
+                i0 = ldg_u8(pp); i1 = ldg_u8(pp + 1); i2 = ldg_u8(pp + 2);
                 accp = P.acc + (size_t)(P.ay + cty) * P.canvas_w + (P.ax + ctx_);
                 accv = *accp;
             }
