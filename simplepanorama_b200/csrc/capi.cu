@@ -204,6 +204,12 @@ extern "C" void spano_destroy(spano_ctx *ctx)
     for (auto &b : ctx->buf)
         if (b.ptr) cudaFree(b.ptr);
     for (void *p : ctx->owned) cudaFree(p);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+        for (int b = 0; b < 2; ++b) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_free[b]); }
+        cudaEventDestroy(ctx->ev_start);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -537,70 +543,105 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
     if (row1 > chh) row1 = chh;
     if (row1 <= row0) return spano_fail(ctx, SPANO_E_INVALID, "empty row band [%d,%d)", row0, row1);
     if (canvas_step < (size_t)cw * 3) return spano_fail(ctx, SPANO_E_INVALID, "canvas_step too small");
-    int radius = (int)std::ceil(3 * sigma);
+    const int rows = row1 - row0;
 
-    // tiles that touch canvas rows [row0 - radius, row1 + radius) take part (halo recomputed locally)
+    // Tiles that touch canvas rows [row0,row1) take part.  BORDER_REFLECT is resolved inside each tile,
+    // so a band needs the full extent of exactly those tiles and nothing from neighbouring bands.
     std::vector<int> use;
-    size_t tiles_bytes = 0, src_bytes_max = 0, cut_bytes_max = 0;
-    std::vector<size_t> off_t(n), off_v(n), st_t(n), st_m(n);
+    size_t src_max = 0, tile_max = 0, mask_max = 0;
     for (int j = 0; j < n; ++j) {
         if (int rc = check_image_args(ctx, im[j].src_bgr, im[j].src_w, im[j].src_h, im[j].src_step, 3, "source")) return rc;
         if (int rc = check_image_args(ctx, im[j].mask_cut, im[j].w, im[j].h, im[j].mask_cut_step, 1, "mask_cut")) return rc;
         if (!(im[j].gain > 0.0)) return spano_fail(ctx, SPANO_E_INVALID, "gain[%d] must be > 0", j);
         if (int rc = check_remap_limits(ctx, im[j].src_w, im[j].src_h, im[j].w, im[j].h)) return rc;
         const int cy = im[j].tl_y - my;
-        if (cy + im[j].h <= row0 || cy >= row1) continue; // blur support never crosses tile borders (reflect)
+        if (cy + im[j].h <= row0 || cy >= row1) continue;
         use.push_back(j);
-        st_t[j] = align_up((size_t)im[j].w * 3, 16);
-        st_m[j] = align_up((size_t)im[j].w, 16);
-        off_t[j] = tiles_bytes; tiles_bytes += st_t[j] * im[j].h;
-        off_v[j] = tiles_bytes; tiles_bytes += st_m[j] * im[j].h;
-        src_bytes_max = std::max(src_bytes_max, align_up((size_t)im[j].src_w * 3, 16) * im[j].src_h + 16);
-        cut_bytes_max = std::max(cut_bytes_max, st_m[j] * im[j].h);
+        src_max = std::max(src_max, align_up((size_t)im[j].src_w * 3, 16) * im[j].src_h + 16);
+        tile_max = std::max(tile_max, align_up((size_t)im[j].w * 3, 16) * im[j].h);
+        mask_max = std::max(mask_max, align_up((size_t)im[j].w, 16) * im[j].h);
     }
-    (void)radius;
-    uint8_t *arena = nullptr, *d_src = nullptr, *d_cut_all = nullptr;
-    if (!use.empty())
-        if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, tiles_bytes, (void **)&arena)) return rc;
-    size_t cut_total = 0;
-    std::vector<size_t> off_c(n);
-    if (host) {
-        for (int j : use) { off_c[j] = cut_total; cut_total += st_m[j] * im[j].h; }
-        if (!use.empty()) {
-            if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC, src_bytes_max, (void **)&d_src)) return rc;
-            if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTMASK, cut_total, (void **)&d_cut_all)) return rc;
-        }
-    }
-    std::vector<BlendTile> bt;
-    for (int j : use) {
-        SpanoProjector P;
-        spano_host_set_camera(&P, proj, scale, im[j].K, im[j].R);
-        const uint8_t *src = im[j].src_bgr;
-        size_t s_step = im[j].src_step;
-        const uint8_t *cut = im[j].mask_cut;
-        size_t c_step = im[j].mask_cut_step;
+    const int radius = launch_blend_setup(ctx, bands, sigma);
+    if (radius < 0) return radius;
+    float4 *acc = nullptr;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_ACC, (size_t)cw * rows * sizeof(float4), (void **)&acc)) return rc;
+    uint8_t *d_tile = nullptr, *d_valid = nullptr, *d_srcbuf[2] = {nullptr, nullptr}, *d_cutbuf[2] = {nullptr, nullptr};
+    if (!use.empty()) {
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, tile_max, (void **)&d_tile)) return rc;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILEMASK, mask_max, (void **)&d_valid)) return rc;
         if (host) {
-            s_step = align_up((size_t)im[j].src_w * 3, 16);
-            SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_src, s_step, im[j].src_bgr, im[j].src_step, (size_t)im[j].src_w * 3, im[j].src_h, cudaMemcpyHostToDevice, ctx->stream));
-            src = d_src;
-            c_step = st_m[j];
-            SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_cut_all + off_c[j], c_step, im[j].mask_cut, im[j].mask_cut_step, (size_t)im[j].w, im[j].h, cudaMemcpyHostToDevice, ctx->stream));
-            cut = d_cut_all + off_c[j];
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC, src_max, (void **)&d_srcbuf[0])) return rc;
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC2, src_max, (void **)&d_srcbuf[1])) return rc;
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTMASK, mask_max, (void **)&d_cutbuf[0])) return rc;
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUT2, mask_max, (void **)&d_cutbuf[1])) return rc;
         }
-        if (int rc = dev_warp_tile(ctx, P, src, im[j].src_w, im[j].src_h, s_step, im[j].gain, im[j].tl_x, im[j].tl_y, im[j].w, im[j].h,
-                                   arena + off_t[j], st_t[j], arena + off_v[j], st_m[j]))
-            return rc;
-        bt.push_back(BlendTile{arena + off_t[j], st_t[j], cut, c_step, arena + off_v[j], st_m[j], im[j].w, im[j].h, im[j].tl_x - mx, im[j].tl_y - my});
     }
     uint8_t *d_canvas = canvas;
     size_t d_step = canvas_step;
     if (host) {
         d_step = align_up((size_t)cw * 3, 16);
-        if (int rc = spano_reserve(ctx, spano_ctx::BUF_CANVAS, d_step * (row1 - row0), (void **)&d_canvas)) return rc;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_CANVAS, d_step * rows, (void **)&d_canvas)) return rc;
+        if (!ctx->copy_stream) {
+            SPANO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {
+                SPANO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
+                SPANO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_free[b], cudaEventDisableTiming));
+            }
+            SPANO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+        }
+        // uploads must not overtake work already queued on the compute stream that still reads the staging buffers
+        SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));
+        SPANO_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_start, 0));
     }
-    if (int rc = dev_multiblend(ctx, (int)bt.size(), bt.data(), cw, chh, bands, sigma, row0, row1, SPANO_OUT_U8, d_canvas, d_step)) return rc;
+    // host path: image i+1 is uploaded on the copy stream while image i is warped and blended
+    auto issue_copy = [&](int idx) -> int {
+        const int j = use[idx], b = idx & 1;
+        cudaStream_t cs = ctx->copy_stream;
+        if (idx >= 2) SPANO_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_free[b], 0));
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_srcbuf[b], align_up((size_t)im[j].src_w * 3, 16), im[j].src_bgr, im[j].src_step,
+                                          (size_t)im[j].src_w * 3, im[j].src_h, cudaMemcpyHostToDevice, cs));
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_cutbuf[b], align_up((size_t)im[j].w, 16), im[j].mask_cut, im[j].mask_cut_step,
+                                          (size_t)im[j].w, im[j].h, cudaMemcpyHostToDevice, cs));
+        SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], cs));
+        return 0;
+    };
+    {
+        StageTimer t(ctx, 2);
+        if (int rc = launch_blend_clear(ctx, acc, cw, rows)) return rc;
+        t.stop(0);
+    }
+    if (host && !use.empty())
+        if (int rc = issue_copy(0)) return rc;
+    for (int idx = 0; idx < (int)use.size(); ++idx) {
+        const int j = use[idx], b = idx & 1;
+        if (host && idx + 1 < (int)use.size())
+            if (int rc = issue_copy(idx + 1)) return rc;
+        SpanoProjector P;
+        spano_host_set_camera(&P, proj, scale, im[j].K, im[j].R);
+        const uint8_t *src = im[j].src_bgr, *cut = im[j].mask_cut;
+        size_t s_step = im[j].src_step, c_step = im[j].mask_cut_step;
+        const size_t t_step = align_up((size_t)im[j].w * 3, 16), m_step = align_up((size_t)im[j].w, 16);
+        if (host) {
+            SPANO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+            src = d_srcbuf[b];  s_step = align_up((size_t)im[j].src_w * 3, 16);
+            cut = d_cutbuf[b];  c_step = m_step;
+        }
+        if (int rc = dev_warp_tile(ctx, P, src, im[j].src_w, im[j].src_h, s_step, im[j].gain, im[j].tl_x, im[j].tl_y, im[j].w, im[j].h,
+                                   d_tile, t_step, d_valid, m_step))
+            return rc;
+        StageTimer t2(ctx, 2);
+        const BlendTile bt{d_tile, t_step, cut, c_step, d_valid, m_step, im[j].w, im[j].h, im[j].tl_x - mx, im[j].tl_y - my};
+        int k = launch_blend_tile(ctx, bt, bands, radius, acc, cw, row0, row1);
+        if (k < 0) return k;
+        t2.stop(k);
+        if (host) SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], ctx->stream));
+    }
+    StageTimer t3(ctx, 3);
+    int k = launch_normalise(ctx, acc, cw, rows, bands, SPANO_OUT_U8, d_canvas, d_step);
+    if (k < 0) return k;
+    t3.stop(k);
     if (host) {
-        SPANO_CUDA(ctx, cudaMemcpy2DAsync(canvas, canvas_step, d_canvas, d_step, (size_t)cw * 3, row1 - row0, cudaMemcpyDeviceToHost, ctx->stream));
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(canvas, canvas_step, d_canvas, d_step, (size_t)cw * 3, rows, cudaMemcpyDeviceToHost, ctx->stream));
         SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return SPANO_OK;

@@ -7,6 +7,8 @@
 //           flood-fills from every border pixel with cv::floodFill)
 //   mask  = 255 everywhere except `out`; then three 3x3 erosions with OpenCV's default
 //           morphology border (+inf)  ==  one (2*3+1)^2 minimum that ignores out-of-image taps.
+//           Done on a 1-bit-per-pixel image of `out` (ballot-packed): vertical OR of the window rows,
+//           horizontal dilation by shifts, 32 output pixels per thread as two 16-byte stores.
 //
 // The flood fill is a whole-tile property, so it is computed as a parallel union-find
 // (label equivalence) over the dark pixels with one virtual node for "the border":
@@ -20,7 +22,6 @@
 
 namespace {
 
-constexpr uint32_t NOT_DARK = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t ld_label(const uint32_t *L, uint32_t i) { return __ldcg(L + i); }
 
@@ -61,7 +62,7 @@ __global__ void ccl_init_kernel(const uint8_t *dark, size_t dark_step, int w, in
     const uint32_t bits = __ballot_sync(0xFFFFFFFFu, d);
     if (!in) return;
     const size_t p = (size_t)y * w + x;
-    if (!d) { L[p + 1] = NOT_DARK; return; }
+    if (!d) return;   // labels of non-dark pixels are never read
     const uint32_t lane = threadIdx.x;
     const uint32_t zeros_below = ~bits & ((1u << lane) - 1u);
     const uint32_t start = zeros_below ? (32u - __clz(zeros_below)) : 0u; // first lane of my run
@@ -88,41 +89,57 @@ __global__ void ccl_merge_kernel(const uint8_t *dark, size_t dark_step, int w, i
     }
 }
 
-// mask = min over a (2r+1)^2 window (out-of-image ignored) of [border-connected dark ? 0 : 255]
-constexpr int ER_TW = 64, ER_TH = 16, ER_RMAX = 8;
-
-__global__ void __launch_bounds__(256) resolve_erode_kernel(const uint8_t *dark, size_t dark_step, int w, int h,
-                                                            uint32_t *L, int r, uint8_t *mask, size_t mask_step)
+// "outside" bit of every pixel (dark and connected to the border), 32 pixels per word
+__global__ void resolve_bits_kernel(const uint8_t *dark, size_t dark_step, int w, int h, uint32_t *L, uint32_t *bits,
+                                    int words_per_row)
 {
-    __shared__ uint8_t s_in[ER_TH + 2 * ER_RMAX][ER_TW + 2 * ER_RMAX];
-    __shared__ uint8_t s_row[ER_TH + 2 * ER_RMAX][ER_TW];
-    const int x0 = blockIdx.x * ER_TW, y0 = blockIdx.y * ER_TH;
-    const int tw = ER_TW + 2 * r, th = ER_TH + 2 * r;
-    for (int i = threadIdx.x; i < tw * th; i += blockDim.x) {
-        const int lx = i % tw, ly = i / tw;
-        const int gx = x0 - r + lx, gy = y0 - r + ly;
-        uint8_t v = 255;
-        if (gx >= 0 && gx < w && gy >= 0 && gy < h && dark[(size_t)gy * dark_step + gx]) {
-            const uint32_t id = (uint32_t)((size_t)gy * w + gx) + 1u;
-            if (find_root(L, id) == 0u) v = 0;
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    bool out = false;
+    if (x < w && y < h && dark[(size_t)y * dark_step + x]) {
+        const uint32_t id = (uint32_t)((size_t)y * w + x) + 1u;
+        out = find_root(L, id) == 0u;
+    }
+    const uint32_t word = __ballot_sync(0xFFFFFFFFu, out);
+    if (threadIdx.x == 0 && y < h && blockIdx.x < words_per_row) bits[(size_t)y * words_per_row + blockIdx.x] = word;
+}
+
+// mask = 0 where any outside pixel lies in the (2r+1)^2 window (out-of-image taps ignored), else 255:
+// r erosions with a 3x3 box == one (2r+1)^2 minimum.  One thread = one 32-pixel word of one row.
+__global__ void erode_bits_kernel(const uint32_t *bits, int words_per_row, int w, int h, int r, uint8_t *mask, size_t mask_step)
+{
+    const int wx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (wx >= words_per_row || y >= h) return;
+    uint32_t lo = 0, mid = 0, hi = 0;   // vertical OR over the window rows of words wx-1, wx, wx+1
+    for (int dy = -r; dy <= r; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= h) continue;
+        const uint32_t *row = bits + (size_t)yy * words_per_row;
+        mid |= row[wx];
+        if (wx > 0) lo |= row[wx - 1];
+        if (wx + 1 < words_per_row) hi |= row[wx + 1];
+    }
+    uint32_t o = mid;
+    for (int d = 1; d <= r; ++d) {
+        o |= (mid << d) | (lo >> (32 - d));   // outside pixel d to the left
+        o |= (mid >> d) | (hi << (32 - d));   // outside pixel d to the right
+    }
+    const int x0 = wx * 32;
+    uint8_t *dst = mask + (size_t)y * mask_step + x0;
+    if (x0 + 32 <= w && (((uintptr_t)dst) & 15) == 0) {
+        uint32_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t nib = (o >> (4 * q)) & 15u;
+            // 4 pixels -> 4 bytes: 0x00 where the bit is set, 0xFF otherwise
+            v[q] = ((nib & 1u) ? 0u : 0x000000FFu) | ((nib & 2u) ? 0u : 0x0000FF00u) | ((nib & 4u) ? 0u : 0x00FF0000u) |
+                   ((nib & 8u) ? 0u : 0xFF000000u);
         }
-        s_in[ly][lx] = v;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < ER_TW * th; i += blockDim.x) {
-        const int lx = i % ER_TW, ly = i / ER_TW;
-        uint8_t m = 255;
-        for (int k = 0; k <= 2 * r; ++k) m = min(m, s_in[ly][lx + k]);
-        s_row[ly][lx] = m;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < ER_TW * ER_TH; i += blockDim.x) {
-        const int lx = i % ER_TW, ly = i / ER_TW;
-        const int gx = x0 + lx, gy = y0 + ly;
-        if (gx >= w || gy >= h) continue;
-        uint8_t m = 255;
-        for (int k = 0; k <= 2 * r; ++k) m = min(m, s_row[ly + k][lx]);
-        mask[(size_t)gy * mask_step + gx] = m;
+        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    } else {
+        for (int i = 0; i < 32 && x0 + i < w; ++i) dst[i] = ((o >> i) & 1u) ? 0 : 255;
     }
 }
 
@@ -132,17 +149,21 @@ int launch_valid_mask(spano_ctx *ctx, const uint8_t *dark, int w, int h, size_t 
                       uint8_t *mask, size_t mask_step)
 {
     if (w <= 0 || h <= 0) return 0;
-    if (erode_iters < 0 || erode_iters > ER_RMAX)
-        return spano_fail(ctx, SPANO_E_INVALID, "erode iterations %d not in [0,%d]", erode_iters, ER_RMAX);
-    uint32_t *L = nullptr;
+    if (erode_iters < 0 || erode_iters > 15)
+        return spano_fail(ctx, SPANO_E_INVALID, "erode iterations %d not in [0,15]", erode_iters);
+    uint32_t *L = nullptr, *bits = nullptr;
+    const int wpr = (w + 31) / 32;
     int rc = spano_reserve(ctx, spano_ctx::BUF_LABELS, ((size_t)w * h + 1) * sizeof(uint32_t), (void **)&L);
     if (rc) return rc;
-    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+    rc = spano_reserve(ctx, spano_ctx::BUF_MASK0, (size_t)wpr * h * sizeof(uint32_t), (void **)&bits);
+    if (rc) return rc;
+    dim3 block(32, 8), grid(wpr, (h + 7) / 8);
     ccl_init_kernel<<<grid, block, 0, ctx->stream>>>(dark, dark_step, w, h, L);
     ccl_merge_kernel<<<grid, block, 0, ctx->stream>>>(dark, dark_step, w, h, L);
-    dim3 egrid((w + ER_TW - 1) / ER_TW, (h + ER_TH - 1) / ER_TH);
-    resolve_erode_kernel<<<egrid, 256, 0, ctx->stream>>>(dark, dark_step, w, h, L, erode_iters, mask, mask_step);
+    resolve_bits_kernel<<<grid, block, 0, ctx->stream>>>(dark, dark_step, w, h, L, bits, wpr);
+    dim3 eblock(64), egrid((wpr + 63) / 64, h);
+    erode_bits_kernel<<<egrid, eblock, 0, ctx->stream>>>(bits, wpr, w, h, erode_iters, mask, mask_step);
     SPANO_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 3;
-    return 3;
+    ctx->launches += 4;
+    return 4;
 }

@@ -34,12 +34,15 @@ struct spano_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    // host-buffer fused path: uploads run on their own stream, double-buffered against the compute stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
     std::mutex mu;
     std::string err;
     long long launches = 0;
     // grow-only scratch buffers, indexed by role
     enum { BUF_LABELS = 0, BUF_DARK, BUF_MASK0, BUF_TABLES, BUF_ACC, BUF_TILE, BUF_TILEMASK, BUF_CUTMASK, BUF_SRC,
-           BUF_CANVAS, BUF_MISC, BUF_COUNT };
+           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_COUNT };
     DeviceBuffer buf[BUF_COUNT];
     std::vector<void *> owned; // extra allocations freed at destroy / end of call
     // timers
