@@ -113,6 +113,23 @@ int spano_surrounding_mask(spano_ctx *ctx, const uint8_t *bgr, int w, int h, siz
 /* a6 alone: `img / gain` on CV_8UC3, in place. */
 int spano_apply_gain(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, double gain);
 
+/* ---- a5: sten_proj::disk_reproj, the little-planet centre fix (HOST buffers) -----------
+ * (src/math/_projection.cpp:193-294 with get_bounding_box/create_border :87-190 and
+ * util::RadialNormalizer src/system/_util.h:172-200).  Inputs: the stereographic tiles and their
+ * corners as proj::get_proj_parameters returned them, and the circle (ansatz, radius) that
+ * sten_proj::estimate_circle found (that connected-component search stays in the reference).
+ * spano_disk_reproj_size gives the new corners (relative to the canvas centre, exactly the values
+ * the reference stores back into proj.corners) and sizes; spano_disk_reproj fills the resampled
+ * tiles and their recomputed validity masks (createSurroundingMask + 3 erosions).
+ * quadratic != 0 selects QUADRATIC_SCALING.  The size query is host arithmetic: ctx may be NULL. */
+int spano_disk_reproj_size(spano_ctx *ctx, int n, const int *tl_x, const int *tl_y, const int *w, const int *h,
+                           int ansatz_x, int ansatz_y, float radius, int quadratic, int *out_tl_x, int *out_tl_y,
+                           int *out_w, int *out_h);
+int spano_disk_reproj(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps, const int *tl_x,
+                      const int *tl_y, const int *w, const int *h, int ansatz_x, int ansatz_y, float radius,
+                      int quadratic, uint8_t *const *out_tiles, const size_t *out_steps, uint8_t *const *out_masks,
+                      const size_t *out_mask_steps);
+
 /* ---- a7 + a8 + a10: blnd::multi_blend (+ the x255/convertTo tail of blend()) ----------
  * tiles[j]  : CV_8UC3 w[j] x h[j]      (gain already applied)
  * masks[j]  : CV_8UC1 mask_cut, 0..255 (seam mask resized to the tile, _panorama.cpp:329-335)

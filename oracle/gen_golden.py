@@ -164,8 +164,21 @@ def gen_misc(rng):
             "resize_dst": cv2.resize(src, (200, 117), interpolation=cv2.INTER_LINEAR)}
 
 
+def gen_cubic_gather():
+    """KAT for a5: cv::remap(INTER_CUBIC, BORDER_CONSTANT) on INTEGER-valued maps (what
+    sten_proj::disk_reproj feeds it, src/math/_projection.cpp:259-278) is an exact pixel gather."""
+    rng = np.random.default_rng(7)
+    H, W = 41, 57
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    xm = rng.integers(-4, W + 4, (50, 66)).astype(np.float32)
+    ym = rng.integers(-4, H + 4, (50, 66)).astype(np.float32)
+    dst = cv2.remap(img, xm, ym, cv2.INTER_CUBIC, borderMode=cv2.BORDER_CONSTANT, borderValue=0)
+    return {"cubic_img": img, "cubic_x": xm, "cubic_y": ym, "cubic_dst": dst}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "cubic_gather.npz"), **gen_cubic_gather())
     rng = np.random.default_rng(20261018)
     np.savez_compressed(os.path.join(OUT, "roi_table.npz"), table=gen_roi_table(), cv2_version=np.array(cv2.__version__))
     np.savez_compressed(os.path.join(OUT, "warp_cases.npz"), **gen_warp_cases(rng))

@@ -144,6 +144,32 @@ def resize_linear_u8(mask, size_wh):
     return out
 
 
+class _DiskParams(C.Structure):
+    _fields_ = [("cx", C.c_float), ("cy", C.c_float), ("scale", C.c_float), ("radius_n", C.c_float), ("quadratic", C.c_int)]
+
+
+def disk_reproj(tiles, corners, ansatz, radius, quadratic=True, erode_iters=3):
+    """sten_proj::disk_reproj -> (new tiles, new masks, new centre-relative corners)."""
+    n = len(tiles)
+    tiles = [np.ascontiguousarray(t) for t in tiles]
+    tlx = np.array([c[0] for c in corners], np.int32); tly = np.array([c[1] for c in corners], np.int32)
+    w = np.array([t.shape[1] for t in tiles], np.int32); h = np.array([t.shape[0] for t in tiles], np.int32)
+    ow = np.zeros(n, np.int32); oh = np.zeros(n, np.int32); ox = np.zeros(n, np.int32); oy = np.zeros(n, np.int32)
+    P = _DiskParams()
+    lib().orc_disk_reproj_plan(n, _p(tlx, C.c_int), _p(tly, C.c_int), _p(w, C.c_int), _p(h, C.c_int), int(ansatz[0]), int(ansatz[1]),
+                               C.c_float(radius), int(bool(quadratic)), _p(ow, C.c_int), _p(oh, C.c_int), _p(ox, C.c_int),
+                               _p(oy, C.c_int), C.byref(P))
+    outs, msks = [], []
+    for i in range(n):
+        dst = np.empty((int(oh[i]), int(ow[i]), 3), np.uint8)
+        lib().orc_disk_reproj_tile(C.byref(P), _p(tiles[i], C.c_uint8), int(w[i]), int(h[i]), C.c_size_t(tiles[i].strides[0]),
+                                   int(ox[i]), int(oy[i]), _p(dst, C.c_uint8), int(ow[i]), int(oh[i]), C.c_size_t(dst.strides[0]),
+                                   int(tlx[i]), int(tly[i]))
+        outs.append(dst)
+        msks.append(surrounding_mask(dst, erode_iters))
+    return outs, msks, [(int(a), int(b)) for a, b in zip(tlx, tly)]
+
+
 def adjusted_camera(K, R, w_ref, h_ref):
     """K_adj / R as float32 (src/math/_projection.cpp:36-49)."""
     K = np.asarray(K, np.float64)

@@ -543,3 +543,148 @@ void orc_resize_linear_u8c1(const uint8_t *src, int sw, int sh, uint8_t *dst, in
     }
     free(xofs); free(yofs); free(ialpha); free(ibeta);
 }
+
+/* ==== sten_proj::disk_reproj (src/math/_projection.cpp:193-294) ===========================
+ * Little-planet centre fix: every tile is resampled through a radial stretch about the
+ * estimated circle centre so that the annulus fills the hole.  Restated line by line:
+ *   util::get_pan_dimension, the shift of `ansatz` and the corners to canvas-centre coordinates
+ *   (:196-210), util::RadialNormalizer::computeParameters (src/system/_util.cpp:603-625),
+ *   the normalised radius (:214-218), sten_proj::get_bounding_box + create_border (:87-190),
+ *   the per-pixel inverse radial map with integer-rounded source coordinates (:229-269;
+ *   RadialNormalizer::denormalizePoint returns cv::Point, src/system/_util.h:191-195), and
+ *   cv::remap(INTER_CUBIC, BORDER_CONSTANT) on integer maps == exact pixel gather (:278).
+ * Unqualified sqrt/atan2/cos/sin on float arguments resolve to the double overloads with
+ * libstdc++'s <cmath> (checked with g++ 13 for the reference's include set); results are
+ * stored to float members, as in struct polar / struct kartesian (_projection.h:26-35).
+ * PARITY PIN: the gather is pinned against cv2.remap(INTER_CUBIC) on integer maps
+ * (tests/golden/kernels.npz); the geometry is the reference's own code and has no golden
+ * vectors upstream: "parity unpinned" beyond this restatement.                              */
+typedef struct {
+    float cx, cy, scale;  /* RadialNormalizer */
+    float radius_n;       /* normalised circle radius */
+    int quadratic;
+} orc_disk_params;
+
+static void disk_norm_point(const orc_disk_params *p, int x, int y, float *fx, float *fy)
+{
+    *fx = ((float)x - p->cx) * p->scale;
+    *fy = ((float)y - p->cy) * p->scale;
+}
+
+static void disk_denorm_point(const orc_disk_params *p, float fx, float fy, int *x, int *y)
+{
+    *x = (int)((fx / p->scale) + p->cx + 0.5f);
+    *y = (int)((fy / p->scale) + p->cy + 0.5f);
+}
+
+static void disk_polar(float kx, float ky, float *r, float *phi)
+{
+    *r = (float)sqrt((double)(kx * kx + ky * ky));
+    *phi = (float)atan2((double)ky, (double)kx);
+}
+
+static void disk_cart(float r, float phi, float *kx, float *ky)
+{
+    *kx = (float)((double)r * cos((double)phi));
+    *ky = (float)((double)r * sin((double)phi));
+}
+
+/* in/out: tl_x, tl_y (corners; become the transformed, centre-relative corners), out sizes;
+ * org_x/org_y receive the centre-relative original corners (org_bbox.x/y). */
+void orc_disk_reproj_plan(int n, int *tl_x, int *tl_y, const int *w, const int *h, int ansatz_x, int ansatz_y, float radius,
+                          int quadratic, int *out_w, int *out_h, int *org_x, int *org_y, orc_disk_params *P)
+{
+    int dim[6];
+    orc_pan_dimension(n, tl_x, tl_y, w, h, dim);
+    const int W = dim[0], H = dim[1], min_x = dim[2], min_y = dim[3];
+    ansatz_x = ansatz_x - (int)(W / 2 + 1);
+    ansatz_y = ansatz_y - (int)(H / 2 + 1);
+    float maxd = 0.f;
+    P->cx = (float)ansatz_x;
+    P->cy = (float)ansatz_y;
+    for (int i = 0; i < n; i++) {
+        tl_x[i] -= min_x + (int)(W / 2 + 1);
+        tl_y[i] -= min_y + (int)(H / 2 + 1);
+        const int px[4] = {tl_x[i], tl_x[i] + w[i], tl_x[i] + w[i], tl_x[i]};
+        const int py[4] = {tl_y[i], tl_y[i], tl_y[i] + h[i], tl_y[i] + h[i]};
+        for (int k = 0; k < 4; k++) {
+            float dx = (float)px[k] - P->cx, dy = (float)py[k] - P->cy;
+            float d = sqrtf(dx * dx + dy * dy);
+            if (d > maxd) maxd = d;
+        }
+    }
+    P->scale = (maxd == 0.0f) ? 1.0f : 1.0f / maxd;
+    P->quadratic = quadratic;
+    {
+        float fx, fy;
+        disk_norm_point(P, ansatz_x, ansatz_y + (int)radius, &fx, &fy);
+        P->radius_n = (float)sqrt((double)(fx * fx + fy * fy));
+    }
+    const int N = 1000; /* sten_proj::precision */
+    for (int i = 0; i < n; i++) {
+        /* boundingRect of the 4 integer corners is (cols+1) x (rows+1); x,y reset to the corner */
+        const int bx = tl_x[i], by = tl_y[i], bw = w[i] + 1, bh = h[i] + 1;
+        org_x[i] = bx;
+        org_y[i] = by;
+        const int perimeter = 2 * (bw + bh);
+        const float ppu = (float)N / perimeter;
+        const int top = (int)(bw * ppu), right = (int)(bh * ppu);
+        int minx = INT_MAX, miny = INT_MAX, maxx = INT_MIN, maxy = INT_MIN;
+        for (int side = 0; side < 4; side++) {
+            const int cnt = (side % 2 == 0) ? top : right;
+            const float step = (side % 2 == 0) ? (float)bw / (cnt + 1) : (float)bh / (cnt + 1);
+            for (int k = 1; k <= cnt; k++) {
+                int qx, qy;
+                const int d = (int)(k * step);
+                if (side == 0) { qx = bx + d; qy = by; }
+                else if (side == 1) { qx = bx + bw; qy = by + d; }
+                else if (side == 2) { qx = bx + bw - d; qy = by + bh; }
+                else { qx = bx; qy = by + bh - d; }
+                float fx, fy, r, phi;
+                disk_norm_point(P, qx, qy, &fx, &fy);
+                disk_polar(fx, fy, &r, &phi);
+                float e = quadratic ? r * r : r;
+                if (e > P->radius_n) r = (e - P->radius_n) / (1 - P->radius_n);
+                disk_cart(r, phi, &fx, &fy);
+                disk_denorm_point(P, fx, fy, &qx, &qy);
+                if (qx < minx) minx = qx;
+                if (qy < miny) miny = qy;
+                if (qx > maxx) maxx = qx;
+                if (qy > maxy) maxy = qy;
+            }
+        }
+        tl_x[i] = minx;
+        tl_y[i] = miny;
+        out_w[i] = maxx - minx + 1;
+        out_h[i] = maxy - miny + 1;
+    }
+}
+
+/* one tile: dst (dw x dh at centre-relative corner (dx0,dy0)) gathers from src (sw x sh at (ox,oy)) */
+void orc_disk_reproj_tile(const orc_disk_params *P, const uint8_t *src, int sw, int sh, size_t sstep, int ox, int oy,
+                          uint8_t *dst, int dw, int dh, size_t dstep, int dx0, int dy0)
+{
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++) {
+            float fx, fy, r, phi;
+            disk_norm_point(P, x + dx0, y + dy0, &fx, &fy);
+            disk_polar(fx, fy, &r, &phi);
+            float e;
+            int sub;
+            if (P->quadratic) { e = r * r; sub = 2; }
+            else { e = r; sub = 1; }
+            r = e * (sub - P->radius_n) + P->radius_n;
+            disk_cart(r, phi, &fx, &fy);
+            int qx, qy;
+            disk_denorm_point(P, fx, fy, &qx, &qy);
+            qx -= ox;
+            qy -= oy;
+            uint8_t *D = dst + (size_t)y * dstep + (size_t)x * 3;
+            if (qx >= 0 && qx < sw && qy >= 0 && qy < sh) {
+                const uint8_t *S = src + (size_t)qy * sstep + (size_t)qx * 3;
+                D[0] = S[0]; D[1] = S[1]; D[2] = S[2];
+            } else {
+                D[0] = D[1] = D[2] = 0;
+            }
+        }
+}

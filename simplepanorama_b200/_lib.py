@@ -47,6 +47,10 @@ SYMBOLS = {
     "spano_remap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_surrounding_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_apply_gain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double]),
+    "spano_disk_reproj_size": (C.c_int, [C.c_void_p, C.c_int, c_intp, c_intp, c_intp, c_intp, C.c_int, C.c_int, C.c_float,
+                                         C.c_int, c_intp, c_intp, c_intp, c_intp]),
+    "spano_disk_reproj": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_intp, c_intp, c_intp, c_intp, C.c_int, C.c_int,
+                                    C.c_float, C.c_int, c_u8pp, c_sizep, c_u8pp, c_sizep]),
     "spano_multiblend": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_u8pp, c_sizep, c_u8pp, c_sizep, c_intp, c_intp,
                                    c_intp, c_intp, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_composite": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int, C.POINTER(ImageDesc), C.c_int, C.c_double,

@@ -302,6 +302,44 @@ def blend(images, masks, masks_orig, top_lefts, bands: int, sigma: float, ctx: C
     return _blend_call(images, masks, masks_orig, top_lefts, bands, sigma, OUT_U8, ctx)
 
 
+def disk_reproj_size(corners, sizes, ansatz, radius: float, quadratic: bool = True, ctx: Context | None = None):
+    """Geometry of sten_proj::disk_reproj: the new (canvas-centre-relative) corners and sizes of every
+    tile for the circle (ansatz, radius) that sten_proj::estimate_circle returned.  Host arithmetic."""
+    n = len(sizes)
+    if n == 0 or n != len(corners):
+        raise SpanoError(_lib.E_INVALID, "Input consistency!")
+    tlx = np.array([c[0] for c in corners], np.int32); tly = np.array([c[1] for c in corners], np.int32)
+    w = np.array([s[0] for s in sizes], np.int32); h = np.array([s[1] for s in sizes], np.int32)
+    ox = np.zeros(n, np.int32); oy = np.zeros(n, np.int32); ow = np.zeros(n, np.int32); oh = np.zeros(n, np.int32)
+    lib = ctx.lib if ctx is not None else _lib.load()
+    rc = lib.spano_disk_reproj_size(ctx.h if ctx is not None else None, n, _ip(tlx), _ip(tly), _ip(w), _ip(h),
+                                    int(ansatz[0]), int(ansatz[1]), C.c_float(radius), int(bool(quadratic)),
+                                    _ip(ox), _ip(oy), _ip(ow), _ip(oh))
+    if rc != 0:
+        raise SpanoError(rc, "spano_disk_reproj_size failed")
+    return [(int(a), int(b)) for a, b in zip(ox, oy)], [(int(a), int(b)) for a, b in zip(ow, oh)]
+
+
+def disk_reproj(pd: "ProjData", ansatz, radius: float, quadratic: bool = True, ctx: Context | None = None) -> "ProjData":
+    """sten_proj::disk_reproj(proj_data, quadratic) with the circle forced to (ansatz, radius):
+    returns the re-projected tiles, their new corners and recomputed validity masks."""
+    ctx = ctx or default_context()
+    n = len(pd.imgs)
+    tiles = [_u8img(t, 3, f"imgs[{i}]") for i, t in enumerate(pd.imgs)]
+    sizes = [(t.shape[1], t.shape[0]) for t in tiles]
+    new_corners, new_sizes = disk_reproj_size(pd.corners, sizes, ansatz, radius, quadratic, ctx)
+    outs = [np.empty((h, w, 3), np.uint8) for (w, h) in new_sizes]
+    msks = [np.empty((h, w), np.uint8) for (w, h) in new_sizes]
+    tlx = np.array([c[0] for c in pd.corners], np.int32); tly = np.array([c[1] for c in pd.corners], np.int32)
+    w = np.array([s[0] for s in sizes], np.int32); h = np.array([s[1] for s in sizes], np.int32)
+    ptr = lambda arrs: (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    steps = lambda arrs: (C.c_size_t * n)(*[a.strides[0] for a in arrs])
+    ctx.check(ctx.lib.spano_disk_reproj(ctx.h, n, ptr(tiles), steps(tiles), _ip(tlx), _ip(tly), _ip(w), _ip(h),
+                                        int(ansatz[0]), int(ansatz[1]), C.c_float(radius), int(bool(quadratic)),
+                                        ptr(outs), steps(outs), ptr(msks), steps(msks)))
+    return ProjData(imgs=outs, msks=msks, corners=new_corners)
+
+
 def plan_tiles(images, R, K, kind: int, focal: float, ctx: Context | None = None):
     """Geometry of every warped tile without warping: list of (K32, R32, (tl_x, tl_y), (w, h))."""
     plan = []

@@ -479,6 +479,64 @@ extern "C" int spano_apply_gain(spano_ctx *ctx, uint8_t *bgr, int w, int h, size
     return SPANO_OK;
 }
 
+extern "C" int spano_disk_reproj_size(spano_ctx *ctx, int n, const int *tl_x, const int *tl_y, const int *w, const int *h,
+                                      int ansatz_x, int ansatz_y, float radius, int quadratic, int *out_tl_x,
+                                      int *out_tl_y, int *out_w, int *out_h)
+{
+    if (n <= 0 || !tl_x || !tl_y || !w || !h || !out_tl_x || !out_tl_y || !out_w || !out_h)
+        return spano_fail(ctx, SPANO_E_INVALID, "spano_disk_reproj_size: null/empty argument");
+    for (int i = 0; i < n; ++i)
+        if (w[i] <= 0 || h[i] <= 0) return spano_fail(ctx, SPANO_E_INVALID, "tile %d is empty", i);
+    SpanoDiskParams P;
+    std::vector<int> ox(n), oy(n);
+    if (spano_disk_plan(n, tl_x, tl_y, w, h, ansatz_x, ansatz_y, radius, quadratic, &P, ox.data(), oy.data(), out_tl_x,
+                        out_tl_y, out_w, out_h))
+        return spano_fail(ctx, SPANO_E_LIMIT, "degenerate tile in disk_reproj (no border samples)");
+    return SPANO_OK;
+}
+
+extern "C" int spano_disk_reproj(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps,
+                                 const int *tl_x, const int *tl_y, const int *w, const int *h, int ansatz_x, int ansatz_y,
+                                 float radius, int quadratic, uint8_t *const *out_tiles, const size_t *out_steps,
+                                 uint8_t *const *out_masks, const size_t *out_mask_steps)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (n <= 0 || !tiles || !tile_steps || !tl_x || !tl_y || !w || !h || !out_tiles || !out_steps)
+        return spano_fail(ctx, SPANO_E_INVALID, "spano_disk_reproj: null/empty argument");
+    for (int i = 0; i < n; ++i)
+        if (int rc = check_image_args(ctx, tiles[i], w[i], h[i], tile_steps[i], 3, "tile")) return rc;
+    SpanoDiskParams P;
+    std::vector<int> ox(n), oy(n), nx(n), ny(n), nw(n), nh(n);
+    if (spano_disk_plan(n, tl_x, tl_y, w, h, ansatz_x, ansatz_y, radius, quadratic, &P, ox.data(), oy.data(), nx.data(),
+                        ny.data(), nw.data(), nh.data()))
+        return spano_fail(ctx, SPANO_E_LIMIT, "degenerate tile in disk_reproj (no border samples)");
+    for (int i = 0; i < n; ++i) {
+        if (int rc = check_image_args(ctx, out_tiles[i], nw[i], nh[i], out_steps[i], 3, "output tile")) return rc;
+        if (int rc = check_remap_limits(ctx, w[i], h[i], nw[i], nh[i])) return rc;
+        const size_t s_step = align_up((size_t)w[i] * 3, 16), t_step = align_up((size_t)nw[i] * 3, 16), m_step = align_up((size_t)nw[i], 16);
+        uint8_t *d_src, *d_tile, *d_dark, *d_mask;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC, s_step * h[i] + 16, (void **)&d_src)) return rc;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, t_step * nh[i], (void **)&d_tile)) return rc;
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_src, s_step, tiles[i], tile_steps[i], (size_t)w[i] * 3, h[i], cudaMemcpyHostToDevice, ctx->stream));
+        int k = launch_disk_gather(ctx, P, d_src, w[i], h[i], s_step, ox[i], oy[i], d_tile, nw[i], nh[i], t_step, nx[i], ny[i]);
+        if (k < 0) return k;
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(out_tiles[i], out_steps[i], d_tile, t_step, (size_t)nw[i] * 3, nh[i], cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_masks && out_masks[i]) {
+            if (!out_mask_steps || out_mask_steps[i] < (size_t)nw[i]) return spano_fail(ctx, SPANO_E_INVALID, "output mask step too small");
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_DARK, m_step * nh[i], (void **)&d_dark)) return rc;
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILEMASK, m_step * nh[i], (void **)&d_mask)) return rc;
+            k = launch_dark_flags(ctx, d_tile, nw[i], nh[i], t_step, d_dark, m_step);
+            if (k < 0) return k;
+            k = launch_valid_mask(ctx, d_dark, nw[i], nh[i], m_step, 3, d_mask, m_step);
+            if (k < 0) return k;
+            SPANO_CUDA(ctx, cudaMemcpy2DAsync(out_masks[i], out_mask_steps[i], d_mask, m_step, (size_t)nw[i], nh[i], cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // staging buffers are reused by the next tile
+    }
+    return SPANO_OK;
+}
+
 extern "C" int spano_multiblend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps,
                                 const uint8_t *const *masks, const size_t *mask_steps,
                                 const uint8_t *const *masks_orig, const size_t *orig_steps, const int *tl_x,

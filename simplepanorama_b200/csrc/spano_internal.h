@@ -90,3 +90,14 @@ int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius,
 int launch_normalise(spano_ctx *ctx, const float4 *acc, int canvas_w, int rows, int bands, int out_kind, void *out,
                      size_t out_step);
 int launch_fp32_peak(spano_ctx *ctx, int variant, double *tflops);
+// disk_kernels.cu: stereographic centre fix (util::RadialNormalizer state + normalised radius)
+struct SpanoDiskParams {
+    float cx, cy, scale;
+    float radius_n;
+    int quadratic;
+};
+int spano_disk_plan(int n, const int *tl_x, const int *tl_y, const int *w, const int *h, int ansatz_x, int ansatz_y,
+                    float radius, int quadratic, SpanoDiskParams *P, int *org_x, int *org_y, int *new_x, int *new_y,
+                    int *new_w, int *new_h);
+int launch_disk_gather(spano_ctx *ctx, const SpanoDiskParams &P, const uint8_t *src, int sw, int sh, size_t sstep, int ox,
+                       int oy, uint8_t *dst, int dw, int dh, size_t dstep, int dx0, int dy0);

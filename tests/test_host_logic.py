@@ -99,3 +99,22 @@ def test_band_planner():
     # work-balanced: a tall, wide tile at the bottom pulls the cut downwards
     eq = dist.plan_row_bands([((0, 0), (10, 50)), ((0, 50), (1000, 50))], 2, 0, 100)
     assert eq[0][1] > 50
+
+
+def test_disk_reproj_geometry_matches_oracle(spano_lib, oracle):
+    """a5 host geometry (normaliser, normalised radius, stretched bounding boxes) == oracle restatement."""
+    from simplepanorama_b200 import api
+    rng = np.random.default_rng(9)
+    for trial in range(6):
+        n = int(rng.integers(1, 9))
+        sizes = [(int(rng.integers(40, 400)), int(rng.integers(40, 400))) for _ in range(n)]
+        corners = [(int(rng.integers(-300, 300)), int(rng.integers(-300, 300))) for _ in range(n)]
+        tiles = [np.zeros((h, w, 3), np.uint8) for (w, h) in sizes]
+        W, H, mx, my = oracle.pan_dimension(corners, sizes)
+        ansatz = (W // 2 + int(rng.integers(-20, 20)), H // 2 + int(rng.integers(-20, 20)))
+        radius = float(rng.uniform(5, 60))
+        for quad in (True, False):
+            new_c, new_s = api.disk_reproj_size(corners, sizes, ansatz, radius, quad, ctx=None)
+            outs, _, ocorners = oracle.disk_reproj(tiles, corners, ansatz, radius, quad, erode_iters=0)
+            assert new_c == ocorners
+            assert new_s == [(o.shape[1], o.shape[0]) for o in outs]

@@ -89,3 +89,47 @@ def test_single_tile_closed_form(oracle):
     G = [oracle.gaussian_blur(I, 43, math.sqrt(2 * (B - i) + 1) * sigma) for i in range(B)]
     expect = (I + G[0] + G[1] - 2 * G[B - 1]) / B / float(255 // B)
     assert np.allclose(out, expect, rtol=2e-5, atol=1e-6)
+
+
+def test_cubic_remap_on_integer_maps_is_a_gather(golden):
+    """a5 pin: sten_proj::disk_reproj hands cv::remap(INTER_CUBIC) integer-valued maps
+    (denormalizePoint returns cv::Point); OpenCV's result is then an exact pixel gather with
+    BORDER_CONSTANT(0) outside -- which is how the oracle and the CUDA kernel implement it."""
+    g = golden("cubic_gather.npz")
+    img, xm, ym, dst = g["cubic_img"], g["cubic_x"], g["cubic_y"], g["cubic_dst"]
+    H, W = img.shape[:2]
+    xi, yi = xm.astype(int), ym.astype(int)
+    ok = (xi >= 0) & (xi < W) & (yi >= 0) & (yi < H)
+    ref = np.zeros_like(dst)
+    ref[ok] = img[yi[ok], xi[ok]]
+    assert np.array_equal(ref, dst)
+
+
+def _stereo_tiles(oracle, scale=0.05, n_max=None):
+    from simplepanorama_b200 import synth
+    cfg = synth.config("cfg3", scale)
+    K, R, gains = synth.cameras(cfg)
+    tiles, corners = [], []
+    for j in range(cfg.n if n_max is None else n_max):
+        img = synth.make_image(cfg, j, 1.0)
+        K32, R32 = oracle.adjusted_camera(K[j], R[j], cfg.width, cfg.height)
+        tl, tile = oracle.warp(cfg.kind, np.float32(cfg.focal), K32, R32, img)
+        tiles.append(tile); corners.append(tl)
+    return tiles, corners
+
+
+def test_disk_reproj_oracle_properties(oracle):
+    """The centre fix pulls content towards the circle centre: a pixel well outside the circle keeps
+    its direction (same polar angle about the centre) and the tiles stay 8-bit gathers of the input."""
+    tiles, corners = _stereo_tiles(oracle, 0.04, 6)
+    sizes = [(t.shape[1], t.shape[0]) for t in tiles]
+    W, H, mx, my = oracle.pan_dimension(corners, sizes)
+    ansatz, radius = (W // 2 + 3, H // 2 - 2), 9.0
+    for quad in (True, False):
+        outs, msks, new_corners = oracle.disk_reproj(tiles, corners, ansatz, radius, quad)
+        assert len(outs) == len(tiles)
+        for t, o, m in zip(tiles, outs, msks):
+            assert o.dtype == np.uint8 and o.shape[:2] == m.shape
+            vals = set(map(tuple, o.reshape(-1, 3)[:: 37]))
+            src = set(map(tuple, t.reshape(-1, 3))) | {(0, 0, 0)}
+            assert vals <= src          # every output pixel is a copy of an input pixel (or border 0)
