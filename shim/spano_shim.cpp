@@ -1,0 +1,159 @@
+// spano_shim.cpp -- drop-in callee bodies for SimplePanorama's compositing path.
+//
+// Build this file INSTEAD of the bodies it names; the entry points in
+// src/classes/_panorama.cpp (stitch_parameters::set_config / get_preview / return_full / blend)
+// stay untouched and keep calling the same C++ signatures:
+//
+//   proj::spherical_proj::project, cylindrical_proj::project, sten_proj::project   src/math/_projection.cpp:27-84,297-324
+//   proj::get_proj_parameters                                                     src/math/_projection.cpp:422-454
+//   sten_proj::disk_reproj                                                        src/math/_projection.cpp:193-294
+//   blnd::createSurroundingMask                                                   src/math/_blending.cpp:278-324
+//   blnd::multi_blend                                                             src/math/_blending.cpp:186-252
+//
+// Each body only converts cv::Mat / Eigen arguments to pointers + sizes and forwards to the C ABI
+// (include/spano.h).  Errors come back as status codes and are re-thrown as std::runtime_error, the
+// exception type the reference already uses on this path (_blending.cpp:86); the worker thread's
+// try/catch (src/ui/_image_viewer.cpp:535-550) keeps working.
+//
+// NOT compiled in the build container (no OpenCV C++ headers / Eigen there); it needs the
+// reference's own include set.
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "_projection.h" // reference headers: proj::, blnd::, util::
+#include "_blending.h"
+#include "spano.h"
+
+namespace {
+
+// one context per thread: stitch_panorama/get_preview run on a worker thread, get_panorama on the GTK thread
+spano_ctx *ctx()
+{
+    thread_local struct Holder {
+        spano_ctx *c = nullptr;
+        Holder() { if (spano_create(&c, 0) != SPANO_OK) throw std::runtime_error("spano: no CUDA device (no CPU fallback)"); }
+        ~Holder() { spano_destroy(c); }
+    } h;
+    return h.c;
+}
+
+void check(int rc)
+{
+    if (rc != SPANO_OK) throw std::runtime_error(std::string("spano: ") + spano_last_error(ctx()));
+}
+
+struct Camera { float K[9], R[9]; };
+
+// K_adj = [f 0 w-cx; 0 f h-cy; 0 0 1] and R, both cast to float32 (what the reference hands to OpenCV)
+Camera adjusted(const Eigen::MatrixXd &R, const Eigen::MatrixXd &K, const cv::Mat &img)
+{
+    Camera c{};
+    const double f = K(0, 0);
+    const double k[9] = {f, 0, img.cols - K(0, 2), 0, f, img.rows - K(1, 2), 0, 0, 1};
+    for (int i = 0; i < 9; ++i) { c.K[i] = (float)k[i]; c.R[i] = (float)R(i / 3, i % 3); }
+    return c;
+}
+
+proj::warped warp_with(int kind, float focal, const Eigen::MatrixXd &R, const Eigen::MatrixXd &K, const cv::Mat &img, cv::Mat *mask)
+{
+    const Camera c = adjusted(R, K, img);
+    int x, y, w, h;
+    check(spano_warp_roi(ctx(), kind, focal, c.K, c.R, img.cols, img.rows, &x, &y, &w, &h));
+    proj::warped out;
+    out.imgs.create(h, w, CV_8UC3);
+    if (mask) mask->create(h, w, CV_8UC1);
+    check(spano_warp(ctx(), kind, focal, c.K, c.R, img.data, img.cols, img.rows, img.step, 1.0, out.imgs.data, out.imgs.step,
+                     mask ? mask->data : nullptr, mask ? mask->step : 0));
+    out.corners = cv::Point(x, y);
+    return out;
+}
+
+} // namespace
+
+namespace proj {
+
+// `focal` is the private member set by the constructor / change_focal (unchanged in _projection.h)
+warped spherical_proj::project(const Eigen::MatrixXd &R, const Eigen::MatrixXd &K, const cv::Mat &img) const
+{ return warp_with(SPANO_SPHERICAL, focal, R, K, img, nullptr); }
+warped cylindrical_proj::project(const Eigen::MatrixXd &R, const Eigen::MatrixXd &K, const cv::Mat &img) const
+{ return warp_with(SPANO_CYLINDRICAL, focal, R, K, img, nullptr); }
+warped sten_proj::project(const Eigen::MatrixXd &R, const Eigen::MatrixXd &K, const cv::Mat &img) const
+{ return warp_with(SPANO_STEREOGRAPHIC, focal, R, K, img, nullptr); }
+
+proj_data get_proj_parameters(const std::vector<cv::Mat> &images, std::vector<Eigen::MatrixXd> &R, std::vector<Eigen::MatrixXd> &K,
+                              std::vector<double> &con, std::shared_ptr<projection> projector, bool get_masks)
+{
+    proj_data out;
+    for (size_t i = 0; i < images.size(); ++i) {
+        if (!(con[i] > 0)) continue;
+        warped w = projector->project(R[i], K[i], images[i]);
+        if (get_masks) {
+            cv::Mat m(w.imgs.rows, w.imgs.cols, CV_8UC1);
+            check(spano_surrounding_mask(ctx(), w.imgs.data, w.imgs.cols, w.imgs.rows, w.imgs.step, 3, m.data, m.step));
+            out.msks.push_back(m);
+        }
+        out.imgs.push_back(w.imgs);
+        out.corners.push_back(w.corners);
+    }
+    return out;
+}
+
+void sten_proj::disk_reproj(proj_data &p, bool quadratic)
+{
+    const int n = (int)p.imgs.size();
+    std::vector<const uint8_t *> src(n);
+    std::vector<size_t> sstep(n), ostep(n), mstep(n);
+    std::vector<int> x(n), y(n), w(n), h(n), nx(n), ny(n), nw(n), nh(n);
+    for (int i = 0; i < n; ++i) {
+        src[i] = p.imgs[i].data; sstep[i] = p.imgs[i].step;
+        x[i] = p.corners[i].x; y[i] = p.corners[i].y; w[i] = p.imgs[i].cols; h[i] = p.imgs[i].rows;
+    }
+    check(spano_disk_reproj_size(ctx(), n, x.data(), y.data(), w.data(), h.data(), ansatz.x, ansatz.y, radius, quadratic,
+                                 nx.data(), ny.data(), nw.data(), nh.data()));
+    std::vector<cv::Mat> tiles(n), masks(n);
+    std::vector<uint8_t *> optr(n), mptr(n);
+    for (int i = 0; i < n; ++i) {
+        tiles[i].create(nh[i], nw[i], CV_8UC3); masks[i].create(nh[i], nw[i], CV_8UC1);
+        optr[i] = tiles[i].data; ostep[i] = tiles[i].step; mptr[i] = masks[i].data; mstep[i] = masks[i].step;
+    }
+    check(spano_disk_reproj(ctx(), n, src.data(), sstep.data(), x.data(), y.data(), w.data(), h.data(), ansatz.x, ansatz.y, radius,
+                            quadratic, optr.data(), ostep.data(), mptr.data(), mstep.data()));
+    p.msks.resize(n);
+    for (int i = 0; i < n; ++i) { p.imgs[i] = tiles[i]; p.msks[i] = masks[i]; p.corners[i] = cv::Point(nx[i], ny[i]); }
+}
+
+} // namespace proj
+
+namespace blnd {
+
+cv::Mat createSurroundingMask(const cv::Mat &img, bool invert, uchar /*thresholdValue == 1 at every call site*/)
+{
+    if (img.empty()) return cv::Mat();
+    cv::Mat m(img.rows, img.cols, CV_8UC1);
+    check(spano_surrounding_mask(ctx(), img.data, img.cols, img.rows, img.step, 0, m.data, m.step));
+    if (!invert) cv::bitwise_not(m, m);
+    return m;
+}
+
+cv::Mat multi_blend(const std::vector<cv::Mat> &images, const std::vector<cv::Mat> &masks, const std::vector<cv::Mat> &masks_orig,
+                    const std::vector<cv::Point> &top_lefts, int bands, double sigma)
+{
+    const int n = (int)images.size();
+    std::vector<const uint8_t *> t(n), c(n), v(n);
+    std::vector<size_t> ts(n), cs(n), vs(n);
+    std::vector<int> x(n), y(n), w(n), h(n);
+    for (int i = 0; i < n; ++i) {
+        t[i] = images[i].data; ts[i] = images[i].step; c[i] = masks[i].data; cs[i] = masks[i].step;
+        v[i] = masks_orig[i].data; vs[i] = masks_orig[i].step;
+        x[i] = top_lefts[i].x; y[i] = top_lefts[i].y; w[i] = images[i].cols; h[i] = images[i].rows;
+    }
+    int cw, ch, mx, my;
+    check(spano_pan_dimension(n, x.data(), y.data(), w.data(), h.data(), &cw, &ch, &mx, &my));
+    cv::Mat out(ch, cw, CV_32FC3);
+    check(spano_multiblend(ctx(), n, t.data(), ts.data(), c.data(), cs.data(), v.data(), vs.data(), x.data(), y.data(), w.data(),
+                           h.data(), bands, sigma, SPANO_OUT_F32, out.data, out.step));
+    return out;
+}
+
+} // namespace blnd

@@ -1,0 +1,90 @@
+"""CPU, world_size 2 (gloo): the multi-GPU plumbing of the row-band path -- band planning by tile-pixel
+work, per-rank band production and the gather of the finished 8-bit bands -- without a GPU.  The per-band
+compositor is injected (the oracle here; libspano on the GPU box, see
+test_gpu_parity.py::test_row_bands_equal_full_canvas for the CUDA side of the same property)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as tdist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _scene():
+    rng = np.random.default_rng(3)
+    sizes = [(120, 90), (100, 110), (90, 60), (70, 150)]
+    corners = [(0, 0), (80, 40), (150, -10), (30, 60)]
+    tiles = [rng.integers(16, 240, (h, w, 3), dtype=np.uint8) for (w, h) in sizes]
+    cuts = [(rng.random((h, w)) * 255).astype(np.uint8) for (w, h) in sizes]
+    valids = [np.full((h, w), 255, np.uint8) for (w, h) in sizes]
+    return tiles, cuts, valids, corners, sizes
+
+
+def _worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from simplepanorama_b200 import dist as sdist
+    tiles, cuts, valids, corners, sizes = _scene()
+    W, H, mx, my = orc.pan_dimension(corners, sizes)
+    bands = sdist.plan_row_bands(list(zip(corners, sizes)), world, my, H)
+    row0, row1 = bands[rank]
+    # the rank's band: here the oracle's canvas rows (every rank could compute only its rows; the oracle
+    # has no band mode, so it computes the canvas and keeps its slice)
+    full = orc.blend_to_u8(orc.multi_blend(tiles, cuts, valids, corners, 2, 7.0))
+    band = torch.from_numpy(np.ascontiguousarray(full[row0:row1]))
+    canvas = sdist.gather_bands(band, bands, W, rank, world)
+    if rank == 0:
+        assert canvas is not None and tuple(canvas.shape) == (H, W, 3)
+        np.save(out_path, canvas.numpy())
+        np.save(out_path + ".ref.npy", full)
+    else:
+        assert canvas is None
+    tdist.barrier()
+    tdist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_row_band_gather_world2(tmp_path):
+    world = 2
+    out = str(tmp_path / "canvas.npy")
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got, ref = np.load(out), np.load(out + ".ref.npy")
+    assert np.array_equal(got, ref)
+
+
+def test_bands_are_work_balanced():
+    sys.path.insert(0, ROOT)
+    from simplepanorama_b200 import dist as sdist, synth, api
+    cfg = synth.config("cfg4", 0.02)
+    K, R, _ = synth.cameras(cfg)
+    tiles = []
+    for j in range(cfg.n):
+        K32, R32 = api.adjusted_camera(K[j], R[j], cfg.width, cfg.height)
+        tiles.append(api.warp_roi(cfg.kind, cfg.focal, K32, R32, cfg.width, cfg.height, ctx=None))
+    W, H, mx, my = api.pan_dimension([t[0] for t in tiles], [t[1] for t in tiles])
+    for world in (2, 4, 8):
+        bands = sdist.plan_row_bands(tiles, world, my, H)
+        work = []
+        for (a, b) in bands:
+            tot = 0
+            for (tl, (w, h)) in tiles:
+                y0, y1 = max(a, tl[1] - my), min(b, tl[1] - my + h)
+                tot += max(0, y1 - y0) * w
+            work.append(tot)
+        assert max(work) / (sum(work) / world) < 1.05, (world, work)
