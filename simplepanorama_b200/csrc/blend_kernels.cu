@@ -37,6 +37,9 @@ constexpr int MAXR = SPANO_BLUR_RADIUS_MAX;
 
 // c_taps[b][k] = tap at distance k from the centre for band b's sigma (k = 0..radius)
 __constant__ float c_taps[MAXB][MAXR + 1];
+// radius-21 vertical pass, two output rows per packed FMA: c_tap2[b][d] = {T[d], T[d-1]} with T[d] = tap at
+// |d - 21| for d in 0..42 and T[-1] = T[43] = 0 (the tap pair that rows o, o+1 apply to input row o + d)
+__constant__ float2 c_tap2[MAXB][44];
 
 struct BlendParams {
     const uint8_t *tile;  size_t tile_step;
@@ -450,6 +453,16 @@ int launch_blend_setup(spano_ctx *ctx, int bands, double sigma)
         for (int k = 0; k <= radius; ++k) host[i][k] = full[radius + k];
     }
     SPANO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_taps, host, sizeof(host), 0, cudaMemcpyHostToDevice, ctx->stream));
+    if (radius == 21) {
+        float2 pairs[MAXB][44] = {};
+        for (int i = 0; i < bands; ++i)
+            for (int d = 0; d <= 43; ++d) {
+                const float hi = d <= 42 ? host[i][d < 21 ? 21 - d : d - 21] : 0.f;
+                const float lo = d >= 1 ? host[i][(d - 1) < 21 ? 21 - (d - 1) : (d - 1) - 21] : 0.f;
+                pairs[i][d] = make_float2(hi, lo);
+            }
+        SPANO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tap2, pairs, sizeof(pairs), 0, cudaMemcpyHostToDevice, ctx->stream));
+    }
     return radius;
 }
 

@@ -68,6 +68,19 @@ __device__ __forceinline__ uint32_t ldg_u8(const uint8_t *p)
     return v;
 }
 
+// Blackwell packed FP32: one FFMA2 issues two FMAs.  acc.{lo,hi} += v.{lo,hi} * s   (s broadcast)
+__device__ __forceinline__ void ffma2_vs(unsigned long long &acc, float v_lo, float v_hi, float s)
+{
+    asm("{ .reg .b64 vb, sb; mov.b64 vb, {%1,%2}; mov.b64 sb, {%3,%3}; fma.rn.f32x2 %0, vb, sb, %0; }"
+        : "+l"(acc) : "f"(v_lo), "f"(v_hi), "f"(s));
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v)
+{
+    float2 r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+
 __device__ __forceinline__ int reflect_idx(int p, int len)
 {
     if ((unsigned)p < (unsigned)len) return p;
@@ -108,20 +121,31 @@ __device__ __forceinline__ void row_pass_item(const float *raw, float *rowbuf, i
         const float4 s = src[q];
         v[4 * q] = s.x; v[4 * q + 1] = s.y; v[4 * q + 2] = s.z; v[4 * q + 3] = s.w;
     }
-    float out[B][4];
+    // outputs j, j+1 share one packed FMA per tap: acc2 += {pair_j[k], pair_{j+1}[k]} * tap[b][k]
+    unsigned long long acc2[B][2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float pair[R + 1];
-        pair[0] = v[j + R];
+    for (int jp = 0; jp < 2; ++jp) {
+        float plo[R + 1], phi[R + 1];
+        plo[0] = v[2 * jp + R];
+        phi[0] = v[2 * jp + 1 + R];
 #pragma unroll
-        for (int k = 1; k <= R; ++k) pair[k] = v[j + R - k] + v[j + R + k];
+        for (int k = 1; k <= R; ++k) {
+            plo[k] = v[2 * jp + R - k] + v[2 * jp + R + k];
+            phi[k] = v[2 * jp + 1 + R - k] + v[2 * jp + 1 + R + k];
+        }
 #pragma unroll
         for (int b = 0; b < B; ++b) {
-            float a = c_taps[b][0] * pair[0];
+            unsigned long long a = 0ull;
 #pragma unroll
-            for (int k = 1; k <= R; ++k) a = fmaf(c_taps[b][k], pair[k], a);
-            out[b][j] = a;
+            for (int k = 0; k <= R; ++k) ffma2_vs(a, plo[k], phi[k], c_taps[b][k]);
+            acc2[b][jp] = a;
         }
+    }
+    float out[B][4];
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        const float2 q0 = unpack2(acc2[b][0]), q1 = unpack2(acc2[b][1]);
+        out[b][0] = q0.x; out[b][1] = q0.y; out[b][2] = q1.x; out[b][3] = q1.y;
     }
     float *dst = rowbuf + (size_t)ch * C::PLANE_STRIDE + (slot_row0 + i) * SW + 4 * g;
 #pragma unroll
@@ -129,16 +153,15 @@ __device__ __forceinline__ void row_pass_item(const float *raw, float *rowbuf, i
         *reinterpret_cast<float4 *>(dst + (size_t)(b * 4) * C::PLANE_STRIDE) = make_float4(out[b][0], out[b][1], out[b][2], out[b][3]);
 }
 
-// vertical pass of one sigma (run-time b, taps in registers so the code exists once and stays in the
-// instruction cache): 50 rows of one plane column -> 8 outputs
+// vertical pass of one sigma: 50 rows of one plane column -> 8 outputs.  Output rows (o, o+1) take one
+// packed FMA per input row: {res[o], res[o+1]} += {T[d], T[d-1]} * val with d = i - o; the tap pairs come
+// from constant memory through uniform registers (tp is warp-uniform), val is the broadcast scalar.
 template <int SW>
-__device__ __forceinline__ void vertical_one(const float *col /* plane + x */, const float *tp, int chunk0, float (&res)[STEP])
+__device__ __forceinline__ void vertical_one(const float *col /* plane + x */, const float2 *tp, int chunk0, float (&res)[STEP])
 {
-    float tap[R + 1];
+    unsigned long long acc[STEP / 2];
 #pragma unroll
-    for (int j = 0; j <= R; ++j) tap[j] = tp[j];
-#pragma unroll
-    for (int o = 0; o < STEP; ++o) res[o] = 0.f;
+    for (int p = 0; p < STEP / 2; ++p) acc[p] = 0ull;
 #pragma unroll
     for (int c = 0; c < NCHUNK; ++c) {
         int slot = chunk0 + c;
@@ -150,12 +173,21 @@ __device__ __forceinline__ void vertical_one(const float *col /* plane + x */, c
             if (i < STEP + 2 * R) {
                 const float val = p[j * SW];
 #pragma unroll
-                for (int o = 0; o < STEP; ++o) {
-                    const int d = i - o;                // tap index 0..42
-                    if (d >= 0 && d <= 2 * R) res[o] = fmaf(tap[d < R ? R - d : d - R], val, res[o]);
+                for (int q = 0; q < STEP / 2; ++q) {
+                    const int d = i - 2 * q;            // tap index of output row 2q (2q+1 uses d-1)
+                    if (d >= 0 && d <= 2 * R + 1) {
+                        const float2 t = tp[d];
+                        ffma2_vs(acc[q], t.x, t.y, val);
+                    }
                 }
             }
         }
+    }
+#pragma unroll
+    for (int q = 0; q < STEP / 2; ++q) {
+        const float2 r = unpack2(acc[q]);
+        res[2 * q] = r.x;
+        res[2 * q + 1] = r.y;
     }
 }
 
@@ -255,7 +287,7 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
             for (int b = 0; b < B; ++b) {
                 if (b / C::HB == vg) {
                     float res[STEP];
-                    vertical_one<SW>(rowbuf + (size_t)(b * 4 + vch) * C::PLANE_STRIDE + vx, c_taps[b], chunk0, res);
+                    vertical_one<SW>(rowbuf + (size_t)(b * 4 + vch) * C::PLANE_STRIDE + vx, c_tap2[b], chunk0, res);
                     float *gp = G + (size_t)(b * 4 + vch) * STEP * SW + vx;
 #pragma unroll
                     for (int o = 0; o < STEP; ++o) gp[o * SW] = res[o];
