@@ -102,8 +102,11 @@ __device__ __forceinline__ uint32_t fetch_raw(const Params &P, const int *xtab, 
     const int i = t & (STEP - 1), ch = t >> 3;
     const int y = reflect_idx(yrow0 + i, P.h);
     const int x = xtab[c];
-    if (ch == 0) return ldg_u8(P.cut + (size_t)y * P.cut_step + x);
-    return ldg_u8(P.tile + (size_t)y * P.tile_step + (size_t)x * 3 + (ch - 1));
+    // one load through a selected address (two predicated loads into one register would serialise
+    // on the first one's latency)
+    const uint8_t *pc = P.cut + (size_t)y * P.cut_step + x;
+    const uint8_t *pt = P.tile + (size_t)y * P.tile_step + (size_t)x * 3 + (ch - 1);
+    return ldg_u8(ch == 0 ? pc : pt);
 }
 
 // horizontal pass of one item (row i of channel ch, 4 columns) of the staged chunk -> circular buffer slot
