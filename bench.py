@@ -223,7 +223,34 @@ def run_ours(args):
     lib = ctx.lib
     import ctypes as C
 
+    # N > 1: validity masks are a whole-tile property (flood fill), so they are computed tile-sharded
+    # (rank r owns tiles j = r mod N) and all-gathered (1 B/px, the one real exchange step of the
+    # path); every rank then warps only the tile rows its band reads.
+    all_masks = my_seg = None
+    owned = []
+    if world > 1:
+        owner = [j % world for j in range(cfg.n)]
+        seg_fill = [0] * world
+        offs = []
+        for j, (w, h) in enumerate(wl["sizes"]):
+            offs.append(seg_fill[owner[j]])
+            seg_fill[owner[j]] += (w * h + 255) // 256 * 256
+        seg_max = max(seg_fill)
+        all_masks = torch.empty(world * seg_max, dtype=torch.uint8, device=dev)
+        my_seg = all_masks[rank * seg_max:(rank + 1) * seg_max]
+        for j, (w, h) in enumerate(wl["sizes"]):
+            descs_dev[j].valid_mask = all_masks.data_ptr() + owner[j] * seg_max + offs[j]
+            descs_dev[j].valid_mask_step = w
+            if owner[j] == rank:
+                owned.append(j)
+
     def step_dev():
+        if world > 1:
+            for j in owned:
+                d = descs_dev[j]
+                ctx.check(lib.spano_dev_tile_mask(ctx.h, cfg.kind, C.c_float(cfg.focal), d.K, d.R, d.src_bgr, d.src_w, d.src_h,
+                                                  d.src_step, d.tl_x, d.tl_y, d.w, d.h, d.valid_mask, d.valid_mask_step))
+            tdist.all_gather_into_tensor(all_masks, my_seg.clone())
         if row1 > row0:
             ctx.check(lib.spano_dev_composite(ctx.h, cfg.kind, C.c_float(cfg.focal), cfg.n, descs_dev, cfg.bands, cfg.sigma,
                                               row0, row1, d_canvas.data_ptr(), d_canvas.stride(0)))

@@ -158,6 +158,12 @@ typedef struct spano_image_desc {
     const uint8_t *mask_cut;   /* w x h, 8UC1 */
     size_t mask_cut_step;
     int tl_x, tl_y, w, h;      /* from spano_warp_roi */
+    /* Optional (spano_dev_composite only): the tile's validity mask computed beforehand with
+     * spano_dev_tile_mask (w x h, 8UC1, device pointer).  When set, the flood fill is skipped and only
+     * the tile rows the band needs are warped -- this is what lets the warp + mask stages shard across
+     * GPUs: masks are a whole-tile property, so ranks compute them for disjoint tiles and all-gather them. */
+    const uint8_t *valid_mask;
+    size_t valid_mask_step;
 } spano_image_desc;
 
 int spano_composite(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *images, int bands,
@@ -170,6 +176,10 @@ int spano_dev_composite(spano_ctx *ctx, int proj, float scale, int n, const span
                         double sigma, int row0, int row1, uint8_t *canvas, size_t canvas_step);
 
 /* ---- device-pointer stage entry points (asynchronous on the context's stream) -------- */
+/* Validity mask of one warped tile without keeping the tile (a3 sampling + a4), DEVICE pointers. */
+int spano_dev_tile_mask(spano_ctx *ctx, int proj, float scale, const float K[9], const float R[9], const uint8_t *src_bgr,
+                        int src_w, int src_h, size_t src_step, int tl_x, int tl_y, int w, int h, uint8_t *valid_mask,
+                        size_t mask_step);
 int spano_dev_warp(spano_ctx *ctx, int proj, float scale, const float K[9], const float R[9], const uint8_t *src_bgr,
                    int src_w, int src_h, size_t src_step, double gain, int tl_x, int tl_y, int dst_w, int dst_h,
                    uint8_t *dst_bgr, size_t dst_step, uint8_t *dst_valid_mask, size_t mask_step);

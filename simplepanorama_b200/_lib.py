@@ -27,6 +27,7 @@ class ImageDesc(C.Structure):
         ("K", C.c_float * 9), ("R", C.c_float * 9), ("gain", C.c_double),
         ("mask_cut", C.c_void_p), ("mask_cut_step", C.c_size_t),
         ("tl_x", C.c_int), ("tl_y", C.c_int), ("w", C.c_int), ("h", C.c_int),
+        ("valid_mask", C.c_void_p), ("valid_mask_step", C.c_size_t),
     ]
 
 
@@ -57,6 +58,8 @@ SYMBOLS = {
                                   C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_dev_composite": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int, C.POINTER(ImageDesc), C.c_int, C.c_double,
                                       C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "spano_dev_tile_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_float, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_dev_warp": (C.c_int, [C.c_void_p, C.c_int, C.c_float, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
                                  C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "spano_dev_multiblend": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_u8pp, c_sizep, c_u8pp, c_sizep, c_intp, c_intp,

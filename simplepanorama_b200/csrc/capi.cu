@@ -337,6 +337,22 @@ extern "C" int spano_dev_warp(spano_ctx *ctx, int proj, float scale, const float
                          dst_valid_mask, mask_step);
 }
 
+extern "C" int spano_dev_tile_mask(spano_ctx *ctx, int proj, float scale, const float K[9], const float R[9],
+                                   const uint8_t *src_bgr, int src_w, int src_h, size_t src_step, int tl_x, int tl_y, int w,
+                                   int h, uint8_t *valid_mask, size_t mask_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (!K || !R) return spano_fail(ctx, SPANO_E_INVALID, "spano_dev_tile_mask: null K/R");
+    if (int rc = valid_proj(ctx, proj, scale)) return rc;
+    if (int rc = check_image_args(ctx, src_bgr, src_w, src_h, src_step, 3, "source")) return rc;
+    if (int rc = check_image_args(ctx, valid_mask, w, h, mask_step, 1, "mask")) return rc;
+    if (int rc = check_remap_limits(ctx, src_w, src_h, w, h)) return rc;
+    SpanoProjector P;
+    spano_host_set_camera(&P, proj, scale, K, R);
+    return dev_warp_tile(ctx, P, src_bgr, src_w, src_h, src_step, 1.0, tl_x, tl_y, w, h, nullptr, 0, valid_mask, mask_step);
+}
+
 extern "C" int spano_dev_multiblend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps,
                                     const uint8_t *const *masks, const size_t *mask_steps,
                                     const uint8_t *const *masks_orig, const size_t *orig_steps, const int *tl_x,
@@ -684,11 +700,29 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
             src = d_srcbuf[b];  s_step = align_up((size_t)im[j].src_w * 3, 16);
             cut = d_cutbuf[b];  c_step = m_step;
         }
-        if (int rc = dev_warp_tile(ctx, P, src, im[j].src_w, im[j].src_h, s_step, im[j].gain, im[j].tl_x, im[j].tl_y, im[j].w, im[j].h,
-                                   d_tile, t_step, d_valid, m_step))
+        const uint8_t *valid = d_valid;
+        size_t v_step = m_step;
+        if (!host && im[j].valid_mask) {
+            // mask supplied (computed elsewhere for the whole tile): warp only the rows this band reads --
+            // its own rows plus the blur radius, which BORDER_REFLECT keeps inside the tile
+            if (im[j].valid_mask_step < (size_t)im[j].w) return spano_fail(ctx, SPANO_E_INVALID, "valid_mask step too small");
+            valid = im[j].valid_mask;
+            v_step = im[j].valid_mask_step;
+            const int cy = im[j].tl_y - my;
+            int r0 = std::max(0, row0 - cy) - radius, r1 = std::min(im[j].h, row1 - cy) + radius;
+            if (im[j].h < 4 * radius) { r0 = 0; r1 = im[j].h; }     // several reflections possible: keep it simple
+            r0 = std::max(0, r0);
+            r1 = std::min(im[j].h, r1);
+            StageTimer t0(ctx, 0);
+            int kk = launch_warp(ctx, P, src, im[j].src_w, im[j].src_h, s_step, im[j].gain, im[j].tl_x, im[j].tl_y, im[j].w, im[j].h,
+                                 r0, r1, d_tile, t_step, nullptr, 0);
+            if (kk < 0) return kk;
+            t0.stop(kk);
+        } else if (int rc = dev_warp_tile(ctx, P, src, im[j].src_w, im[j].src_h, s_step, im[j].gain, im[j].tl_x, im[j].tl_y, im[j].w,
+                                          im[j].h, d_tile, t_step, d_valid, m_step))
             return rc;
         StageTimer t2(ctx, 2);
-        const BlendTile bt{d_tile, t_step, cut, c_step, d_valid, m_step, im[j].w, im[j].h, im[j].tl_x - mx, im[j].tl_y - my};
+        const BlendTile bt{d_tile, t_step, cut, c_step, valid, v_step, im[j].w, im[j].h, im[j].tl_x - mx, im[j].tl_y - my};
         int k = launch_blend_tile(ctx, bt, bands, radius, acc, cw, row0, row1);
         if (k < 0) return k;
         t2.stop(k);

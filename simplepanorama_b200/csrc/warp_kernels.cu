@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(WARP_BLOCK_X *WARP_BLOCK_Y) warp_kernel(const 
     }
     uint8_t *drow = P.dst + (size_t)v * P.dst_step + (size_t)x0 * 3;
     const bool full = x0 + WARP_PX_PER_THREAD <= P.dst_w;
-    if (full && (((uintptr_t)drow) & 3) == 0) {
+    if (!P.dst) {
+        // flags-only pass (validity masks computed on another rank's behalf): no tile store
+    } else if (full && (((uintptr_t)drow) & 3) == 0) {
         // 4 px = 12 B = three 32-bit words; a warp writes 384 contiguous bytes
         uint32_t *q = reinterpret_cast<uint32_t *>(drow);
         q[0] = px[0] | (px[1] << 24);

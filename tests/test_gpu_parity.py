@@ -337,3 +337,41 @@ def test_errors(ctx):
         api.remap(np.zeros((4, 40000, 3), np.uint8), np.zeros((2, 2), np.float32), np.zeros((2, 2), np.float32), ctx)
     # the context survives errors
     assert api.apply_gain(t + 10, 2.0, ctx)[0, 0, 0] == 5
+
+
+def test_band_composite_with_supplied_masks(ctx):
+    """Multi-GPU data path on one GPU: validity masks computed per tile with spano_dev_tile_mask (as the
+    owning rank would), handed to spano_dev_composite, which then warps only the rows each band reads.
+    Every band must equal the corresponding rows of the ordinary full-canvas result, bit for bit."""
+    import ctypes as C
+    import torch
+    from simplepanorama_b200 import api, dist
+    cfg, K, R, gains, images, cuts = _fused_case("cfg1", 0.25)
+    full = api.return_full(images, R, K, cfg.kind, cfg.focal, gains, cuts, cfg.bands, cfg.sigma, ctx=ctx)
+    plan = api.plan_tiles(images, R, K, cfg.kind, cfg.focal)
+    W, H, mx, my = api.pan_dimension([p[2] for p in plan], [p[3] for p in plan])
+    dev = torch.device("cuda", 0)
+    d_img = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in images]
+    d_cut = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in cuts]
+    d_val = [torch.zeros((p[3][1], p[3][0]), dtype=torch.uint8, device=dev) for p in plan]
+    torch.cuda.synchronize()
+    descs = api.make_descs(d_img, plan, gains, d_cut, lambda t: t.data_ptr(), lambda t: t.stride(0))
+    lib = ctx.lib
+    for j in range(cfg.n):
+        d = descs[j]
+        ctx.check(lib.spano_dev_tile_mask(ctx.h, cfg.kind, C.c_float(cfg.focal), d.K, d.R, d.src_bgr, d.src_w, d.src_h, d.src_step,
+                                          d.tl_x, d.tl_y, d.w, d.h, d_val[j].data_ptr(), d_val[j].stride(0)))
+        d.valid_mask = d_val[j].data_ptr()
+        d.valid_mask_step = d_val[j].stride(0)
+    for world in (1, 3, 7):
+        bands = dist.plan_row_bands([(p[2], p[3]) for p in plan], world, my, H)
+        parts = []
+        for (a, b) in bands:
+            if b <= a:
+                continue
+            out = torch.empty((b - a, W, 3), dtype=torch.uint8, device=dev)
+            ctx.check(lib.spano_dev_composite(ctx.h, cfg.kind, C.c_float(cfg.focal), cfg.n, descs, cfg.bands, cfg.sigma, a, b,
+                                              out.data_ptr(), out.stride(0)))
+            ctx.sync()
+            parts.append(out.cpu().numpy())
+        assert np.array_equal(np.concatenate(parts, axis=0), full), world
