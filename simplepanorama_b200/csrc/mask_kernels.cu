@@ -2,26 +2,30 @@
 //
 // Replaces blnd::createSurroundingMask(img, true, 1) + cv::erode(mask, Mat(), (-1,-1), 3)
 // (reference src/math/_blending.cpp:278-324, src/math/_projection.cpp:441-443, 287-288):
-//   dark  = gray(BGR) <= 1                      (flag produced by the warp kernel)
+//   dark  = gray(BGR) <= 1                      (flag produced by the warp kernel, 1 byte/px)
 //   out   = 4-connected component of `dark` that touches the tile border (the reference
 //           flood-fills from every border pixel with cv::floodFill)
 //   mask  = 255 everywhere except `out`; then three 3x3 erosions with OpenCV's default
 //           morphology border (+inf)  ==  one (2*3+1)^2 minimum that ignores out-of-image taps.
-//           Done on a 1-bit-per-pixel image of `out` (ballot-packed): vertical OR of the window rows,
-//           horizontal dilation by shifts, 32 output pixels per thread as two 16-byte stores.
 //
 // The flood fill is a whole-tile property, so it is computed as a parallel union-find
 // (label equivalence) over the dark pixels with one virtual node for "the border":
 //   node 0 = border, node p+1 = pixel p.  Links always point to a smaller id, so node 0 is
-//   the root of everything that reaches the border.  Runs of dark pixels inside a 32-px warp
-//   segment start out already linked to their run start (one ballot), and a vertical link is
-//   attempted only where a run of vertical adjacency begins, which removes most atomics.
+//   the root of everything that reaches the border.
+// Every thread owns a group of 16 consecutive pixels of one row (one 16-byte load of flags, packed
+// to a 16-bit word with a multiply); bright groups -- almost all of a tile -- cost one load and one
+// compare.  Runs of dark pixels inside a group start out linked to their run start, horizontal
+// links are only needed across group boundaries, and a vertical link is attempted only where a run of
+// vertical adjacency begins, which removes most atomics.
+// The result is packed to 1 bit/px; the erosion is a vertical OR of the window rows + shifts,
+// 32 output pixels per thread written as two 16-byte stores.
 // Integer work; results are bit-exact with the reference by construction.
-// HBM traffic: 1 B (dark) + 4 B labels written, ~2x4 B labels re-read, 1 B mask written per px.
+// HBM traffic per tile pixel: 3 x 1 B flag reads, 1 B mask write, 4 B label traffic per DARK pixel.
 #include "spano_internal.h"
 
 namespace {
 
+constexpr int GPX = 16; // pixels per thread group
 
 __device__ __forceinline__ uint32_t ld_label(const uint32_t *L, uint32_t i) { return __ldcg(L + i); }
 
@@ -51,57 +55,93 @@ __device__ __forceinline__ void unite(uint32_t *L, uint32_t a, uint32_t b)
     }
 }
 
-// one thread per pixel, blockDim.x == 32 so that a warp is one 32-px row segment
-__global__ void ccl_init_kernel(const uint8_t *dark, size_t dark_step, int w, int h, uint32_t *L)
+// 16 flag bytes (0/1) -> 16-bit word, bit i = pixel i of the group; pixels >= w are cleared
+__device__ __forceinline__ uint32_t load_group(const uint8_t *row, int x0, int w)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) L[0] = 0;
-    const bool in = (x < w) && (y < h);
-    const bool d = in && dark[(size_t)y * dark_step + x] != 0;
-    const uint32_t bits = __ballot_sync(0xFFFFFFFFu, d);
-    if (!in) return;
-    const size_t p = (size_t)y * w + x;
-    if (!d) return;   // labels of non-dark pixels are never read
-    const uint32_t lane = threadIdx.x;
-    const uint32_t zeros_below = ~bits & ((1u << lane) - 1u);
-    const uint32_t start = zeros_below ? (32u - __clz(zeros_below)) : 0u; // first lane of my run
-    L[p + 1] = (uint32_t)(p + 1) - (lane - start);
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row + x0));
+    auto nib = [](uint32_t q) { return (((q & 0x01010101u) * 0x01020408u) >> 24) & 0xFu; };
+    uint32_t bits = nib(v.x) | (nib(v.y) << 4) | (nib(v.z) << 8) | (nib(v.w) << 12);
+    const int valid = w - x0;
+    if (valid < GPX) bits &= (1u << valid) - 1u;
+    return bits;
 }
 
-__global__ void ccl_merge_kernel(const uint8_t *dark, size_t dark_step, int w, int h, uint32_t *L)
+// thread = (group gx, row y)
+__global__ void ccl_init_kernel(const uint8_t *dark, size_t dark_step, int w, int h, int groups, uint32_t *L)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
+    if (gx == 0 && y == 0) L[0] = 0;
+    if (gx >= groups || y >= h) return;
+    const int x0 = gx * GPX;
+    uint32_t bits = load_group(dark + (size_t)y * dark_step, x0, w);
+    if (!bits) return;
+    const uint32_t id0 = (uint32_t)((size_t)y * w + x0) + 1u;
+    uint32_t start = 0, prev = 0;
+    for (uint32_t m = bits; m;) {
+        const uint32_t i = __ffs(m) - 1;
+        m &= m - 1;
+        if (!(prev && i == prev)) start = i;     // a new run begins unless pixel i-1 was dark
+        L[id0 + i] = id0 + start;
+        prev = i + 1;
+    }
+}
+
+__global__ void ccl_merge_kernel(const uint8_t *dark, size_t dark_step, int w, int h, int groups, uint32_t *L)
+{
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (gx >= groups || y >= h) return;
+    const int x0 = gx * GPX;
     const uint8_t *row = dark + (size_t)y * dark_step;
-    if (!row[x]) return;
-    const uint32_t id = (uint32_t)((size_t)y * w + x) + 1u;
-    if (x == 0 || y == 0 || x == w - 1 || y == h - 1) unite(L, id, 0u);
-    const bool left = x > 0 && row[x - 1];
-    if (left && (x & 31) == 0) unite(L, id, id - 1u); // runs are pre-linked only inside a segment
+    const uint32_t bits = load_group(row, x0, w);
+    if (!bits) return;
+    const uint32_t id0 = (uint32_t)((size_t)y * w + x0) + 1u;
+    // bit i+1 of the extended words = pixel i; bit 0 = the pixel left of the group
+    const uint32_t left_px = (x0 > 0 && row[x0 - 1]) ? 1u : 0u;
+    const uint32_t ext = (bits << 1) | left_px;
+    uint32_t up_ext = 0;
     if (y > 0) {
         const uint8_t *up = row - dark_step;
-        if (up[x]) {
-            const bool chained = left && (x & 31) != 0 && up[x - 1];
+        up_ext = (load_group(up, x0, w) << 1) | ((x0 > 0 && up[x0 - 1]) ? 1u : 0u);
+    }
+    const bool border_row = (y == 0 || y == h - 1);
+    for (uint32_t m = bits; m;) {
+        const uint32_t i = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t id = id0 + i;
+        const int x = x0 + (int)i;
+        if (border_row || x == 0 || x == w - 1) unite(L, id, 0u);
+        const bool left = (ext >> i) & 1u;                 // pixel x-1 dark
+        if (left && i == 0) unite(L, id, id - 1u);         // runs are pre-linked only inside a group
+        if ((up_ext >> (i + 1)) & 1u) {                    // pixel above dark
+            // chained: my left neighbour is dark, in my group, and the pixel above it is dark too --
+            // then it links (or chains) to the row above and both rows' runs are already connected
+            const bool chained = left && i != 0 && ((up_ext >> i) & 1u);
             if (!chained) unite(L, id, id - (uint32_t)w);
         }
     }
 }
 
-// "outside" bit of every pixel (dark and connected to the border), 32 pixels per word
-__global__ void resolve_bits_kernel(const uint8_t *dark, size_t dark_step, int w, int h, uint32_t *L, uint32_t *bits,
-                                    int words_per_row)
+// "outside" bit of every pixel (dark and connected to the border): one 16-bit half word per group
+__global__ void resolve_bits_kernel(const uint8_t *dark, size_t dark_step, int w, int h, int groups, uint32_t *L,
+                                    uint16_t *bits16, int halfwords_per_row)
 {
-    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    bool out = false;
-    if (x < w && y < h && dark[(size_t)y * dark_step + x]) {
-        const uint32_t id = (uint32_t)((size_t)y * w + x) + 1u;
-        out = find_root(L, id) == 0u;
+    if (gx >= halfwords_per_row || y >= h) return;
+    uint32_t out = 0;
+    if (gx < groups) {
+        const int x0 = gx * GPX;
+        const uint32_t bits = load_group(dark + (size_t)y * dark_step, x0, w);
+        const uint32_t id0 = (uint32_t)((size_t)y * w + x0) + 1u;
+        for (uint32_t m = bits; m;) {
+            const uint32_t i = __ffs(m) - 1;
+            m &= m - 1;
+            if (find_root(L, id0 + i) == 0u) out |= 1u << i;
+        }
     }
-    const uint32_t word = __ballot_sync(0xFFFFFFFFu, out);
-    if (threadIdx.x == 0 && y < h && blockIdx.x < words_per_row) bits[(size_t)y * words_per_row + blockIdx.x] = word;
+    bits16[(size_t)y * halfwords_per_row + gx] = (uint16_t)out;
 }
 
 // mask = 0 where any outside pixel lies in the (2r+1)^2 window (out-of-image taps ignored), else 255:
@@ -145,22 +185,27 @@ __global__ void erode_bits_kernel(const uint32_t *bits, int words_per_row, int w
 
 } // namespace
 
+// `dark` rows must be 16-byte aligned (dark_step % 16 == 0, base from cudaMalloc): every caller in this
+// library allocates it that way.
 int launch_valid_mask(spano_ctx *ctx, const uint8_t *dark, int w, int h, size_t dark_step, int erode_iters,
                       uint8_t *mask, size_t mask_step)
 {
     if (w <= 0 || h <= 0) return 0;
     if (erode_iters < 0 || erode_iters > 15)
         return spano_fail(ctx, SPANO_E_INVALID, "erode iterations %d not in [0,15]", erode_iters);
+    if ((dark_step & 15) || (((uintptr_t)dark) & 15) || dark_step < (size_t)((w + GPX - 1) / GPX * GPX))
+        return spano_fail(ctx, SPANO_E_INVALID, "dark-flag rows must be 16-byte aligned and padded to 16 pixels");
     uint32_t *L = nullptr, *bits = nullptr;
+    const int groups = (w + GPX - 1) / GPX;
     const int wpr = (w + 31) / 32;
     int rc = spano_reserve(ctx, spano_ctx::BUF_LABELS, ((size_t)w * h + 1) * sizeof(uint32_t), (void **)&L);
     if (rc) return rc;
     rc = spano_reserve(ctx, spano_ctx::BUF_MASK0, (size_t)wpr * h * sizeof(uint32_t), (void **)&bits);
     if (rc) return rc;
-    dim3 block(32, 8), grid(wpr, (h + 7) / 8);
-    ccl_init_kernel<<<grid, block, 0, ctx->stream>>>(dark, dark_step, w, h, L);
-    ccl_merge_kernel<<<grid, block, 0, ctx->stream>>>(dark, dark_step, w, h, L);
-    resolve_bits_kernel<<<grid, block, 0, ctx->stream>>>(dark, dark_step, w, h, L, bits, wpr);
+    dim3 block(32, 8), grid((2 * wpr + 31) / 32, (h + 7) / 8);
+    ccl_init_kernel<<<grid, block, 0, ctx->stream>>>(dark, dark_step, w, h, groups, L);
+    ccl_merge_kernel<<<grid, block, 0, ctx->stream>>>(dark, dark_step, w, h, groups, L);
+    resolve_bits_kernel<<<grid, block, 0, ctx->stream>>>(dark, dark_step, w, h, groups, L, reinterpret_cast<uint16_t *>(bits), 2 * wpr);
     dim3 eblock(64), egrid((wpr + 63) / 64, h);
     erode_bits_kernel<<<egrid, eblock, 0, ctx->stream>>>(bits, wpr, w, h, erode_iters, mask, mask_step);
     SPANO_CUDA(ctx, cudaGetLastError());
