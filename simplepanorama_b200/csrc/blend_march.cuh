@@ -198,7 +198,7 @@ template <int B, int SW>
 __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
 {
     using C = Cfg<B, SW>;
-    static_assert(C::ROW_ITEMS <= THREADS && C::NPX <= THREADS && C::HB <= 5, "thread mapping");
+    static_assert(C::ROW_ITEMS <= THREADS && C::NPX <= THREADS && C::HB <= 5 && THREADS == 256 && STEP == 8, "thread mapping");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *rowbuf = reinterpret_cast<float *>(smem_raw);                  // [PLANES][PLANE_STRIDE]
     float *G = rowbuf + (size_t)C::PLANES * C::PLANE_STRIDE;              // [PLANES][STEP][SW]
@@ -217,16 +217,48 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
     // combine role
     const int po = tid / SW, px = tid % SW;
 
-    for (int c = tid; c < C::NC; c += THREADS) xtab[c] = reflect_idx(tx0 - R + c, P.w);
-    __syncthreads();
+    // Staging role: warp wv owns channel wv>>1 and rows (wv&1)*4 .. +3 of every chunk; its lanes cover the
+    // NC staged columns in NPASS passes of 32.  Column offsets are step-invariant and live in registers,
+    // the row part of the address is warp-uniform: a staged byte costs ~3 instructions.
+    constexpr int NPASS = (C::NC + 31) / 32;
+    constexpr int NQ = (4 * STEP) / (THREADS / 32);        // (channel,row) pairs per warp = 4
+    const int lane = tid & 31, wv = tid >> 5;
+    const int sch = wv >> 1;                               // staged channel of this warp
+    const uint8_t *sbase = (sch == 0) ? P.cut : P.tile + (sch - 1);
+    const size_t sstep = (sch == 0) ? P.cut_step : P.tile_step;
+    int xoff[NPASS];
+#pragma unroll
+    for (int ps = 0; ps < NPASS; ++ps) {
+        const int c = lane + 32 * ps;
+        const int x = reflect_idx(tx0 - R + min(c, C::NC - 1), P.w);
+        xoff[ps] = (sch == 0) ? x : 3 * x;
+    }
+    (void)xtab;
+    auto prefetch = [&](uint32_t (&dst)[NQ * NPASS], int yrow0) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int y = reflect_idx(yrow0 + (wv & 1) * NQ + q, P.h);
+            const uint8_t *rowp = sbase + (size_t)y * sstep;
+#pragma unroll
+            for (int ps = 0; ps < NPASS; ++ps)
+                if (lane + 32 * ps < C::NC) dst[q * NPASS + ps] = ldg_u8(rowp + xoff[ps]);
+        }
+    };
+    auto stage = [&](const uint32_t (&src)[NQ * NPASS]) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            float *rrow = raw + (sch * STEP + (wv & 1) * NQ + q) * C::RAW_PITCH + lane;
+#pragma unroll
+            for (int ps = 0; ps < NPASS; ++ps)
+                if (lane + 32 * ps < C::NC) rrow[32 * ps] = (float)src[q * NPASS + ps];
+        }
+    };
 
     // prefetch registers (raw bytes): chunk 0, consumed in step -7
-    uint32_t pre[C::PRE];
+    uint32_t pre[NQ * NPASS];
 #pragma unroll
-    for (int k = 0; k < C::PRE; ++k) {
-        const int e = tid + k * THREADS;
-        pre[k] = (e < C::STAGE_ELEMS) ? fetch_raw<B, SW>(P, xtab, e, ybase) : 0u;
-    }
+    for (int k = 0; k < NQ * NPASS; ++k) pre[k] = 0u;
+    prefetch(pre, ybase);
 
     int chunk0 = 0;                                        // circular slot of chunk s (== slot chunk s+7 will reuse)
     // registers of the combine of the previous step (loaded one step ahead so their latency is hidden)
@@ -241,18 +273,8 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
         __syncthreads();                                   // A: chunks s..s+6 filtered, G(s-1) published, raw free
         const bool more_rows = s + 1 < nsteps;             // chunk s+7 is needed by step s+1
         if (more_rows) {
-#pragma unroll
-            for (int k = 0; k < C::PRE; ++k) {
-                const int e = tid + k * THREADS;
-                if (e < C::STAGE_ELEMS) raw[(size_t)(e / C::NC) * C::RAW_PITCH + (e % C::NC)] = (float)pre[k];
-            }
-            if (s + 2 < nsteps) {
-#pragma unroll
-                for (int k = 0; k < C::PRE; ++k) {
-                    const int e = tid + k * THREADS;
-                    pre[k] = (e < C::STAGE_ELEMS) ? fetch_raw<B, SW>(P, xtab, e, ybase + (s + 1 + NCHUNK) * STEP) : 0u;
-                }
-            }
+            stage(pre);
+            if (s + 2 < nsteps) prefetch(pre, ybase + (s + 1 + NCHUNK) * STEP);
         }
         // ---- combine of step s-1 (its global loads were issued during step s-1) ----
         if (cdo) {
