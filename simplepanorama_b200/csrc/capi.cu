@@ -204,6 +204,12 @@ extern "C" void spano_destroy(spano_ctx *ctx)
     for (auto &b : ctx->buf)
         if (b.ptr) cudaFree(b.ptr);
     for (void *p : ctx->owned) cudaFree(p);
+    if (ctx->aux_stream) {
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamDestroy(ctx->aux_stream);
+        for (int b = 0; b < 2; ++b) { cudaEventDestroy(ctx->ev_warped[b]); cudaEventDestroy(ctx->ev_blended[b]); }
+        cudaEventDestroy(ctx->ev_start2);
+    }
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
@@ -632,8 +638,8 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         if (cy + im[j].h <= row0 || cy >= row1) continue;
         use.push_back(j);
         src_max = std::max(src_max, align_up((size_t)im[j].src_w * 3, 16) * im[j].src_h + 16);
-        tile_max = std::max(tile_max, align_up((size_t)im[j].w * 3, 16) * im[j].h);
-        mask_max = std::max(mask_max, align_up((size_t)im[j].w, 16) * im[j].h);
+        tile_max = std::max(tile_max, align_up(align_up((size_t)im[j].w * 3, 16) * im[j].h, 256));
+        mask_max = std::max(mask_max, align_up(align_up((size_t)im[j].w, 16) * im[j].h, 256));
     }
     const int radius = launch_blend_setup(ctx, bands, sigma);
     if (radius < 0) return radius;
@@ -641,8 +647,8 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
     if (int rc = spano_reserve(ctx, spano_ctx::BUF_ACC, (size_t)cw * rows * sizeof(float4), (void **)&acc)) return rc;
     uint8_t *d_tile = nullptr, *d_valid = nullptr, *d_srcbuf[2] = {nullptr, nullptr}, *d_cutbuf[2] = {nullptr, nullptr};
     if (!use.empty()) {
-        if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, tile_max, (void **)&d_tile)) return rc;
-        if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILEMASK, mask_max, (void **)&d_valid)) return rc;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, 2 * tile_max, (void **)&d_tile)) return rc;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILEMASK, 2 * mask_max, (void **)&d_valid)) return rc;
         if (host) {
             if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC, src_max, (void **)&d_srcbuf[0])) return rc;
             if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC2, src_max, (void **)&d_srcbuf[1])) return rc;
@@ -684,6 +690,25 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         if (int rc = launch_blend_clear(ctx, acc, cw, rows)) return rc;
         t.stop(0);
     }
+    // Warp + validity mask of image i+1 run on an auxiliary stream while image i is blended on the main
+    // stream (two tile buffers): the blend CTAs leave issue slots and registers free, the small warp/mask
+    // CTAs (no shared memory) co-reside on the same SMs and fill them.
+    if (!ctx->aux_stream) {
+        SPANO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            SPANO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_warped[b], cudaEventDisableTiming));
+            SPANO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_blended[b], cudaEventDisableTiming));
+        }
+        SPANO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_start2, cudaEventDisableTiming));
+    }
+    cudaStream_t main_stream = ctx->stream, aux = ctx->aux_stream;
+    SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_start2, main_stream));
+    SPANO_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->ev_start2, 0));
+    struct StreamSwap {
+        spano_ctx *c; cudaStream_t keep;
+        StreamSwap(spano_ctx *ctx_, cudaStream_t s) : c(ctx_), keep(ctx_->stream) { c->stream = s; }
+        ~StreamSwap() { c->stream = keep; }
+    };
     if (host && !use.empty())
         if (int rc = issue_copy(0)) return rc;
     for (int idx = 0; idx < (int)use.size(); ++idx) {
@@ -695,38 +720,47 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         const uint8_t *src = im[j].src_bgr, *cut = im[j].mask_cut;
         size_t s_step = im[j].src_step, c_step = im[j].mask_cut_step;
         const size_t t_step = align_up((size_t)im[j].w * 3, 16), m_step = align_up((size_t)im[j].w, 16);
-        if (host) {
-            SPANO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
-            src = d_srcbuf[b];  s_step = align_up((size_t)im[j].src_w * 3, 16);
-            cut = d_cutbuf[b];  c_step = m_step;
-        }
-        const uint8_t *valid = d_valid;
+        uint8_t *tile_b = d_tile + (size_t)b * tile_max, *valid_b = d_valid + (size_t)b * mask_max;
+        const uint8_t *valid = valid_b;
         size_t v_step = m_step;
-        if (!host && im[j].valid_mask) {
-            // mask supplied (computed elsewhere for the whole tile): warp only the rows this band reads --
-            // its own rows plus the blur radius, which BORDER_REFLECT keeps inside the tile
-            if (im[j].valid_mask_step < (size_t)im[j].w) return spano_fail(ctx, SPANO_E_INVALID, "valid_mask step too small");
-            valid = im[j].valid_mask;
-            v_step = im[j].valid_mask_step;
-            const int cy = im[j].tl_y - my;
-            int r0 = std::max(0, row0 - cy) - radius, r1 = std::min(im[j].h, row1 - cy) + radius;
-            if (im[j].h < 4 * radius) { r0 = 0; r1 = im[j].h; }     // several reflections possible: keep it simple
-            r0 = std::max(0, r0);
-            r1 = std::min(im[j].h, r1);
-            StageTimer t0(ctx, 0);
-            int kk = launch_warp(ctx, P, src, im[j].src_w, im[j].src_h, s_step, im[j].gain, im[j].tl_x, im[j].tl_y, im[j].w, im[j].h,
-                                 r0, r1, d_tile, t_step, nullptr, 0);
-            if (kk < 0) return kk;
-            t0.stop(kk);
-        } else if (int rc = dev_warp_tile(ctx, P, src, im[j].src_w, im[j].src_h, s_step, im[j].gain, im[j].tl_x, im[j].tl_y, im[j].w,
-                                          im[j].h, d_tile, t_step, d_valid, m_step))
-            return rc;
+        {   // ---- auxiliary stream: warp (+ mask) into tile buffer b ----
+            StreamSwap sw(ctx, aux);
+            if (idx >= 2) SPANO_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->ev_blended[b], 0));
+            if (host) {
+                SPANO_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->ev_copied[b], 0));
+                src = d_srcbuf[b];  s_step = align_up((size_t)im[j].src_w * 3, 16);
+                cut = d_cutbuf[b];  c_step = m_step;
+            }
+            if (!host && im[j].valid_mask) {
+                // mask supplied (computed elsewhere for the whole tile): warp only the rows this band reads --
+                // its own rows plus the blur radius, which BORDER_REFLECT keeps inside the tile
+                if (im[j].valid_mask_step < (size_t)im[j].w) return spano_fail(ctx, SPANO_E_INVALID, "valid_mask step too small");
+                valid = im[j].valid_mask;
+                v_step = im[j].valid_mask_step;
+                const int cy = im[j].tl_y - my;
+                int r0 = std::max(0, row0 - cy) - radius, r1 = std::min(im[j].h, row1 - cy) + radius;
+                if (im[j].h < 4 * radius) { r0 = 0; r1 = im[j].h; }     // several reflections possible: keep it simple
+                r0 = std::max(0, r0);
+                r1 = std::min(im[j].h, r1);
+                StageTimer t0(ctx, 0);
+                int kk = launch_warp(ctx, P, src, im[j].src_w, im[j].src_h, s_step, im[j].gain, im[j].tl_x, im[j].tl_y, im[j].w, im[j].h,
+                                     r0, r1, tile_b, t_step, nullptr, 0);
+                if (kk < 0) return kk;
+                t0.stop(kk);
+            } else if (int rc = dev_warp_tile(ctx, P, src, im[j].src_w, im[j].src_h, s_step, im[j].gain, im[j].tl_x, im[j].tl_y, im[j].w,
+                                              im[j].h, tile_b, t_step, valid_b, m_step))
+                return rc;
+            SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_warped[b], aux));
+        }
+        // ---- main stream: blend tile b into the accumulator ----
+        SPANO_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_warped[b], 0));
         StageTimer t2(ctx, 2);
-        const BlendTile bt{d_tile, t_step, cut, c_step, valid, v_step, im[j].w, im[j].h, im[j].tl_x - mx, im[j].tl_y - my};
+        const BlendTile bt{tile_b, t_step, cut, c_step, valid, v_step, im[j].w, im[j].h, im[j].tl_x - mx, im[j].tl_y - my};
         int k = launch_blend_tile(ctx, bt, bands, radius, acc, cw, row0, row1);
         if (k < 0) return k;
         t2.stop(k);
-        if (host) SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], ctx->stream));
+        SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_blended[b], main_stream));
+        if (host) SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], main_stream));
     }
     StageTimer t3(ctx, 3);
     int k = launch_normalise(ctx, acc, cw, rows, bands, SPANO_OUT_U8, d_canvas, d_step);

@@ -37,6 +37,9 @@ struct spano_ctx {
     // host-buffer fused path: uploads run on their own stream, double-buffered against the compute stream
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
+    // fused path: warp + mask of the next image run on this stream while the current image is blended
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_warped[2] = {nullptr, nullptr}, ev_blended[2] = {nullptr, nullptr}, ev_start2 = nullptr;
     std::mutex mu;
     std::string err;
     long long launches = 0;
