@@ -43,7 +43,7 @@ struct WarpParams {
     size_t dark_step;
     float inv_gain;
     int apply_gain;
-    int src_aligned8; // src pointer and step are multiples of 8: 64-bit window loads allowed
+    int src_aligned8; // src pointer and step are multiples of 4: aligned 32-bit window loads allowed
     const float *colA, *colB, *rowA, *rowB;
 };
 
@@ -84,34 +84,46 @@ __device__ __forceinline__ int sat_short(int v) { return max(-32768, min(32767, 
 // Bilinear sample of one destination pixel -> packed 0x00RRGGBB (un-gained).
 __device__ __forceinline__ uint32_t sample_bilinear(const WarpParams &P, float x, float y)
 {
-    const int fx = fixed_coord(x), fy = fixed_coord(y);
-    const int sx = sat_short(fx >> 5), sy = sat_short(fy >> 5);
+    // cvRound(32 x) is INT_MIN on x86 for NaN / |32 x| >= 2^31, which lands outside every image:
+    // any such coordinate makes the whole sample the border constant
+    if (!(fabsf(x) < 67108864.f) || !(fabsf(y) < 67108864.f)) return 0u;
+    const int fx = __float2int_rn(x * 32.f), fy = __float2int_rn(y * 32.f);
+    // (OpenCV saturates the integer part to short; images are < 32767 px, so saturated and unsaturated
+    // values fail the same range tests below)
+    const int sx = fx >> 5, sy = fy >> 5;
     const int ax = fx & 31, ay = fy & 31;
     const uint32_t wx = (uint32_t)(32 - ax) | ((uint32_t)ax << 24); // bytes {32-ax,0,0,ax}
     uint32_t hb[2], hg[2], hr[2];
     if ((unsigned)sx < (unsigned)(P.src_w - 1) && (unsigned)sy < (unsigned)(P.src_h - 1)) {
-        const uint8_t *row = P.src + (size_t)sy * P.src_step;
         const int o = 3 * sx;
+        if (P.src_aligned8) {
+            // the 6 bytes {B0 G0 R0 B1 G1 R1} start at byte t of three aligned 32-bit words; straight-line code:
+            // two funnel shifts align bytes o..o+7, two more give the G- and R-phased words
+            const int t8 = (o & 3) * 8;
+            const uint32_t *w0 = reinterpret_cast<const uint32_t *>(P.src + (size_t)sy * P.src_step + (o & ~3));
+            const uint32_t *w1 = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(w0) + P.src_step);
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            uint64_t win;
-            if (P.src_aligned8) {
-                const int a = o & ~7, sh = (o & 7) * 8;
-                uint64_t lo = __ldg(reinterpret_cast<const unsigned long long *>(row + a));
-                win = lo >> sh;
-                if (sh > 16) { // the 6 bytes cross into the next aligned word
-                    uint64_t hi = __ldg(reinterpret_cast<const unsigned long long *>(row + a + 8));
-                    win |= hi << (64 - sh);
-                }
-            } else {
-                win = 0;
+            for (int r = 0; r < 2; ++r) {
+                const uint32_t *w = r ? w1 : w0;
+                const uint32_t a = __ldg(w), b = __ldg(w + 1);
+                const uint32_t c = (t8 == 24) ? __ldg(w + 2) : 0u;   // third word only when the window crosses into it
+                const uint32_t lo = __funnelshift_r(a, b, t8), hi = __funnelshift_r(b, c, t8);
+                hb[r] = __dp4a(lo, wx, 0u);
+                hg[r] = __dp4a(__funnelshift_r(lo, hi, 8), wx, 0u);
+                hr[r] = __dp4a(__funnelshift_r(lo, hi, 16), wx, 0u);
+            }
+        } else {
+            const uint8_t *row = P.src + (size_t)sy * P.src_step;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                uint64_t win = 0;
 #pragma unroll
                 for (int b = 0; b < 6; ++b) win |= (uint64_t)__ldg(row + o + b) << (8 * b);
+                hb[r] = __dp4a((uint32_t)win, wx, 0u);
+                hg[r] = __dp4a((uint32_t)(win >> 8), wx, 0u);
+                hr[r] = __dp4a((uint32_t)(win >> 16), wx, 0u);
+                row += P.src_step;
             }
-            hb[r] = __dp4a((uint32_t)win, wx, 0u);
-            hg[r] = __dp4a((uint32_t)(win >> 8), wx, 0u);
-            hr[r] = __dp4a((uint32_t)(win >> 16), wx, 0u);
-            row += P.src_step;
         }
     } else {
         // BORDER_CONSTANT(0): every tap outside the source contributes 0
@@ -203,6 +215,13 @@ constexpr int WARP_BLOCK_X = 32, WARP_BLOCK_Y = 8;
 template <int KIND>
 __global__ void __launch_bounds__(WARP_BLOCK_X *WARP_BLOCK_Y) warp_kernel(const WarpParams P)
 {
+    // 8-bit gain as a 256-entry table (one shared-memory load per channel instead of convert/multiply/round/clamp)
+    __shared__ uint8_t s_gain[256];
+    {
+        const uint32_t t = threadIdx.y * WARP_BLOCK_X + threadIdx.x;
+        s_gain[t] = (uint8_t)(P.apply_gain ? gain_u8(t, P.inv_gain) : t);
+    }
+    __syncthreads();
     const int x0 = (blockIdx.x * WARP_BLOCK_X + threadIdx.x) * WARP_PX_PER_THREAD;
     const int v = P.row_begin + blockIdx.y * WARP_BLOCK_Y + threadIdx.y;
     if (x0 >= P.dst_w || v >= P.row_end) return;
@@ -218,7 +237,7 @@ __global__ void __launch_bounds__(WARP_BLOCK_X *WARP_BLOCK_Y) warp_kernel(const 
             map_backward<KIND>(P, u, v, x, y);
             s = sample_bilinear(P, x, y);
             d = is_dark(s);
-            if (P.apply_gain) s = gain_bgr(s, P.inv_gain);
+            s = (uint32_t)s_gain[s & 255u] | ((uint32_t)s_gain[(s >> 8) & 255u] << 8) | ((uint32_t)s_gain[(s >> 16) & 255u] << 16);
         }
         px[i] = s;
         dark |= d << (8 * i);
@@ -300,7 +319,7 @@ int launch_remap(spano_ctx *ctx, const uint8_t *src, int src_w, int src_h, size_
     P.dst_w = dst_w;  P.dst_h = dst_h;
     P.src = src;  P.src_w = src_w;  P.src_h = src_h;  P.src_step = src_step;
     P.dst = dst;  P.dst_step = dst_step;
-    P.src_aligned8 = ((((uintptr_t)src) | src_step) & 7) == 0;
+    P.src_aligned8 = ((((uintptr_t)src) | src_step) & 3) == 0;
     dim3 block(256), grid((dst_w + 255) / 256, dst_h);
     remap_kernel<<<grid, block, 0, ctx->stream>>>(P, xmap, ymap);
     SPANO_CUDA(ctx, cudaGetLastError());
@@ -329,7 +348,7 @@ int launch_warp(spano_ctx *ctx, const SpanoProjector &proj, const uint8_t *src, 
     P.dark = dark;  P.dark_step = dark_step;
     P.inv_gain = (float)(1.0 / gain);
     P.apply_gain = (gain != 1.0);
-    P.src_aligned8 = ((((uintptr_t)src) | src_step) & 7) == 0;
+    P.src_aligned8 = ((((uintptr_t)src) | src_step) & 3) == 0;
     P.colA = tables;
     P.colB = tables + dst_w;
     P.rowA = tables + 2 * (size_t)dst_w;
