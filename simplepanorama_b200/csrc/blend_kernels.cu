@@ -303,11 +303,11 @@ __global__ void __launch_bounds__(GTHREADS) blend_generic_kernel(const BlendPara
 
 // out = color / clamp(alpha) / float(255/B)  [ -> *255 -> u8 ]
 __global__ void normalise_kernel(const float4 *acc, int canvas_w, int rows, float inv_div, int out_kind, void *out,
-                                 size_t out_step)
+                                 size_t out_step, int col0, int col1)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = col0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
-    if (x >= canvas_w || y >= rows) return;
+    if (x >= col1 || y >= rows) return;
     const float4 t = acc[(size_t)y * canvas_w + x];
     float d = t.w;
     d = copysignf(fmaxf(fabsf(d), 1e-6f), d);
@@ -529,13 +529,14 @@ int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius,
 }
 
 int launch_normalise(spano_ctx *ctx, const float4 *acc, int canvas_w, int rows, int bands, int out_kind, void *out,
-                     size_t out_step)
+                     size_t out_step, int col0, int col1)
 {
-    if (rows <= 0 || canvas_w <= 0) return 0;
+    if (col1 < 0) col1 = canvas_w;
+    if (rows <= 0 || col1 <= col0) return 0;
     const float divisor = (float)(255 / bands); // integer division, as in the reference
     const float inv_div = (float)(1.0 / (double)divisor);
-    dim3 block(256), grid((canvas_w + 255) / 256, rows);
-    normalise_kernel<<<grid, block, 0, ctx->stream>>>(acc, canvas_w, rows, inv_div, out_kind, out, out_step);
+    dim3 block(256), grid((col1 - col0 + 255) / 256, rows);
+    normalise_kernel<<<grid, block, 0, ctx->stream>>>(acc, canvas_w, rows, inv_div, out_kind, out, out_step, col0, col1);
     SPANO_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
     return 1;

@@ -204,6 +204,10 @@ extern "C" void spano_destroy(spano_ctx *ctx)
     for (auto &b : ctx->buf)
         if (b.ptr) cudaFree(b.ptr);
     for (void *p : ctx->owned) cudaFree(p);
+    if (ctx->d2h_stream) {
+        cudaStreamSynchronize(ctx->d2h_stream);
+        cudaStreamDestroy(ctx->d2h_stream);
+    }
     if (ctx->aux_stream) {
         cudaStreamSynchronize(ctx->aux_stream);
         cudaStreamDestroy(ctx->aux_stream);
@@ -709,6 +713,25 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         StreamSwap(spano_ctx *ctx_, cudaStream_t s) : c(ctx_), keep(ctx_->stream) { c->stream = s; }
         ~StreamSwap() { c->stream = keep; }
     };
+    // host path: for every canvas column the last image (in processing order) whose tile covers it
+    struct ColRun { int c0, c1, idx; };
+    std::vector<ColRun> runs;
+    std::vector<cudaEvent_t> flush_events;
+    if (host && !use.empty()) {
+        if (!ctx->d2h_stream) SPANO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        std::vector<int> last(cw, 0);   // uncovered columns are final from the start: flushed after the first image
+        for (int idx = 0; idx < (int)use.size(); ++idx) {
+            const int j = use[idx];
+            const int c0 = std::max(0, im[j].tl_x - mx), c1 = std::min(cw, im[j].tl_x - mx + im[j].w);
+            for (int c = c0; c < c1; ++c) last[c] = idx;
+        }
+        for (int c = 0; c < cw;) {
+            int e = c + 1;
+            while (e < cw && last[e] == last[c]) ++e;
+            runs.push_back(ColRun{c, e, last[c]});
+            c = e;
+        }
+    }
     if (host && !use.empty())
         if (int rc = issue_copy(0)) return rc;
     for (int idx = 0; idx < (int)use.size(); ++idx) {
@@ -760,15 +783,38 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         if (k < 0) return k;
         t2.stop(k);
         SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_blended[b], main_stream));
-        if (host) SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], main_stream));
+        if (host) {
+            SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], main_stream));
+            // canvas columns that no later image touches are final: normalise and download them now, on the
+            // download stream, while the remaining images are still being blended
+            for (const ColRun &r : runs) {
+                if (r.idx != idx) continue;
+                StageTimer t3(ctx, 3);
+                int kn = launch_normalise(ctx, acc, cw, rows, bands, SPANO_OUT_U8, d_canvas, d_step, r.c0, r.c1);
+                if (kn < 0) return kn;
+                t3.stop(kn);
+                cudaEvent_t e;
+                SPANO_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                flush_events.push_back(e);
+                SPANO_CUDA(ctx, cudaEventRecord(e, main_stream));
+                SPANO_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, e, 0));
+                SPANO_CUDA(ctx, cudaMemcpy2DAsync(canvas + (size_t)r.c0 * 3, canvas_step, d_canvas + (size_t)r.c0 * 3, d_step,
+                                                  (size_t)(r.c1 - r.c0) * 3, rows, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            }
+        }
     }
-    StageTimer t3(ctx, 3);
-    int k = launch_normalise(ctx, acc, cw, rows, bands, SPANO_OUT_U8, d_canvas, d_step);
-    if (k < 0) return k;
-    t3.stop(k);
+    if (!host || use.empty()) {
+        StageTimer t3(ctx, 3);
+        int k = launch_normalise(ctx, acc, cw, rows, bands, SPANO_OUT_U8, d_canvas, d_step);
+        if (k < 0) return k;
+        t3.stop(k);
+        if (host)
+            SPANO_CUDA(ctx, cudaMemcpy2DAsync(canvas, canvas_step, d_canvas, d_step, (size_t)cw * 3, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     if (host) {
-        SPANO_CUDA(ctx, cudaMemcpy2DAsync(canvas, canvas_step, d_canvas, d_step, (size_t)cw * 3, rows, cudaMemcpyDeviceToHost, ctx->stream));
         SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
+        for (cudaEvent_t e : flush_events) cudaEventDestroy(e);
     }
     return SPANO_OK;
 }

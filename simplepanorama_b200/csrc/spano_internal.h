@@ -38,6 +38,7 @@ struct spano_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_start = nullptr;
     // fused path: warp + mask of the next image run on this stream while the current image is blended
+    cudaStream_t d2h_stream = nullptr; // host-buffer fused path: finished canvas columns are downloaded while blending continues
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_warped[2] = {nullptr, nullptr}, ev_blended[2] = {nullptr, nullptr}, ev_start2 = nullptr;
     std::mutex mu;
@@ -91,7 +92,7 @@ int launch_blend_clear(spano_ctx *ctx, float4 *acc, int canvas_w, int rows);
 int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius, float4 *acc, int canvas_w, int row0,
                       int row1);
 int launch_normalise(spano_ctx *ctx, const float4 *acc, int canvas_w, int rows, int bands, int out_kind, void *out,
-                     size_t out_step);
+                     size_t out_step, int col0 = 0, int col1 = -1);
 int launch_fp32_peak(spano_ctx *ctx, int variant, double *tflops);
 // disk_kernels.cu: stereographic centre fix (util::RadialNormalizer state + normalised radius)
 struct SpanoDiskParams {
