@@ -103,7 +103,9 @@ def build_workload(args):
         plan = api.plan_tiles(images, R, K, cfg.kind, cfg.focal)   # host geometry only
         corners = [p[2] for p in plan]
         sizes = [p[3] for p in plan]
-        cuts = list(ex.map(lambda j: synth.seam_masks(corners, sizes, only=j), range(cfg.n)))
+        # mask_cut stays at preview scale (1/8), as stitch_parameters::return_full receives it; the up-scaling to
+        # tile size (cv::resize, 8-bit INTER_LINEAR) is part of the path and happens on the device
+        cuts = list(ex.map(lambda j: synth.seam_masks(corners, sizes, only=j, coarse=True), range(cfg.n)))
     W, H, mx, my = api.pan_dimension(corners, sizes)
     T = sum(w * h for w, h in sizes)
     return dict(cfg=cfg, K=K, R=R, gains=gains, images=images, plan=plan, corners=corners, sizes=sizes, cuts=cuts,
@@ -116,7 +118,8 @@ def config_json(wl, args, world):
             "projection": ["spherical", "cylindrical", "stereographic"][cfg.kind], "focal": cfg.focal, "bands": cfg.bands,
             "sigma": cfg.sigma, "canvas": [wl["W"], wl["H"]], "tile_mpx": round(wl["T"] / 1e6, 1),
             "sharding": f"row-bands x{world}" if world > 1 else "single GPU",
-            "l2": "inputs larger than L2 (sources+masks > 2 GB vs 126 MB)", "scale": args.scale}
+            "mask_cut": "preview scale (1/8), resized to tile size on the device inside the step",
+            "l2": "inputs larger than L2 (sources 1.7 GB vs 126 MB)", "scale": args.scale}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -140,7 +143,8 @@ def cpu_reference_sample(wl, seconds: float, steps: int = 1, warmup: int = 0):
         corner, tile = cv2_ref.project(cfg.kind, cfg.focal, wl["R"][0], K, img)
         msk = cv2_ref.validity_mask(tile)
         tile = cv2_ref.apply_gain(tile, wl["gains"][0])
-        cut = np.full(tile.shape[:2], 255, np.uint8)
+        small = np.full((max(1, tile.shape[0] // 8), max(1, tile.shape[1] // 8)), 255, np.uint8)
+        cut = cv2_ref.resize_mask(small, (tile.shape[1], tile.shape[0]))   # return_full's mask_cut up-scaling
         out = cv2_ref.blend_to_u8(cv2_ref.multi_blend([tile], [cut], [msk], [corner], cfg.bands, cfg.sigma))
         return time.perf_counter() - t0, tile.shape[0] * tile.shape[1], out
 

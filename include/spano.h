@@ -110,6 +110,12 @@ int spano_remap(spano_ctx *ctx, const uint8_t *src_bgr, int src_w, int src_h, si
 int spano_surrounding_mask(spano_ctx *ctx, const uint8_t *bgr, int w, int h, size_t step, int erode_iters,
                            uint8_t *mask, size_t mask_step);
 
+/* cv::resize(src, dst, Size(dst_w, dst_h)) for CV_8UC1 with the default INTER_LINEAR -- what return_full
+ * applies to every mask_cut (src/classes/_panorama.cpp:329-335; the INTER_CUBIC there lands in `fx`).
+ * OpenCV's fixed-point arithmetic, bit-exact.  HOST buffers.                                          */
+int spano_resize_mask(spano_ctx *ctx, const uint8_t *src, int src_w, int src_h, size_t src_step, uint8_t *dst,
+                      int dst_w, int dst_h, size_t dst_step);
+
 /* a6 alone: `img / gain` on CV_8UC3, in place. */
 int spano_apply_gain(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, double gain);
 
@@ -164,6 +170,10 @@ typedef struct spano_image_desc {
      * GPUs: masks are a whole-tile property, so ranks compute them for disjoint tiles and all-gather them. */
     const uint8_t *valid_mask;
     size_t valid_mask_step;
+    /* Size of `mask_cut` when it is still at PREVIEW scale, as stitch_parameters::return_full receives it
+     * (src/classes/_panorama.cpp:329-335): the fused path then up-scales it to w x h on the device with
+     * cv::resize's 8-bit INTER_LINEAR arithmetic.  0, 0 = mask_cut is already w x h.                    */
+    int mask_cut_w, mask_cut_h;
 } spano_image_desc;
 
 int spano_composite(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *images, int bands,

@@ -188,6 +188,8 @@ def return_full(images, R, K, kind, focal, gains, masks_cut, bands, sigma, want_
         tiles.append(tile)
         corners.append(tl)
     gained = [apply_gain(t, g) for t, g in zip(tiles, gains)] if gains is not None else tiles
+    # cv::resize(mask_cut[i], .., tile size) -- default INTER_LINEAR (src/classes/_panorama.cpp:329-335)
+    masks_cut = [m if m.shape == t.shape[:2] else resize_linear_u8(m, (t.shape[1], t.shape[0])) for m, t in zip(masks_cut, tiles)]
     blend = multi_blend(gained, masks_cut, msks, corners, bands, sigma)
     out = blend_to_u8(blend)
     if want_float:

@@ -28,6 +28,7 @@ class ImageDesc(C.Structure):
         ("mask_cut", C.c_void_p), ("mask_cut_step", C.c_size_t),
         ("tl_x", C.c_int), ("tl_y", C.c_int), ("w", C.c_int), ("h", C.c_int),
         ("valid_mask", C.c_void_p), ("valid_mask_step", C.c_size_t),
+        ("mask_cut_w", C.c_int), ("mask_cut_h", C.c_int),
     ]
 
 
@@ -47,6 +48,7 @@ SYMBOLS = {
     "spano_build_maps": (C.c_int, [C.c_void_p, C.c_int, C.c_float, c_f32p, c_f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "spano_remap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_surrounding_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]),
+    "spano_resize_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
     "spano_apply_gain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double]),
     "spano_disk_reproj_size": (C.c_int, [C.c_void_p, C.c_int, c_intp, c_intp, c_intp, c_intp, C.c_int, C.c_int, C.c_float,
                                          C.c_int, c_intp, c_intp, c_intp, c_intp]),

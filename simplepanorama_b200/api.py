@@ -367,7 +367,24 @@ def make_descs(images, plan, gains, masks_cut, ptr_of=lambda a: a.ctypes.data, s
         d.mask_cut = ptr_of(masks_cut[j])
         d.mask_cut_step = step_of(masks_cut[j])
         d.tl_x, d.tl_y, d.w, d.h = int(tlx), int(tly), int(w), int(h)
+        mh, mw = int(masks_cut[j].shape[0]), int(masks_cut[j].shape[1])
+        if (mw, mh) != (int(w), int(h)):     # preview-scale mask: the fused path resizes it like return_full does
+            d.mask_cut_w, d.mask_cut_h = mw, mh
     return descs
+
+
+def resize_mask(mask, size_wh, ctx: Context | None = None) -> np.ndarray:
+    """cv::resize(mask, dst, size) on CV_8UC1 with the default INTER_LINEAR -- return_full's mask_cut
+    up-scaling (src/classes/_panorama.cpp:329-335)."""
+    ctx = ctx or default_context()
+    m = _u8img(mask, 1, "mask")
+    dw, dh = int(size_wh[0]), int(size_wh[1])
+    if dw <= 0 or dh <= 0:
+        raise SpanoError(_lib.E_INVALID, "empty destination size")
+    out = np.empty((dh, dw), np.uint8)
+    ctx.check(ctx.lib.spano_resize_mask(ctx.h, m.ctypes.data, m.shape[1], m.shape[0], m.strides[0], out.ctypes.data, dw, dh,
+                                        out.strides[0]))
+    return out
 
 
 def return_full(images, R, K, kind: int, focal: float, gains, masks_cut, bands: int, sigma: float,
@@ -384,8 +401,9 @@ def return_full(images, R, K, kind: int, focal: float, gains, masks_cut, bands: 
     cuts = [_u8img(a, 1, f"mask_cut[{i}]") for i, a in enumerate(masks_cut)]
     for j in range(n):
         w, h = plan[j][3]
-        if cuts[j].shape != (h, w):
-            raise SpanoError(_lib.E_INVALID, f"mask_cut[{j}] is {cuts[j].shape}, tile is {(h, w)}")
+        if cuts[j].size == 0:
+            raise SpanoError(_lib.E_INVALID, f"mask_cut[{j}] is empty")
+        # any other size is taken as the preview-scale mask and resized to (h, w) on the device
     W, H, _, _ = pan_dimension([p[2] for p in plan], [p[3] for p in plan])
     row0, row1 = rows if rows is not None else (0, H)
     descs = make_descs(imgs, plan, gains, cuts)

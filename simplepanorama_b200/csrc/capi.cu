@@ -488,6 +488,25 @@ extern "C" int spano_surrounding_mask(spano_ctx *ctx, const uint8_t *bgr, int w,
     return SPANO_OK;
 }
 
+extern "C" int spano_resize_mask(spano_ctx *ctx, const uint8_t *src, int src_w, int src_h, size_t src_step, uint8_t *dst,
+                                 int dst_w, int dst_h, size_t dst_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (int rc = check_image_args(ctx, src, src_w, src_h, src_step, 1, "source mask")) return rc;
+    if (int rc = check_image_args(ctx, dst, dst_w, dst_h, dst_step, 1, "destination mask")) return rc;
+    const size_t s_step = align_up((size_t)src_w, 16), d_step = align_up((size_t)dst_w, 16);
+    uint8_t *d_src, *d_dst;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTSMALL, s_step * src_h, (void **)&d_src)) return rc;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILEMASK, d_step * dst_h, (void **)&d_dst)) return rc;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_src, s_step, src, src_step, (size_t)src_w, src_h, cudaMemcpyHostToDevice, ctx->stream));
+    int k = launch_resize_mask(ctx, d_src, src_w, src_h, s_step, d_dst, dst_w, dst_h, d_step);
+    if (k < 0) return k;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(dst, dst_step, d_dst, d_step, (size_t)dst_w, dst_h, cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}
+
 extern "C" int spano_apply_gain(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, double gain)
 {
     if (!ctx) return SPANO_E_INVALID;
@@ -632,10 +651,18 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
     // Tiles that touch canvas rows [row0,row1) take part.  BORDER_REFLECT is resolved inside each tile,
     // so a band needs the full extent of exactly those tiles and nothing from neighbouring bands.
     std::vector<int> use;
-    size_t src_max = 0, tile_max = 0, mask_max = 0;
+    size_t src_max = 0, tile_max = 0, mask_max = 0, small_max = 0;
+    bool any_small = false;
     for (int j = 0; j < n; ++j) {
         if (int rc = check_image_args(ctx, im[j].src_bgr, im[j].src_w, im[j].src_h, im[j].src_step, 3, "source")) return rc;
-        if (int rc = check_image_args(ctx, im[j].mask_cut, im[j].w, im[j].h, im[j].mask_cut_step, 1, "mask_cut")) return rc;
+        const bool small = im[j].mask_cut_w > 0 || im[j].mask_cut_h > 0;   // preview-scale mask, resized on the device
+        if (int rc = check_image_args(ctx, im[j].mask_cut, small ? im[j].mask_cut_w : im[j].w, small ? im[j].mask_cut_h : im[j].h,
+                                      im[j].mask_cut_step, 1, "mask_cut"))
+            return rc;
+        if (small) {
+            any_small = true;
+            small_max = std::max(small_max, align_up(align_up((size_t)im[j].mask_cut_w, 16) * im[j].mask_cut_h, 256));
+        }
         if (!(im[j].gain > 0.0)) return spano_fail(ctx, SPANO_E_INVALID, "gain[%d] must be > 0", j);
         if (int rc = check_remap_limits(ctx, im[j].src_w, im[j].src_h, im[j].w, im[j].h)) return rc;
         const int cy = im[j].tl_y - my;
@@ -650,14 +677,21 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
     float4 *acc = nullptr;
     if (int rc = spano_reserve(ctx, spano_ctx::BUF_ACC, (size_t)cw * rows * sizeof(float4), (void **)&acc)) return rc;
     uint8_t *d_tile = nullptr, *d_valid = nullptr, *d_srcbuf[2] = {nullptr, nullptr}, *d_cutbuf[2] = {nullptr, nullptr};
+    uint8_t *d_cutsmall[2] = {nullptr, nullptr};
     if (!use.empty()) {
         if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, 2 * tile_max, (void **)&d_tile)) return rc;
         if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILEMASK, 2 * mask_max, (void **)&d_valid)) return rc;
         if (host) {
             if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC, src_max, (void **)&d_srcbuf[0])) return rc;
             if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC2, src_max, (void **)&d_srcbuf[1])) return rc;
+        }
+        if (host || any_small) {
             if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTMASK, mask_max, (void **)&d_cutbuf[0])) return rc;
             if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUT2, mask_max, (void **)&d_cutbuf[1])) return rc;
+        }
+        if (host && any_small) {
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTSMALL, small_max, (void **)&d_cutsmall[0])) return rc;
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTSMALL2, small_max, (void **)&d_cutsmall[1])) return rc;
         }
     }
     uint8_t *d_canvas = canvas;
@@ -684,8 +718,12 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         if (idx >= 2) SPANO_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_free[b], 0));
         SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_srcbuf[b], align_up((size_t)im[j].src_w * 3, 16), im[j].src_bgr, im[j].src_step,
                                           (size_t)im[j].src_w * 3, im[j].src_h, cudaMemcpyHostToDevice, cs));
-        SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_cutbuf[b], align_up((size_t)im[j].w, 16), im[j].mask_cut, im[j].mask_cut_step,
-                                          (size_t)im[j].w, im[j].h, cudaMemcpyHostToDevice, cs));
+        if (im[j].mask_cut_w > 0 || im[j].mask_cut_h > 0)   // preview-scale mask: resized on the device after the upload
+            SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_cutsmall[b], align_up((size_t)im[j].mask_cut_w, 16), im[j].mask_cut, im[j].mask_cut_step,
+                                              (size_t)im[j].mask_cut_w, im[j].mask_cut_h, cudaMemcpyHostToDevice, cs));
+        else
+            SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_cutbuf[b], align_up((size_t)im[j].w, 16), im[j].mask_cut, im[j].mask_cut_step,
+                                              (size_t)im[j].w, im[j].h, cudaMemcpyHostToDevice, cs));
         SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], cs));
         return 0;
     };
@@ -752,6 +790,14 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
             if (host) {
                 SPANO_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->ev_copied[b], 0));
                 src = d_srcbuf[b];  s_step = align_up((size_t)im[j].src_w * 3, 16);
+                cut = d_cutbuf[b];  c_step = m_step;
+            }
+            if (im[j].mask_cut_w > 0 || im[j].mask_cut_h > 0) {
+                // mask_cut is at preview scale: cv::resize(.., tile size) with the 8-bit INTER_LINEAR arithmetic
+                const uint8_t *small = host ? d_cutsmall[b] : im[j].mask_cut;
+                const size_t small_step = host ? align_up((size_t)im[j].mask_cut_w, 16) : im[j].mask_cut_step;
+                int kk = launch_resize_mask(ctx, small, im[j].mask_cut_w, im[j].mask_cut_h, small_step, d_cutbuf[b], im[j].w, im[j].h, m_step);
+                if (kk < 0) return kk;
                 cut = d_cutbuf[b];  c_step = m_step;
             }
             if (!host && im[j].valid_mask) {

@@ -1,0 +1,94 @@
+// resize_kernels.cu -- up-scaling of the preview-scale seam masks to tile size (sm_100a).
+//
+// Replaces  cv::resize(mask_cut[i], blend_dat.msks_cut[i], blend_dat.imgs[i].size(), cv::INTER_CUBIC)
+// in stitch_parameters::return_full (reference src/classes/_panorama.cpp:329-335).  The fourth argument
+// is cv::resize's `fx` slot, so the interpolation is the DEFAULT, INTER_LINEAR.
+// For CV_8UC1 OpenCV's linear resize is fixed point: per axis two 11-bit coefficients
+// (INTER_RESIZE_COEF_SCALE = 2048) from a float fraction, horizontal pass in int, vertical pass
+//   dst = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2 .
+// The source coordinate is (d + 0.5) * scale - 0.5 in double, cast to float, floor'ed, clamped.
+// Bit-exact against cv2 4.13 (tests/golden/kernels.npz and tests/test_gpu_resize.py).
+// Integer work; 1 B written per tile pixel, the small source stays in L2.
+#include "spano_internal.h"
+
+namespace {
+
+struct AxisEntry {
+    int ofs;      // first source index (second = min(ofs + 1, len - 1)), clamped rows for y
+    short c0, c1; // 11-bit coefficients
+};
+
+// one entry per destination column (axis 0) and row (axis 1)
+__global__ void resize_tables_kernel(int sw, int sh, int dw, int dh, AxisEntry *xt, AxisEntry *yt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < dw) {
+        const double scale = (double)sw / dw;
+        float f = (float)((i + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (s < 0) { f = 0.f; s = 0; }
+        if (s >= sw - 1) { f = 0.f; s = sw - 1; }
+        AxisEntry e;
+        e.ofs = s;
+        e.c0 = (short)__float2int_rn((1.f - f) * 2048.f);
+        e.c1 = (short)__float2int_rn(f * 2048.f);
+        xt[i] = e;
+    }
+    if (i < dh) {
+        const double scale = (double)sh / dh;
+        float f = (float)((i + 0.5) * scale - 0.5);
+        const int s = (int)floorf(f);
+        f -= (float)s;
+        AxisEntry e;
+        e.ofs = s;   // rows s and s+1 are clamped to [0, sh-1] when they are read (OpenCV keeps the fraction)
+        e.c0 = (short)__float2int_rn((1.f - f) * 2048.f);
+        e.c1 = (short)__float2int_rn(f * 2048.f);
+        yt[i] = e;
+    }
+}
+
+__global__ void resize_linear_u8_kernel(const uint8_t *src, int sw, int sh, size_t sstep, const AxisEntry *xt,
+                                        const AxisEntry *yt, uint8_t *dst, int dw, int dh, size_t dstep)
+{
+    // 4 consecutive destination pixels per thread, one 32-bit store when the row allows it
+    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int dy = blockIdx.y;
+    if (dx0 >= dw || dy >= dh) return;
+    const AxisEntry ey = yt[dy];
+    const int y0 = min(max(ey.ofs, 0), sh - 1), y1 = min(max(ey.ofs + 1, 0), sh - 1);
+    const uint8_t *r0p = src + (size_t)y0 * sstep, *r1p = src + (size_t)y1 * sstep;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int dx = min(dx0 + i, dw - 1);
+        const AxisEntry ex = xt[dx];
+        const int x0 = ex.ofs, x1 = min(ex.ofs + 1, sw - 1);
+        const int r0 = (int)__ldg(r0p + x0) * ex.c0 + (int)__ldg(r0p + x1) * ex.c1;
+        const int r1 = (int)__ldg(r1p + x0) * ex.c0 + (int)__ldg(r1p + x1) * ex.c1;
+        const int v = ((((int)ey.c0 * (r0 >> 4)) >> 16) + (((int)ey.c1 * (r1 >> 4)) >> 16) + 2) >> 2;
+        packed |= (uint32_t)min(255, max(0, v)) << (8 * i);
+    }
+    uint8_t *d = dst + (size_t)dy * dstep + dx0;
+    if (dx0 + 4 <= dw && (((uintptr_t)d) & 3) == 0) *reinterpret_cast<uint32_t *>(d) = packed;
+    else
+        for (int i = 0; i < 4 && dx0 + i < dw; ++i) d[i] = (uint8_t)(packed >> (8 * i));
+}
+
+} // namespace
+
+int launch_resize_mask(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_t sstep, uint8_t *dst, int dw, int dh,
+                       size_t dstep)
+{
+    if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return spano_fail(ctx, SPANO_E_INVALID, "resize: empty image");
+    AxisEntry *tab = nullptr;
+    int rc = spano_reserve(ctx, spano_ctx::BUF_RESIZE, (size_t)(dw + dh) * sizeof(AxisEntry), (void **)&tab);
+    if (rc) return rc;
+    const int n = dw > dh ? dw : dh;
+    resize_tables_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sw, sh, dw, dh, tab, tab + dw);
+    dim3 block(128), grid((dw + 511) / 512, dh);
+    resize_linear_u8_kernel<<<grid, block, 0, ctx->stream>>>(src, sw, sh, sstep, tab, tab + dw, dst, dw, dh, dstep);
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return 2;
+}

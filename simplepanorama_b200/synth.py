@@ -111,7 +111,7 @@ def make_images(cfg: Config, gains, noise: int = 0):
     return [make_image(cfg, j, gains[j], noise) for j in range(cfg.n)]
 
 
-def seam_masks(corners, sizes, soft: int = 8, only: int | None = None):
+def seam_masks(corners, sizes, soft: int = 8, only: int | None = None, coarse: bool = False):
     """Soft-edged 0..255 seam masks (uint8, one per tile): pixel p of tile j is 255 when j's
     centre is the nearest among the tiles whose rectangle contains p (a Voronoi seam), computed on
     a coarse grid and bilinearly up-sampled to tile size like the reference's preview->full resize."""
@@ -135,7 +135,10 @@ def seam_masks(corners, sizes, soft: int = 8, only: int | None = None):
             inside = (GX >= x0[i]) & (GX < x1[i]) & (GY >= y0[i]) & (GY < y1[i])
             di = (GX - cx[i]) ** 2 + (GY - cy[i]) ** 2
             keep &= ~(inside & ((di < dj) | ((di == dj) & (i < j))))
-        out.append(_upsample_u8(keep.astype(np.float32) * 255.0, w, h))
+        if coarse:   # the preview-scale binary mask itself (what dist_cut / graph_cut hand to return_full)
+            out.append(np.ascontiguousarray(keep.astype(np.uint8) * 255))
+        else:
+            out.append(_upsample_u8(keep.astype(np.float32) * 255.0, w, h))
     return out if only is None else out[0]
 
 
