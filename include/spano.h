@@ -116,6 +116,12 @@ int spano_surrounding_mask(spano_ctx *ctx, const uint8_t *bgr, int w, int h, siz
 int spano_resize_mask(spano_ctx *ctx, const uint8_t *src, int src_w, int src_h, size_t src_step, uint8_t *dst,
                       int dst_w, int dst_h, size_t dst_step);
 
+/* test::adjust_intensity for one image, in place on CV_8UC3 (src/test/_test.cpp:110-122): the CV_32FC1
+ * correction field (field_w x field_h, field_step in bytes) is resized to the image with cv::resize's
+ * float INTER_LINEAR and the image becomes  sat_u8(rint((v/255 / clamp(field)) * 255)).  HOST buffers. */
+int spano_adjust_intensity(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, const float *field, int field_w,
+                           int field_h, size_t field_step);
+
 /* a6 alone: `img / gain` on CV_8UC3, in place. */
 int spano_apply_gain(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, double gain);
 
@@ -174,6 +180,12 @@ typedef struct spano_image_desc {
      * (src/classes/_panorama.cpp:329-335): the fused path then up-scales it to w x h on the device with
      * cv::resize's 8-bit INTER_LINEAR arithmetic.  0, 0 = mask_cut is already w x h.                    */
     int mask_cut_w, mask_cut_h;
+    /* Optional intensity-correction field of test::adjust_intensity (conf.blend_intensity; CV_32FC1,
+     * low resolution; src/test/_test.cpp:110-122, src/classes/_panorama.cpp:337-339): applied to the
+     * gained tile before the blend.  NULL = blend_intensity off.  intensity_step in BYTES.            */
+    const float *intensity;
+    int intensity_w, intensity_h;
+    size_t intensity_step;
 } spano_image_desc;
 
 int spano_composite(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *images, int bands,

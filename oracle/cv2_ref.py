@@ -119,6 +119,15 @@ def resize_mask(mask: np.ndarray, size_wh) -> np.ndarray:
     return cv2.resize(mask, size_wh, interpolation=cv2.INTER_LINEAR)
 
 
+def adjust_intensity(img: np.ndarray, field: np.ndarray) -> np.ndarray:
+    """test::adjust_intensity for one image (src/test/_test.cpp:110-122): resize the float correction
+    field to the tile, tile/255 -> divide by the (clamped) field -> *255 -> CV_8UC3."""
+    f = cv2.resize(np.asarray(field, np.float32), (img.shape[1], img.shape[0]), interpolation=cv2.INTER_LINEAR)
+    x = img.astype(np.float32) * np.float32(1.0 / 255.0)
+    x = elementwise_divide(x, f)
+    return np.clip(np.rint(x * np.float32(255.0)), 0, 255).astype(np.uint8)
+
+
 def elementwise_divide(A: np.ndarray, B: np.ndarray) -> np.ndarray:
     """imgm::elementwiseOperation(DIVIDE) (src/math/_img_manipulation.cpp:31-84)."""
     d = np.copysign(np.maximum(np.abs(B), np.float32(1e-6)), B).astype(np.float32)

@@ -176,9 +176,21 @@ def gen_cubic_gather():
     return {"cubic_img": img, "cubic_x": xm, "cubic_y": ym, "cubic_dst": dst}
 
 
+def gen_intensity():
+    """KAT for test::adjust_intensity (src/test/_test.cpp:110-122): float field resized by cv2.resize,
+    tile/255 -> divide -> *255 -> u8."""
+    rng = np.random.default_rng(11)
+    field = cv2.GaussianBlur((0.6 + 0.8 * rng.random((23, 31))).astype(np.float32), (13, 13), 7, borderType=cv2.BORDER_REFLECT)
+    field[3, 4] = 0.0          # exercises the 1e-6 clamp of elementwiseOperation(DIVIDE)
+    img = rng.integers(0, 256, (97, 141, 3), dtype=np.uint8)
+    return {"int_field": field, "int_img": img, "int_field_resized": cv2.resize(field, (141, 97), interpolation=cv2.INTER_LINEAR),
+            "int_out": ref.adjust_intensity(img, field)}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "cubic_gather.npz"), **gen_cubic_gather())
+    np.savez_compressed(os.path.join(OUT, "intensity.npz"), **gen_intensity())
     rng = np.random.default_rng(20261018)
     np.savez_compressed(os.path.join(OUT, "roi_table.npz"), table=gen_roi_table(), cv2_version=np.array(cv2.__version__))
     np.savez_compressed(os.path.join(OUT, "warp_cases.npz"), **gen_warp_cases(rng))

@@ -144,6 +144,23 @@ def resize_linear_u8(mask, size_wh):
     return out
 
 
+def resize_linear_f32(field, size_wh):
+    field = np.ascontiguousarray(field, np.float32)
+    dw, dh = size_wh
+    out = np.empty((dh, dw), np.float32)
+    lib().orc_resize_linear_f32c1(_p(field, C.c_float), field.shape[1], field.shape[0], _p(out, C.c_float), dw, dh)
+    return out
+
+
+def adjust_intensity(img, field):
+    """test::adjust_intensity for one image -> new CV_8UC3 image."""
+    out = np.array(img, copy=True, order="C")
+    field = np.ascontiguousarray(field, np.float32)
+    lib().orc_adjust_intensity(_p(out, C.c_uint8), out.shape[1], out.shape[0], C.c_size_t(out.strides[0]), _p(field, C.c_float),
+                               field.shape[1], field.shape[0])
+    return out
+
+
 class _DiskParams(C.Structure):
     _fields_ = [("cx", C.c_float), ("cy", C.c_float), ("scale", C.c_float), ("radius_n", C.c_float), ("quadratic", C.c_int)]
 
@@ -178,7 +195,7 @@ def adjusted_camera(K, R, w_ref, h_ref):
     return K_adj.astype(np.float32), np.asarray(R, np.float64).astype(np.float32)
 
 
-def return_full(images, R, K, kind, focal, gains, masks_cut, bands, sigma, want_float=False):
+def return_full(images, R, K, kind, focal, gains, masks_cut, bands, sigma, want_float=False, intensities=None):
     """stitch_parameters::return_full (MULTI_BLEND): sources -> (u8 canvas, tiles, masks, corners)."""
     tiles, msks, corners = [], [], []
     for img, r, k in zip(images, R, K):
@@ -190,6 +207,8 @@ def return_full(images, R, K, kind, focal, gains, masks_cut, bands, sigma, want_
     gained = [apply_gain(t, g) for t, g in zip(tiles, gains)] if gains is not None else tiles
     # cv::resize(mask_cut[i], .., tile size) -- default INTER_LINEAR (src/classes/_panorama.cpp:329-335)
     masks_cut = [m if m.shape == t.shape[:2] else resize_linear_u8(m, (t.shape[1], t.shape[0])) for m, t in zip(masks_cut, tiles)]
+    if intensities is not None:   # test::adjust_intensity (conf.blend_intensity), src/classes/_panorama.cpp:337-339
+        gained = [adjust_intensity(t, f) for t, f in zip(gained, intensities)]
     blend = multi_blend(gained, masks_cut, msks, corners, bands, sigma)
     out = blend_to_u8(blend)
     if want_float:

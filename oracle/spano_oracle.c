@@ -688,3 +688,55 @@ void orc_disk_reproj_tile(const orc_disk_params *P, const uint8_t *src, int sw, 
             }
         }
 }
+
+/* ==== test::adjust_intensity (src/test/_test.cpp:110-122; SURVEY section 8f "next" #1) ==========
+ * per image: field = cv::resize(intensities[i], tile size, INTER_LINEAR)   (CV_32FC1, float bilinear)
+ *            tile  = convertTo(CV_32FC3, 1/255) ; elementwiseOperation(DIVIDE by field, clamped) ;
+ *            convertTo(CV_8UC3, 255)
+ * i.e. per channel  u8 <- sat(rint(((float(v) * float(1/255)) * (1.f / clamp(field))) * 255.f)).
+ * OpenCV's float linear resize: source coordinate (d + 0.5) * scale - 0.5 in double -> float, floor,
+ * fraction kept in float, horizontal pass S[sx]*(1-fx) + S[sx+1]*fx, vertical pass r0*(1-fy) + r1*fy.
+ * PARITY PIN: cv2.resize(float32) + the same arithmetic in numpy (tests/golden/intensity.npz); the
+ * interpolated field agrees to float rounding (OpenCV's SIMD path may fuse one multiply-add), the
+ * 8-bit result within 1 LSB.                                                                       */
+void orc_resize_linear_f32c1(const float *src, int sw, int sh, float *dst, int dw, int dh)
+{
+    double scale_x = (double)sw / dw, scale_y = (double)sh / dh;
+    for (int dy = 0; dy < dh; dy++) {
+        float fy = (float)((dy + 0.5) * scale_y - 0.5);
+        int sy = (int)floorf(fy);
+        fy -= sy;
+        int sy0 = sy < 0 ? 0 : (sy >= sh ? sh - 1 : sy), sy1 = sy + 1 < 0 ? 0 : (sy + 1 >= sh ? sh - 1 : sy + 1);
+        for (int dx = 0; dx < dw; dx++) {
+            float fx = (float)((dx + 0.5) * scale_x - 0.5);
+            int sx = (int)floorf(fx);
+            fx -= sx;
+            if (sx < 0) { fx = 0; sx = 0; }
+            if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+            int sx1 = sx + 1 < sw ? sx + 1 : sx;
+            float r0 = src[(size_t)sy0 * sw + sx] * (1.f - fx) + src[(size_t)sy0 * sw + sx1] * fx;
+            float r1 = src[(size_t)sy1 * sw + sx] * (1.f - fx) + src[(size_t)sy1 * sw + sx1] * fx;
+            dst[(size_t)dy * dw + dx] = r0 * (1.f - fy) + r1 * fy;
+        }
+    }
+}
+
+void orc_adjust_intensity(uint8_t *bgr, int w, int h, size_t step, const float *field, int fw, int fh)
+{
+    float *f = (float *)malloc((size_t)w * h * sizeof(float));
+    orc_resize_linear_f32c1(field, fw, fh, f, w, h);
+    const float inv255 = (float)(1.0 / 255.0);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            float d = f[(size_t)y * w + x];
+            d = copysignf(fmaxf(fabsf(d), 1e-6f), d);
+            float s = 1.f / d;
+            uint8_t *p = bgr + (size_t)y * step + (size_t)x * 3;
+            for (int c = 0; c < 3; c++) {
+                float v = ((float)p[c] * inv255) * s;
+                int r = cv_round_f32(v * 255.f);
+                p[c] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+            }
+        }
+    free(f);
+}

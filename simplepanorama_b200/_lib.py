@@ -29,6 +29,7 @@ class ImageDesc(C.Structure):
         ("tl_x", C.c_int), ("tl_y", C.c_int), ("w", C.c_int), ("h", C.c_int),
         ("valid_mask", C.c_void_p), ("valid_mask_step", C.c_size_t),
         ("mask_cut_w", C.c_int), ("mask_cut_h", C.c_int),
+        ("intensity", C.c_void_p), ("intensity_w", C.c_int), ("intensity_h", C.c_int), ("intensity_step", C.c_size_t),
     ]
 
 
@@ -49,6 +50,7 @@ SYMBOLS = {
     "spano_remap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_surrounding_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_resize_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
+    "spano_adjust_intensity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
     "spano_apply_gain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double]),
     "spano_disk_reproj_size": (C.c_int, [C.c_void_p, C.c_int, c_intp, c_intp, c_intp, c_intp, C.c_int, C.c_int, C.c_float,
                                          C.c_int, c_intp, c_intp, c_intp, c_intp]),

@@ -387,10 +387,24 @@ def resize_mask(mask, size_wh, ctx: Context | None = None) -> np.ndarray:
     return out
 
 
+def adjust_intensity(img, field, ctx: Context | None = None) -> np.ndarray:
+    """test::adjust_intensity for one image (src/test/_test.cpp:110-122): resize the CV_32FC1 correction
+    field to the image (float INTER_LINEAR) and divide, through 1/255 and 255 round trips, on 8 bits."""
+    ctx = ctx or default_context()
+    out = np.array(_u8img(img, 3, "image"), copy=True, order="C")
+    f = np.ascontiguousarray(field, np.float32)
+    if f.ndim != 2 or f.size == 0:
+        raise SpanoError(_lib.E_INVALID, "intensity field must be a non-empty 2-D float32 array")
+    ctx.check(ctx.lib.spano_adjust_intensity(ctx.h, out.ctypes.data, out.shape[1], out.shape[0], out.strides[0], f.ctypes.data,
+                                             f.shape[1], f.shape[0], f.strides[0]))
+    return out
+
+
 def return_full(images, R, K, kind: int, focal: float, gains, masks_cut, bands: int, sigma: float,
-                rows: tuple[int, int] | None = None, ctx: Context | None = None):
+                rows: tuple[int, int] | None = None, ctx: Context | None = None, intensities=None):
     """stitch_parameters::return_full (MULTI_BLEND, gain optional): decoded sources + K/R + gains +
-    full-resolution mask_cut[] -> final CV_8UC3 canvas, through the fused device path.
+    mask_cut[] (tile-sized or preview-scale) [+ intensity-correction fields when conf.blend_intensity]
+    -> final CV_8UC3 canvas, through the fused device path.
     `rows=(row0,row1)` restricts the result to a band of canvas rows (row-band sharding)."""
     ctx = ctx or default_context()
     n = len(images)
@@ -407,6 +421,15 @@ def return_full(images, R, K, kind: int, focal: float, gains, masks_cut, bands: 
     W, H, _, _ = pan_dimension([p[2] for p in plan], [p[3] for p in plan])
     row0, row1 = rows if rows is not None else (0, H)
     descs = make_descs(imgs, plan, gains, cuts)
+    fields = None
+    if intensities is not None:
+        if len(intensities) != n:
+            raise SpanoError(_lib.E_INVALID, "Input consistency!")
+        fields = [np.ascontiguousarray(f, np.float32) for f in intensities]   # kept alive for the call
+        for j, f in enumerate(fields):
+            descs[j].intensity = f.ctypes.data
+            descs[j].intensity_h, descs[j].intensity_w = int(f.shape[0]), int(f.shape[1])
+            descs[j].intensity_step = f.strides[0]
     canvas = np.empty((row1 - row0, W, 3), np.uint8)
     ctx.check(ctx.lib.spano_composite(ctx.h, int(kind), C.c_float(focal), n, descs, int(bands), float(sigma),
                                       int(row0), int(row1), canvas.ctypes.data, canvas.strides[0]))

@@ -507,6 +507,27 @@ extern "C" int spano_resize_mask(spano_ctx *ctx, const uint8_t *src, int src_w, 
     return SPANO_OK;
 }
 
+extern "C" int spano_adjust_intensity(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, const float *field,
+                                      int field_w, int field_h, size_t field_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (int rc = check_image_args(ctx, bgr, w, h, step, 3, "image")) return rc;
+    if (int rc = check_image_args(ctx, field, field_w, field_h, field_step, 4, "intensity field")) return rc;
+    const size_t t_step = align_up((size_t)w * 3, 16), f_step = align_up((size_t)field_w * 4, 16);
+    uint8_t *d_img;
+    float *d_field;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, t_step * h, (void **)&d_img)) return rc;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_FIELD, f_step * field_h, (void **)&d_field)) return rc;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_img, t_step, bgr, step, (size_t)w * 3, h, cudaMemcpyHostToDevice, ctx->stream));
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_field, f_step, field, field_step, (size_t)field_w * 4, field_h, cudaMemcpyHostToDevice, ctx->stream));
+    int k = launch_adjust_intensity(ctx, d_img, w, h, t_step, d_field, field_w, field_h, f_step / 4);
+    if (k < 0) return k;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(bgr, step, d_img, t_step, (size_t)w * 3, h, cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}
+
 extern "C" int spano_apply_gain(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, double gain)
 {
     if (!ctx) return SPANO_E_INVALID;
@@ -651,7 +672,7 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
     // Tiles that touch canvas rows [row0,row1) take part.  BORDER_REFLECT is resolved inside each tile,
     // so a band needs the full extent of exactly those tiles and nothing from neighbouring bands.
     std::vector<int> use;
-    size_t src_max = 0, tile_max = 0, mask_max = 0, small_max = 0;
+    size_t src_max = 0, tile_max = 0, mask_max = 0, small_max = 0, field_max = 0;
     bool any_small = false;
     for (int j = 0; j < n; ++j) {
         if (int rc = check_image_args(ctx, im[j].src_bgr, im[j].src_w, im[j].src_h, im[j].src_step, 3, "source")) return rc;
@@ -662,6 +683,11 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         if (small) {
             any_small = true;
             small_max = std::max(small_max, align_up(align_up((size_t)im[j].mask_cut_w, 16) * im[j].mask_cut_h, 256));
+        }
+        if (im[j].intensity) {
+            if (int rc = check_image_args(ctx, im[j].intensity, im[j].intensity_w, im[j].intensity_h, im[j].intensity_step, 4, "intensity field"))
+                return rc;
+            field_max = std::max(field_max, align_up(align_up((size_t)im[j].intensity_w * 4, 16) * im[j].intensity_h, 256));
         }
         if (!(im[j].gain > 0.0)) return spano_fail(ctx, SPANO_E_INVALID, "gain[%d] must be > 0", j);
         if (int rc = check_remap_limits(ctx, im[j].src_w, im[j].src_h, im[j].w, im[j].h)) return rc;
@@ -678,6 +704,7 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
     if (int rc = spano_reserve(ctx, spano_ctx::BUF_ACC, (size_t)cw * rows * sizeof(float4), (void **)&acc)) return rc;
     uint8_t *d_tile = nullptr, *d_valid = nullptr, *d_srcbuf[2] = {nullptr, nullptr}, *d_cutbuf[2] = {nullptr, nullptr};
     uint8_t *d_cutsmall[2] = {nullptr, nullptr};
+    float *d_field[2] = {nullptr, nullptr};
     if (!use.empty()) {
         if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, 2 * tile_max, (void **)&d_tile)) return rc;
         if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILEMASK, 2 * mask_max, (void **)&d_valid)) return rc;
@@ -692,6 +719,10 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         if (host && any_small) {
             if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTSMALL, small_max, (void **)&d_cutsmall[0])) return rc;
             if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTSMALL2, small_max, (void **)&d_cutsmall[1])) return rc;
+        }
+        if (host && field_max) {
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_FIELD, field_max, (void **)&d_field[0])) return rc;
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_FIELD2, field_max, (void **)&d_field[1])) return rc;
         }
     }
     uint8_t *d_canvas = canvas;
@@ -819,6 +850,20 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
             } else if (int rc = dev_warp_tile(ctx, P, src, im[j].src_w, im[j].src_h, s_step, im[j].gain, im[j].tl_x, im[j].tl_y, im[j].w,
                                               im[j].h, tile_b, t_step, valid_b, m_step))
                 return rc;
+            if (im[j].intensity) {
+                // test::adjust_intensity on the gained tile (conf.blend_intensity), before the blend
+                const float *fld = im[j].intensity;
+                size_t fpitch = im[j].intensity_step / 4;
+                if (host) {
+                    const size_t f_step = align_up((size_t)im[j].intensity_w * 4, 16);
+                    SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_field[b], f_step, im[j].intensity, im[j].intensity_step, (size_t)im[j].intensity_w * 4,
+                                                      im[j].intensity_h, cudaMemcpyHostToDevice, aux));
+                    fld = d_field[b];
+                    fpitch = f_step / 4;
+                }
+                int kk = launch_adjust_intensity(ctx, tile_b, im[j].w, im[j].h, t_step, fld, im[j].intensity_w, im[j].intensity_h, fpitch);
+                if (kk < 0) return kk;
+            }
             SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_warped[b], aux));
         }
         // ---- main stream: blend tile b into the accumulator ----

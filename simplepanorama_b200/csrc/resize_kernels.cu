@@ -75,7 +75,77 @@ __global__ void resize_linear_u8_kernel(const uint8_t *src, int sw, int sh, size
         for (int i = 0; i < 4 && dx0 + i < dw; ++i) d[i] = (uint8_t)(packed >> (8 * i));
 }
 
+// ---- test::adjust_intensity (reference src/test/_test.cpp:110-122): float-bilinear up-scaling of the
+// per-image intensity-correction field (cv::resize CV_32FC1 INTER_LINEAR) fused with
+//   tile <- sat_u8(rint(((float(v) * float(1/255)) * (1.f / clamp(field))) * 255.f))
+// One pass over the tile, in place; the field itself is never materialised at tile size.
+struct AxisEntryF {
+    int ofs;
+    float f;
+};
+
+__global__ void intensity_tables_kernel(int sw, int sh, int dw, int dh, AxisEntryF *xt, AxisEntryF *yt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < dw) {
+        const double scale = (double)sw / dw;
+        float f = (float)((i + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (s < 0) { f = 0.f; s = 0; }
+        if (s >= sw - 1) { f = 0.f; s = sw - 1; }
+        xt[i] = AxisEntryF{s, f};
+    }
+    if (i < dh) {
+        const double scale = (double)sh / dh;
+        float f = (float)((i + 0.5) * scale - 0.5);
+        const int s = (int)floorf(f);
+        f -= (float)s;
+        yt[i] = AxisEntryF{s, f};
+    }
+}
+
+__global__ void adjust_intensity_kernel(uint8_t *bgr, int w, int h, size_t step, const float *field, int fw, int fh,
+                                        size_t fpitch, const AxisEntryF *xt, const AxisEntryF *yt)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const AxisEntryF ex = xt[x], ey = yt[y];
+    const int y0 = min(max(ey.ofs, 0), fh - 1), y1 = min(max(ey.ofs + 1, 0), fh - 1);
+    const int x0 = ex.ofs, x1 = min(ex.ofs + 1, fw - 1);
+    const float *p0 = field + (size_t)y0 * fpitch, *p1 = field + (size_t)y1 * fpitch;
+    const float ax1 = ex.f, ax0 = __fsub_rn(1.f, ex.f), ay1 = ey.f, ay0 = __fsub_rn(1.f, ey.f);
+    const float r0 = __fadd_rn(__fmul_rn(__ldg(p0 + x0), ax0), __fmul_rn(__ldg(p0 + x1), ax1));
+    const float r1 = __fadd_rn(__fmul_rn(__ldg(p1 + x0), ax0), __fmul_rn(__ldg(p1 + x1), ax1));
+    float d = __fadd_rn(__fmul_rn(r0, ay0), __fmul_rn(r1, ay1));
+    d = copysignf(fmaxf(fabsf(d), 1e-6f), d);
+    const float s = __fdiv_rn(1.f, d);
+    uint8_t *p = bgr + (size_t)y * step + (size_t)x * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float v = __fmul_rn(__fmul_rn((float)p[c], (float)(1.0 / 255.0)), s);
+        p[c] = (uint8_t)min(255, max(0, __float2int_rn(__fmul_rn(v, 255.f))));
+    }
+}
+
 } // namespace
+
+int launch_adjust_intensity(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, const float *field, int fw, int fh,
+                            size_t fpitch_elems)
+{
+    if (w <= 0 || h <= 0 || fw <= 0 || fh <= 0) return spano_fail(ctx, SPANO_E_INVALID, "adjust_intensity: empty image");
+    AxisEntryF *tab = nullptr;
+    int rc = spano_reserve(ctx, spano_ctx::BUF_RESIZE, (size_t)(w + h) * sizeof(AxisEntryF), (void **)&tab);
+    if (rc) return rc;
+    const int n = w > h ? w : h;
+    intensity_tables_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(fw, fh, w, h, tab, tab + w);
+    dim3 block(256), grid((w + 255) / 256, h);
+    adjust_intensity_kernel<<<grid, block, 0, ctx->stream>>>(bgr, w, h, step, field, fw, fh, fpitch_elems, tab, tab + w);
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return 2;
+}
 
 int launch_resize_mask(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_t sstep, uint8_t *dst, int dw, int dh,
                        size_t dstep)

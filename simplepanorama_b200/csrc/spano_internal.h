@@ -46,7 +46,7 @@ struct spano_ctx {
     long long launches = 0;
     // grow-only scratch buffers, indexed by role
     enum { BUF_LABELS = 0, BUF_DARK, BUF_MASK0, BUF_TABLES, BUF_ACC, BUF_TILE, BUF_TILEMASK, BUF_CUTMASK, BUF_SRC,
-           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_COUNT };
+           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_COUNT };
     DeviceBuffer buf[BUF_COUNT];
     std::vector<void *> owned; // extra allocations freed at destroy / end of call
     // timers
@@ -97,6 +97,8 @@ int launch_fp32_peak(spano_ctx *ctx, int variant, double *tflops);
 // resize_kernels.cu: cv::resize(CV_8UC1, INTER_LINEAR) of the preview-scale seam masks
 int launch_resize_mask(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_t sstep, uint8_t *dst, int dw, int dh,
                        size_t dstep);
+int launch_adjust_intensity(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, const float *field, int fw, int fh,
+                            size_t fpitch_elems);
 // disk_kernels.cu: stereographic centre fix (util::RadialNormalizer state + normalised radius)
 struct SpanoDiskParams {
     float cx, cy, scale;

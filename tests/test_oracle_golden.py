@@ -133,3 +133,14 @@ def test_disk_reproj_oracle_properties(oracle):
             vals = set(map(tuple, o.reshape(-1, 3)[:: 37]))
             src = set(map(tuple, t.reshape(-1, 3))) | {(0, 0, 0)}
             assert vals <= src          # every output pixel is a copy of an input pixel (or border 0)
+
+
+def test_adjust_intensity_golden(golden, oracle):
+    """test::adjust_intensity: the interpolated field within float rounding of cv2.resize, the 8-bit result
+    within 1 LSB of the cv2-made fixture."""
+    g = golden("intensity.npz")
+    f = oracle.resize_linear_f32(g["int_field"], (g["int_img"].shape[1], g["int_img"].shape[0]))
+    assert np.abs(f - g["int_field_resized"]).max() <= 1e-6 * np.abs(g["int_field_resized"]).max()
+    out = oracle.adjust_intensity(g["int_img"], g["int_field"])
+    d = np.abs(out.astype(int) - g["int_out"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
