@@ -157,3 +157,17 @@ cv::Mat multi_blend(const std::vector<cv::Mat> &images, const std::vector<cv::Ma
 }
 
 } // namespace blnd
+
+namespace test {
+
+// src/test/_test.cpp:110-122 (called from return_full / get_preview when conf.blend_intensity is on)
+void adjust_intensity(std::vector<cv::Mat> &images, const std::vector<cv::Mat> &intensities)
+{
+    for (size_t i = 0; i < images.size(); ++i) {
+        cv::Mat &im = images[i];
+        const cv::Mat &f = intensities[i];   // CV_32FC1, low resolution
+        check(spano_adjust_intensity(ctx(), im.data, im.cols, im.rows, im.step, f.ptr<float>(), f.cols, f.rows, f.step));
+    }
+}
+
+} // namespace test
