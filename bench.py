@@ -117,7 +117,7 @@ def config_json(wl, args, world):
     return {"workload": f"{cfg.name}: {cfg.description}", "images": cfg.n, "image_size": [cfg.width, cfg.height],
             "projection": ["spherical", "cylindrical", "stereographic"][cfg.kind], "focal": cfg.focal, "bands": cfg.bands,
             "sigma": cfg.sigma, "canvas": [wl["W"], wl["H"]], "tile_mpx": round(wl["T"] / 1e6, 1),
-            "sharding": f"row-bands x{world}" if world > 1 else "single GPU",
+            "sharding": (f"tile-sharded warp+mask (owner j % {world}) -> NVLink peer stores -> row-band blend x{world}" if world > 1 else "single GPU"),
             "mask_cut": "preview scale (1/8), resized to tile size on the device inside the step",
             "l2": "inputs larger than L2 (sources 1.7 GB vs 126 MB)", "scale": args.scale}
 
@@ -209,63 +209,94 @@ def run_ours(args):
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
-    bands = sdist.plan_row_bands(list(zip(wl["corners"], wl["sizes"])), world, wl["min_y"], wl["H"])
+    # N = 1: the fused single-GPU path (spano_dev_composite / spano_composite).
+    # N > 1: the tile-sharded path (include/spano.h): image j is uploaded, warped and masked once, by its owner
+    # rank j % N, whose warp / mask kernels store every tile row straight into the memory of the rank(s) whose
+    # canvas row band reads it (NVLink peer stores); rank k blends its band from its own arena.  Per round of N
+    # images one 4-byte all-reduce orders "all owners have written" before "blend"; the finished 8-bit bands are
+    # received straight into rank 0's canvas.
+    sp = sdist.plan_tile_shards(wl["corners"], wl["sizes"], world, cfg.sigma)
+    bands = sp.bands
     row0, row1 = bands[rank]
+    owned = [j for j in range(cfg.n) if sp.owner[j] == rank]
+    mine = set(owned) if world > 1 else set(range(cfg.n))
 
-    # host (pinned) and device copies of the inputs
-    h_img = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in wl["images"]]
+    # host (pinned) and device copies of the inputs; at N > 1 a rank holds only the sources it owns
+    h_img = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() if j in mine else None for j, a in enumerate(wl["images"])]
     h_cut = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in wl["cuts"]]
-    d_img = [t.to(dev, non_blocking=True) for t in h_img]
+    d_img = [t.to(dev, non_blocking=True) if t is not None else None for t in h_img]
     d_cut = [t.to(dev, non_blocking=True) for t in h_cut]
-    d_canvas = torch.empty((max(1, row1 - row0), wl["W"], 3), dtype=torch.uint8, device=dev)
+    if world > 1 and rank == 0:
+        d_full = torch.empty((wl["H"], wl["W"], 3), dtype=torch.uint8, device=dev)
+        d_canvas = d_full[row0:row1] if row1 > row0 else d_full[:1]
+    else:
+        d_full = None
+        d_canvas = torch.empty((max(1, row1 - row0), wl["W"], 3), dtype=torch.uint8, device=dev)
     h_canvas = torch.empty((max(1, row1 - row0), wl["W"], 3), dtype=torch.uint8).pin_memory()
     torch.cuda.synchronize()
-    ptr = lambda t: t.data_ptr()
-    step_of = lambda t: t.stride(0)
-    descs_dev = api.make_descs(d_img, wl["plan"], wl["gains"], d_cut, ptr, step_of)
-    descs_host = api.make_descs(h_img, wl["plan"], wl["gains"], h_cut, ptr, step_of)
+
+    class _Absent:   # placeholder for a source this rank does not own (never dereferenced)
+        shape = (1, 1, 3)
+    ptr = lambda t: t.data_ptr() if not isinstance(t, _Absent) else 0
+    step_of = lambda t: t.stride(0) if not isinstance(t, _Absent) else 0
+    fill = lambda lst: [t if t is not None else _Absent() for t in lst]
+    descs_dev = api.make_descs(fill(d_img), wl["plan"], wl["gains"], d_cut, ptr, step_of)
+    descs_host = api.make_descs(fill(h_img), wl["plan"], wl["gains"], h_cut, ptr, step_of)
+    for j in range(cfg.n):
+        for dd in (descs_dev, descs_host):
+            dd[j].src_h, dd[j].src_w = cfg.height, cfg.width
     lib = ctx.lib
     import ctypes as C
 
-    # N > 1: validity masks are a whole-tile property (flood fill), so they are computed tile-sharded
-    # (rank r owns tiles j = r mod N) and all-gathered (1 B/px, the one real exchange step of the
-    # path); every rank then warps only the tile rows its band reads.
-    all_masks = my_seg = None
-    owned = []
+    ctx_s = aux = arenas = tok = None
     if world > 1:
-        owner = [j % world for j in range(cfg.n)]
-        seg_fill = [0] * world
-        offs = []
-        for j, (w, h) in enumerate(wl["sizes"]):
-            offs.append(seg_fill[owner[j]])
-            seg_fill[owner[j]] += (w * h + 255) // 256 * 256
-        seg_max = max(seg_fill)
-        all_masks = torch.empty(world * seg_max, dtype=torch.uint8, device=dev)
-        my_seg = all_masks[rank * seg_max:(rank + 1) * seg_max]
-        for j, (w, h) in enumerate(wl["sizes"]):
-            descs_dev[j].valid_mask = all_masks.data_ptr() + owner[j] * seg_max + offs[j]
-            descs_dev[j].valid_mask_step = w
-            if owner[j] == rank:
-                owned.append(j)
+        ctx_s = api.Context(local)                     # owner-side work runs on its own stream / context
+        aux = torch.cuda.Stream(device=dev)
+        ctx_s.set_stream(aux.cuda_stream)
+        arenas = sdist.PeerArenas(ctx, sp, rank)
+        tok = torch.zeros(1, device=dev)
+
+    def step_sharded(host):
+        descs = descs_host if host else descs_dev
+        have = row1 > row0
+        if have:   # (host variant: queues the small mask uploads ahead of the large source uploads below)
+            sdist.blend_begin(ctx, sp, rank, cfg.bands, cfg.sigma, host_descs=descs_host if host else None)
+        tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)   # every rank has finished blending the previous step's arenas
+        aux.wait_stream(stream)
+        evs = []
+        for rnd in sp.rounds:
+            for j in rnd:
+                if sp.owner[j] == rank:
+                    sdist.scatter_tile(ctx_s, sp, j, descs[j], arenas.ptrs, cfg.kind, cfg.focal, host=host)
+            ev = torch.cuda.Event()
+            ev.record(aux)
+            evs.append(ev)
+        for t, rnd in enumerate(sp.rounds):
+            stream.wait_event(evs[t])
+            tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)   # round t is in every arena
+            if have:
+                for j in rnd:
+                    sdist.blend_add(ctx, sp, rank, j, descs[j], arenas.own, host=host)
+        if have:
+            if host:
+                sdist.blend_finish(ctx, h_canvas.data_ptr(), h_canvas.stride(0), host=True)
+            else:
+                sdist.blend_finish(ctx, d_canvas.data_ptr(), d_canvas.stride(0))
+        if not host:
+            return sdist.gather_bands_into(d_full, d_canvas[: row1 - row0], bands, rank, world)
 
     def step_dev():
         if world > 1:
-            for j in owned:
-                d = descs_dev[j]
-                ctx.check(lib.spano_dev_tile_mask(ctx.h, cfg.kind, C.c_float(cfg.focal), d.K, d.R, d.src_bgr, d.src_w, d.src_h,
-                                                  d.src_step, d.tl_x, d.tl_y, d.w, d.h, d.valid_mask, d.valid_mask_step))
-            tdist.all_gather_into_tensor(all_masks, my_seg.clone())
-        if row1 > row0:
-            ctx.check(lib.spano_dev_composite(ctx.h, cfg.kind, C.c_float(cfg.focal), cfg.n, descs_dev, cfg.bands, cfg.sigma,
-                                              row0, row1, d_canvas.data_ptr(), d_canvas.stride(0)))
-        if world > 1:
-            return sdist.gather_bands(d_canvas[: row1 - row0], bands, wl["W"], rank, world)
+            return step_sharded(False)
+        ctx.check(lib.spano_dev_composite(ctx.h, cfg.kind, C.c_float(cfg.focal), cfg.n, descs_dev, cfg.bands, cfg.sigma,
+                                          row0, row1, d_canvas.data_ptr(), d_canvas.stride(0)))
         return d_canvas
 
     def step_host():
-        if row1 > row0:
-            ctx.check(lib.spano_composite(ctx.h, cfg.kind, C.c_float(cfg.focal), cfg.n, descs_host, cfg.bands, cfg.sigma,
-                                          row0, row1, h_canvas.data_ptr(), h_canvas.stride(0)))
+        if world > 1:
+            return step_sharded(True)
+        ctx.check(lib.spano_composite(ctx.h, cfg.kind, C.c_float(cfg.focal), cfg.n, descs_host, cfg.bands, cfg.sigma,
+                                      row0, row1, h_canvas.data_ptr(), h_canvas.stride(0)))
 
     def barrier():
         if world > 1:
@@ -279,7 +310,8 @@ def run_ours(args):
         if with_timers:
             ctx.timers_enable(True)
             ctx.timers_reset()
-        l0 = ctx.launch_count
+        count = lambda: ctx.launch_count + (ctx_s.launch_count if ctx_s is not None else 0)
+        l0 = count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(steps):
@@ -291,7 +323,7 @@ def run_ours(args):
         if with_timers:
             stage = ctx.timers_read()
             ctx.timers_enable(False)
-        launches = ctx.launch_count - l0
+        launches = count() - l0
         if world > 1:
             t = torch.tensor([ms], device=dev)
             tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
@@ -312,8 +344,7 @@ def run_ours(args):
         a, b = max(row0, cy), min(row1, cy + h)
         if b > a:
             my_T += w * (b - a)
-    warp_T = sum(w * h for ((tlx, tly), (w, h)) in zip(wl["corners"], wl["sizes"])
-                 if (tly - wl["min_y"]) < row1 and (tly - wl["min_y"] + h) > row0)
+    warp_T = sum(wl["sizes"][j][0] * wl["sizes"][j][1] for j in sorted(mine))   # tiles this rank warps (all at N = 1)
     fp32_peak = max(ctx.fp32_peak(0), ctx.fp32_peak(1), ctx.fp32_peak(2))
     peaks = {}
     try:
@@ -325,8 +356,7 @@ def run_ours(args):
     # Inside a step the warp + mask kernels of image i+1 overlap the blend of image i (auxiliary stream), so
     # their in-step event times measure the overlap, not the kernels.  Their own roofline is taken from an
     # isolated pass over the same tiles right here (same buffers, CUDA events on the launching stream).
-    iso_tiles = [j for j, ((tlx, tly), (w, h)) in enumerate(zip(wl["corners"], wl["sizes"]))
-                 if (tly - wl["min_y"]) < row1 and (tly - wl["min_y"] + h) > row0]
+    iso_tiles = sorted(mine)
     al16 = lambda v: (v + 15) // 16 * 16
     iso_tile = torch.empty(max(al16(3 * w) * h for (w, h) in wl["sizes"]), dtype=torch.uint8, device=dev)
     iso_mask = torch.empty(max(al16(w) * h for (w, h) in wl["sizes"]), dtype=torch.uint8, device=dev)
@@ -373,7 +403,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         ms_e, _, _ = timed(step_host, max(1, min(args.steps, 3)), 1)
-        h2d = sum(a.numel() for a in h_img) + sum(a.numel() for a in h_cut)
+        h2d = sum(a.numel() for a in h_img if a is not None) + sum(a.numel() for a in h_cut)
         d2h = (row1 - row0) * wl["W"] * 3
         e2e = {"value": canvas_mpx / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": ms_e, "api": "spano_composite (host buffers, pinned)"}
@@ -393,6 +423,9 @@ def run_ours(args):
                 "tile_mpx_per_s": wl["T"] / 1e6 / (ms * 1e-3)}
         print(json.dumps(line))
     if world > 1:
+        torch.cuda.synchronize()
+        tdist.barrier()
+        arenas.close()
         tdist.destroy_process_group()
 
 

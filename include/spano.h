@@ -210,6 +210,71 @@ int spano_dev_multiblend(spano_ctx *ctx, int n, const uint8_t *const *tiles, con
                          const size_t *orig_steps, const int *tl_x, const int *tl_y, const int *w, const int *h,
                          int bands, double sigma, int row0, int row1, int out_kind, void *out, size_t out_step);
 
+/* ---- tile-sharded multi-GPU path (one process per GPU, one box) -----------------------------
+ * The reference composites serially on one CPU (stitch_parameters::return_full,
+ * src/classes/_panorama.cpp:259-354: the loop over images of proj::get_proj_parameters followed by the
+ * loop over images inside blnd::multi_blend).  Across G GPUs the two loops shard differently:
+ *   - warp + validity mask (src/math/_projection.cpp:422-454) are per-IMAGE work and the mask's flood
+ *     fill is a whole-tile property: image j is uploaded, warped and masked ONCE, by its owner rank;
+ *   - the blend (src/math/_blending.cpp:186-252) shards by canvas ROW BAND: rank k accumulates and
+ *     normalises the canvas rows [row0,row1) from the rows of every tile that its band reads (its rows
+ *     plus the blur radius; BORDER_REFLECT is resolved inside the tile, so nothing else is needed).
+ * The exchange between the two is fused into the producing kernels: the warp kernel and the mask kernel
+ * store every tile row straight into the memory of the GPU(s) whose band reads it (peer-to-peer stores
+ * over NVLink / NVSwitch through pointers opened with spano_peer_open); no staging copy, no collective
+ * on the data path -- the caller only needs a barrier between "all owners have written" and "blend".
+ *
+ * A slice = rows [row0,row1) of one warped tile as stored at its band owner: `tile` / `valid` point at the
+ * storage of tile row `row0` (8UC3 / 8UC1, steps in bytes; 16-byte aligned rows recommended).           */
+typedef struct spano_slice {
+    int row0, row1;
+    uint8_t *tile;
+    size_t tile_step;
+    uint8_t *valid;
+    size_t valid_step;
+} spano_slice;
+
+/* Peer memory: cudaMalloc + cudaIpcGetMemHandle on the owner, cudaIpcOpenMemHandle on the peers
+ * (handle = the 64 opaque bytes of cudaIpcMemHandle_t, exchanged by the caller, e.g. with
+ * torch.distributed.all_gather_object).  spano_peer_close for opened pointers, spano_peer_free for owned. */
+int spano_peer_alloc(spano_ctx *ctx, size_t bytes, void **dptr, unsigned char handle[64]);
+int spano_peer_open(spano_ctx *ctx, const unsigned char handle[64], void **dptr);
+int spano_peer_close(spano_ctx *ctx, void *dptr);
+int spano_peer_free(spano_ctx *ctx, void *dptr);
+
+/* Owner side: warp image `im` (a3 + a6), build its validity mask (a4) and scatter tile and mask rows to the
+ * `n_slices` band slices (device pointers, local or peer).  Every tile row must be covered by at least one
+ * slice only if somebody reads it; rows covered by no slice are simply not stored.  im->mask_cut,
+ * im->valid_mask and im->intensity are ignored (the intensity field is not supported on this path).
+ * spano_dev_warp_scatter: im->src_bgr is a DEVICE pointer.  spano_warp_scatter: im->src_bgr is a HOST pointer
+ * (pinned for a truly asynchronous upload); the image is uploaded on the context's stream first.
+ * Both are asynchronous on the context's stream.                                                         */
+int spano_dev_warp_scatter(spano_ctx *ctx, int proj, float scale, const spano_image_desc *im, int n_slices,
+                           const spano_slice *slices);
+int spano_warp_scatter(spano_ctx *ctx, int proj, float scale, const spano_image_desc *im, int n_slices,
+                       const spano_slice *slices);
+
+/* Band side: blnd::multi_blend restricted to canvas rows [row0,row1), one image at a time
+ * (begin -> add x n -> finish == the loop body of multi_blend + the normalisation + blend()'s x255/convertTo).
+ * canvas_w/min_x/min_y are spano_pan_dimension's results for the WHOLE panorama.
+ * add: im gives the geometry (tl_x, tl_y, w, h) and mask_cut (+ mask_cut_w/h when at preview scale; it is
+ * up-scaled for the slice rows only); `slice` holds the tile rows this band reads, which must include
+ * [max(0, first-R), min(h, last+R)) of the tile rows [first,last) that fall into the band (R = ceil(3 sigma));
+ * the whole tile when h < 4R.  Tiles that do not touch the band are skipped.
+ * spano_dev_*: mask_cut and canvas are DEVICE pointers, asynchronous.  spano_blend_begin / spano_blend_add /
+ * spano_blend_finish: mask_cut / canvas are HOST pointers; finish returns when the band is in host memory.
+ * spano_blend_begin additionally takes the n images that will be added and uploads their preview-scale
+ * mask_cut right away, so that these small copies are queued on the copy engine AHEAD of the owners' large
+ * source uploads instead of behind them (spano_blend_add finds them by their mask_cut pointer; an image that
+ * was not announced, or a tile-sized mask, is uploaded on demand).                                          */
+int spano_dev_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma);
+int spano_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma,
+                      int n, const spano_image_desc *images);
+int spano_dev_blend_add(spano_ctx *ctx, const spano_image_desc *im, const spano_slice *slice);
+int spano_dev_blend_finish(spano_ctx *ctx, uint8_t *canvas, size_t canvas_step);
+int spano_blend_add(spano_ctx *ctx, const spano_image_desc *im, const spano_slice *slice);
+int spano_blend_finish(spano_ctx *ctx, uint8_t *canvas, size_t canvas_step);
+
 /* ---- measurement helpers ---------------------------------------------------------------
  * Time (ms, CUDA events on the context's stream) spent in the kernels of each stage since
  * the last spano_timers_reset: [0] warp  [1] validity mask  [2] blend  [3] normalise.

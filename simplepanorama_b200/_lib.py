@@ -33,6 +33,12 @@ class ImageDesc(C.Structure):
     ]
 
 
+class Slice(C.Structure):
+    """struct spano_slice: rows [row0,row1) of one warped tile as stored at its band owner"""
+    _fields_ = [("row0", C.c_int), ("row1", C.c_int), ("tile", C.c_void_p), ("tile_step", C.c_size_t),
+                ("valid", C.c_void_p), ("valid_step", C.c_size_t)]
+
+
 # every symbol include/spano.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "spano_version": (C.c_int, []),
@@ -68,6 +74,19 @@ SYMBOLS = {
                                  C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
     "spano_dev_multiblend": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_u8pp, c_sizep, c_u8pp, c_sizep, c_intp, c_intp,
                                        c_intp, c_intp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "spano_peer_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_ubyte)]),
+    "spano_peer_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "spano_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "spano_peer_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "spano_dev_warp_scatter": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.POINTER(ImageDesc), C.c_int, C.POINTER(Slice)]),
+    "spano_warp_scatter": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.POINTER(ImageDesc), C.c_int, C.POINTER(Slice)]),
+    "spano_dev_blend_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "spano_blend_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                                    C.POINTER(ImageDesc)]),
+    "spano_dev_blend_add": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.POINTER(Slice)]),
+    "spano_dev_blend_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "spano_blend_add": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.POINTER(Slice)]),
+    "spano_blend_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "spano_timers_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "spano_timers_reset": (C.c_int, [C.c_void_p]),
     "spano_timers_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),

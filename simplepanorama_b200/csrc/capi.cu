@@ -927,3 +927,304 @@ extern "C" int spano_dev_composite(spano_ctx *ctx, int proj, float scale, int n,
     Guard g(ctx);
     return composite_impl(ctx, proj, scale, n, images, bands, sigma, row0, row1, canvas, canvas_step, false);
 }
+
+// ---------------------------------------------------------------------------------------------
+// tile-sharded multi-GPU path: peer memory, owner-side warp + scatter, band-side incremental blend
+// ---------------------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "spano.h promises a 64-byte handle");
+
+extern "C" int spano_peer_alloc(spano_ctx *ctx, size_t bytes, void **dptr, unsigned char handle[64])
+{
+    if (!ctx || !dptr || !handle || bytes == 0) return ctx ? spano_fail(ctx, SPANO_E_INVALID, "spano_peer_alloc: bad argument") : SPANO_E_INVALID;
+    Guard g(ctx);
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return spano_fail(ctx, SPANO_E_NOMEM, "cudaMalloc(%zu B) failed: %s", bytes, cudaGetErrorString(e));
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return spano_fail(ctx, SPANO_E_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, 64);
+    *dptr = p;
+    return SPANO_OK;
+}
+
+extern "C" int spano_peer_open(spano_ctx *ctx, const unsigned char handle[64], void **dptr)
+{
+    if (!ctx || !dptr || !handle) return ctx ? spano_fail(ctx, SPANO_E_INVALID, "spano_peer_open: bad argument") : SPANO_E_INVALID;
+    Guard g(ctx);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    SPANO_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dptr = p;
+    return SPANO_OK;
+}
+
+extern "C" int spano_peer_close(spano_ctx *ctx, void *dptr)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (dptr) SPANO_CUDA(ctx, cudaIpcCloseMemHandle(dptr));
+    return SPANO_OK;
+}
+
+extern "C" int spano_peer_free(spano_ctx *ctx, void *dptr)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (dptr) {
+        SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SPANO_CUDA(ctx, cudaFree(dptr));
+    }
+    return SPANO_OK;
+}
+
+namespace {
+
+int warp_scatter_impl(spano_ctx *ctx, int proj, float scale, const spano_image_desc *im, int n_slices, const spano_slice *slices,
+                      bool host)
+{
+    if (!im || n_slices < 0 || (n_slices > 0 && !slices)) return spano_fail(ctx, SPANO_E_INVALID, "spano_warp_scatter: null argument");
+    if (n_slices > SPANO_MAX_SLICES) return spano_fail(ctx, SPANO_E_INVALID, "spano_warp_scatter: at most %d slices per tile", SPANO_MAX_SLICES);
+    if (int rc = valid_proj(ctx, proj, scale)) return rc;
+    if (int rc = check_image_args(ctx, im->src_bgr, im->src_w, im->src_h, im->src_step, 3, "source")) return rc;
+    if (im->w <= 0 || im->h <= 0) return spano_fail(ctx, SPANO_E_INVALID, "empty tile %dx%d", im->w, im->h);
+    if (!(im->gain > 0.0)) return spano_fail(ctx, SPANO_E_INVALID, "gain must be > 0");
+    if (im->intensity) return spano_fail(ctx, SPANO_E_INVALID, "the intensity field is not supported on the tile-sharded path");
+    if (int rc = check_remap_limits(ctx, im->src_w, im->src_h, im->w, im->h)) return rc;
+    SpanoScatter st, sm;
+    for (int d = 0; d < n_slices; ++d) {
+        const spano_slice &s = slices[d];
+        if (s.row0 < 0 || s.row1 > im->h || s.row1 <= s.row0) return spano_fail(ctx, SPANO_E_INVALID, "slice %d: rows [%d,%d) outside the tile (h=%d)", d, s.row0, s.row1, im->h);
+        if (!s.tile || !s.valid || s.tile_step < (size_t)im->w * 3 || s.valid_step < (size_t)im->w)
+            return spano_fail(ctx, SPANO_E_INVALID, "slice %d: null pointer or step too small", d);
+        st.row0[d] = sm.row0[d] = s.row0;
+        st.row1[d] = sm.row1[d] = s.row1;
+        st.base[d] = s.tile - (size_t)s.row0 * s.tile_step;   st.step[d] = s.tile_step;
+        sm.base[d] = s.valid - (size_t)s.row0 * s.valid_step; sm.step[d] = s.valid_step;
+    }
+    st.n = sm.n = n_slices;
+    if (n_slices == 0) return SPANO_OK;
+    const uint8_t *src = im->src_bgr;
+    size_t s_step = im->src_step;
+    if (host) {
+        uint8_t *stage = nullptr;
+        s_step = align_up((size_t)im->src_w * 3, 16);
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC, s_step * im->src_h + 16, (void **)&stage)) return rc;
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(stage, s_step, im->src_bgr, im->src_step, (size_t)im->src_w * 3, im->src_h, cudaMemcpyHostToDevice, ctx->stream));
+        src = stage;
+    }
+    uint8_t *dark = nullptr;
+    const size_t dark_step = align_up((size_t)im->w, 16);
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_DARK, dark_step * im->h, (void **)&dark)) return rc;
+    SpanoProjector P;
+    spano_host_set_camera(&P, proj, scale, im->K, im->R);
+    StageTimer t0(ctx, 0);
+    int n = launch_warp(ctx, P, src, im->src_w, im->src_h, s_step, im->gain, im->tl_x, im->tl_y, im->w, im->h, 0, im->h, nullptr, 0, dark,
+                        dark_step, nullptr, nullptr, &st);
+    if (n < 0) return n;
+    t0.stop(n);
+    StageTimer t1(ctx, 1);
+    n = launch_valid_mask(ctx, dark, im->w, im->h, dark_step, 3, nullptr, 0, &sm);
+    if (n < 0) return n;
+    t1.stop(n);
+    return SPANO_OK;
+}
+
+int blend_add_impl(spano_ctx *ctx, const spano_image_desc *im, const spano_slice *slice, bool host)
+{
+    spano_ctx::BlendSession &S = ctx->bs;
+    if (!S.open) return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_add without spano_dev_blend_begin");
+    if (!im || !slice) return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_add: null argument");
+    if (im->w <= 0 || im->h <= 0) return spano_fail(ctx, SPANO_E_INVALID, "empty tile %dx%d", im->w, im->h);
+    const int cy = im->tl_y - S.my;
+    const int first = std::max(0, S.row0 - cy), last = std::min(im->h, S.row1 - cy);
+    if (last <= first) return SPANO_OK;   // the tile does not touch this band
+    const int R = S.radius;
+    const int need0 = (im->h < 4 * R) ? 0 : std::max(0, first - R), need1 = (im->h < 4 * R) ? im->h : std::min(im->h, last + R);
+    if (slice->row0 > need0 || slice->row1 < need1)
+        return spano_fail(ctx, SPANO_E_INVALID, "slice rows [%d,%d) do not cover the rows the band reads [%d,%d)", slice->row0, slice->row1, need0, need1);
+    if (!slice->tile || !slice->valid || slice->tile_step < (size_t)im->w * 3 || slice->valid_step < (size_t)im->w)
+        return spano_fail(ctx, SPANO_E_INVALID, "slice: null pointer or step too small");
+    const bool small = im->mask_cut_w > 0 || im->mask_cut_h > 0;
+    if (int rc = check_image_args(ctx, im->mask_cut, small ? im->mask_cut_w : im->w, small ? im->mask_cut_h : im->h, im->mask_cut_step, 1, "mask_cut"))
+        return rc;
+    const size_t m_step = align_up((size_t)im->w, 16);
+    const uint8_t *cut_v = nullptr;   // virtual address of mask_cut row 0 at tile size
+    size_t c_step = m_step;
+    if (small || host) {
+        uint8_t *cutbuf = nullptr;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTMASK, m_step * (need1 - need0) + 256, (void **)&cutbuf)) return rc;
+        uint8_t *cut_base = cutbuf - (size_t)need0 * m_step;
+        if (small) {
+            const uint8_t *sm = im->mask_cut;
+            size_t sm_step = im->mask_cut_step;
+            const spano_ctx::BlendSession::Staged *hit = nullptr;
+            if (host)
+                for (const auto &st : S.staged)
+                    if (st.host == im->mask_cut) { hit = &st; break; }
+            if (hit) {
+                sm = hit->dev;
+                sm_step = hit->step;
+            } else if (host) {
+                uint8_t *stage = nullptr;
+                sm_step = align_up((size_t)im->mask_cut_w, 16);
+                if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTSMALL2, sm_step * im->mask_cut_h + 256, (void **)&stage)) return rc;
+                SPANO_CUDA(ctx, cudaMemcpy2DAsync(stage, sm_step, im->mask_cut, im->mask_cut_step, (size_t)im->mask_cut_w, im->mask_cut_h,
+                                                  cudaMemcpyHostToDevice, ctx->stream));
+                sm = stage;
+            }
+            int k = launch_resize_mask(ctx, sm, im->mask_cut_w, im->mask_cut_h, sm_step, cut_base, im->w, im->h, m_step, need0, need1);
+            if (k < 0) return k;
+        } else {
+            SPANO_CUDA(ctx, cudaMemcpy2DAsync(cutbuf, m_step, im->mask_cut + (size_t)need0 * im->mask_cut_step, im->mask_cut_step, (size_t)im->w,
+                                              need1 - need0, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        cut_v = cut_base;
+    } else {
+        cut_v = im->mask_cut;
+        c_step = im->mask_cut_step;
+    }
+    StageTimer t2(ctx, 2);
+    const BlendTile bt{slice->tile - (size_t)slice->row0 * slice->tile_step, slice->tile_step, cut_v, c_step,
+                       slice->valid - (size_t)slice->row0 * slice->valid_step, slice->valid_step, im->w, im->h, im->tl_x - S.mx, cy};
+    int k = launch_blend_tile(ctx, bt, S.bands, S.radius, S.acc, S.cw, S.row0, S.row1);
+    if (k < 0) return k;
+    t2.stop(k);
+    return SPANO_OK;
+}
+
+int blend_finish_impl(spano_ctx *ctx, uint8_t *canvas, size_t canvas_step, bool host)
+{
+    spano_ctx::BlendSession &S = ctx->bs;
+    if (!S.open) return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_finish without spano_dev_blend_begin");
+    if (!canvas || canvas_step < (size_t)S.cw * 3) return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_finish: null canvas or step too small");
+    const int rows = S.row1 - S.row0;
+    uint8_t *d_canvas = canvas;
+    size_t d_step = canvas_step;
+    if (host) {
+        d_step = align_up((size_t)S.cw * 3, 16);
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_CANVAS, d_step * rows, (void **)&d_canvas)) return rc;
+    }
+    StageTimer t3(ctx, 3);
+    int k = launch_normalise(ctx, S.acc, S.cw, rows, S.bands, SPANO_OUT_U8, d_canvas, d_step);
+    if (k < 0) return k;
+    t3.stop(k);
+    S.open = false;
+    if (host) {
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(canvas, canvas_step, d_canvas, d_step, (size_t)S.cw * 3, rows, cudaMemcpyDeviceToHost, ctx->stream));
+        SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SPANO_OK;
+}
+
+} // namespace
+
+extern "C" int spano_dev_warp_scatter(spano_ctx *ctx, int proj, float scale, const spano_image_desc *im, int n_slices, const spano_slice *slices)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return warp_scatter_impl(ctx, proj, scale, im, n_slices, slices, false);
+}
+
+extern "C" int spano_warp_scatter(spano_ctx *ctx, int proj, float scale, const spano_image_desc *im, int n_slices, const spano_slice *slices)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return warp_scatter_impl(ctx, proj, scale, im, n_slices, slices, true);
+}
+
+namespace {
+int blend_begin_impl(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma);
+}
+
+extern "C" int spano_dev_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return blend_begin_impl(ctx, canvas_w, min_x, min_y, row0, row1, bands, sigma);
+}
+
+extern "C" int spano_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma,
+                                 int n, const spano_image_desc *images)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (n < 0 || (n > 0 && !images)) return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_begin: null images");
+    if (int rc = blend_begin_impl(ctx, canvas_w, min_x, min_y, row0, row1, bands, sigma)) return rc;
+    spano_ctx::BlendSession &S = ctx->bs;
+    // preview-scale masks of the tiles that touch this band: one staging arena, uploaded now
+    size_t total = 0;
+    std::vector<size_t> off(n, (size_t)-1);
+    for (int j = 0; j < n; ++j) {
+        const spano_image_desc &im = images[j];
+        if (!(im.mask_cut_w > 0 || im.mask_cut_h > 0) || !im.mask_cut) continue;
+        const int cy = im.tl_y - S.my;
+        if (std::min(im.h, S.row1 - cy) <= std::max(0, S.row0 - cy)) continue;
+        if (int rc = check_image_args(ctx, im.mask_cut, im.mask_cut_w, im.mask_cut_h, im.mask_cut_step, 1, "mask_cut")) { S.open = false; return rc; }
+        off[j] = total;
+        total += align_up(align_up((size_t)im.mask_cut_w, 16) * im.mask_cut_h, 256);
+    }
+    if (total) {
+        uint8_t *arena = nullptr;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTSMALL, total, (void **)&arena)) { S.open = false; return rc; }
+        for (int j = 0; j < n; ++j) {
+            if (off[j] == (size_t)-1) continue;
+            const spano_image_desc &im = images[j];
+            const size_t st = align_up((size_t)im.mask_cut_w, 16);
+            SPANO_CUDA(ctx, cudaMemcpy2DAsync(arena + off[j], st, im.mask_cut, im.mask_cut_step, (size_t)im.mask_cut_w, im.mask_cut_h,
+                                              cudaMemcpyHostToDevice, ctx->stream));
+            S.staged.push_back({im.mask_cut, arena + off[j], st});
+        }
+    }
+    return SPANO_OK;
+}
+
+namespace {
+int blend_begin_impl(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma)
+{
+    if (canvas_w <= 0 || row1 <= row0 || row0 < 0) return spano_fail(ctx, SPANO_E_INVALID, "spano_dev_blend_begin: empty band [%d,%d) x %d", row0, row1, canvas_w);
+    const int radius = launch_blend_setup(ctx, bands, sigma);
+    if (radius < 0) return radius;
+    spano_ctx::BlendSession &S = ctx->bs;
+    S.cw = canvas_w;  S.mx = min_x;  S.my = min_y;  S.row0 = row0;  S.row1 = row1;  S.bands = bands;  S.radius = radius;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_ACC, (size_t)canvas_w * (row1 - row0) * sizeof(float4), (void **)&S.acc)) return rc;
+    StageTimer t(ctx, 2);
+    if (int rc = launch_blend_clear(ctx, S.acc, canvas_w, row1 - row0)) return rc;
+    t.stop(0);
+    S.staged.clear();
+    S.open = true;
+    return SPANO_OK;
+}
+} // namespace
+
+extern "C" int spano_dev_blend_add(spano_ctx *ctx, const spano_image_desc *im, const spano_slice *slice)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return blend_add_impl(ctx, im, slice, false);
+}
+
+extern "C" int spano_blend_add(spano_ctx *ctx, const spano_image_desc *im, const spano_slice *slice)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return blend_add_impl(ctx, im, slice, true);
+}
+
+extern "C" int spano_dev_blend_finish(spano_ctx *ctx, uint8_t *canvas, size_t canvas_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return blend_finish_impl(ctx, canvas, canvas_step, false);
+}
+
+extern "C" int spano_blend_finish(spano_ctx *ctx, uint8_t *canvas, size_t canvas_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return blend_finish_impl(ctx, canvas, canvas_step, true);
+}

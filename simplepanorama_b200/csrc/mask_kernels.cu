@@ -146,7 +146,26 @@ __global__ void resolve_bits_kernel(const uint8_t *dark, size_t dark_step, int w
 
 // mask = 0 where any outside pixel lies in the (2r+1)^2 window (out-of-image taps ignored), else 255:
 // r erosions with a 3x3 box == one (2r+1)^2 minimum.  One thread = one 32-pixel word of one row.
-__global__ void erode_bits_kernel(const uint32_t *bits, int words_per_row, int w, int h, int r, uint8_t *mask, size_t mask_step)
+__device__ __forceinline__ void store_mask_word(uint8_t *dst, uint32_t o, int x0, int w)
+{
+    if (x0 + 32 <= w && (((uintptr_t)dst) & 15) == 0) {
+        uint32_t v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint32_t nib = (o >> (4 * q)) & 15u;
+            // 4 pixels -> 4 bytes: 0x00 where the bit is set, 0xFF otherwise
+            v[q] = ((nib & 1u) ? 0u : 0x000000FFu) | ((nib & 2u) ? 0u : 0x0000FF00u) | ((nib & 4u) ? 0u : 0x00FF0000u) |
+                   ((nib & 8u) ? 0u : 0xFF000000u);
+        }
+        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    } else {
+        for (int i = 0; i < 32 && x0 + i < w; ++i) dst[i] = ((o >> i) & 1u) ? 0 : 255;
+    }
+}
+
+__global__ void erode_bits_kernel(const uint32_t *bits, int words_per_row, int w, int h, int r, uint8_t *mask, size_t mask_step,
+                                  const SpanoScatter sc)
 {
     const int wx = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
@@ -166,20 +185,12 @@ __global__ void erode_bits_kernel(const uint32_t *bits, int words_per_row, int w
         o |= (mid >> d) | (hi << (32 - d));   // outside pixel d to the right
     }
     const int x0 = wx * 32;
-    uint8_t *dst = mask + (size_t)y * mask_step + x0;
-    if (x0 + 32 <= w && (((uintptr_t)dst) & 15) == 0) {
-        uint32_t v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const uint32_t nib = (o >> (4 * q)) & 15u;
-            // 4 pixels -> 4 bytes: 0x00 where the bit is set, 0xFF otherwise
-            v[q] = ((nib & 1u) ? 0u : 0x000000FFu) | ((nib & 2u) ? 0u : 0x0000FF00u) | ((nib & 4u) ? 0u : 0x00FF0000u) |
-                   ((nib & 8u) ? 0u : 0xFF000000u);
-        }
-        reinterpret_cast<uint4 *>(dst)[0] = make_uint4(v[0], v[1], v[2], v[3]);
-        reinterpret_cast<uint4 *>(dst)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    if (sc.n > 0) {
+        // tile-sharded multi-GPU path: row y goes to every band slice that reads it (possibly peer-GPU memory)
+        for (int d = 0; d < sc.n; ++d)
+            if (y >= sc.row0[d] && y < sc.row1[d]) store_mask_word(sc.base[d] + (size_t)y * sc.step[d] + x0, o, x0, w);
     } else {
-        for (int i = 0; i < 32 && x0 + i < w; ++i) dst[i] = ((o >> i) & 1u) ? 0 : 255;
+        store_mask_word(mask + (size_t)y * mask_step + x0, o, x0, w);
     }
 }
 
@@ -188,7 +199,7 @@ __global__ void erode_bits_kernel(const uint32_t *bits, int words_per_row, int w
 // `dark` rows must be 16-byte aligned (dark_step % 16 == 0, base from cudaMalloc): every caller in this
 // library allocates it that way.
 int launch_valid_mask(spano_ctx *ctx, const uint8_t *dark, int w, int h, size_t dark_step, int erode_iters,
-                      uint8_t *mask, size_t mask_step)
+                      uint8_t *mask, size_t mask_step, const SpanoScatter *scatter)
 {
     if (w <= 0 || h <= 0) return 0;
     if (erode_iters < 0 || erode_iters > 15)
@@ -207,7 +218,7 @@ int launch_valid_mask(spano_ctx *ctx, const uint8_t *dark, int w, int h, size_t 
     ccl_merge_kernel<<<grid, block, 0, ctx->stream>>>(dark, dark_step, w, h, groups, L);
     resolve_bits_kernel<<<grid, block, 0, ctx->stream>>>(dark, dark_step, w, h, groups, L, reinterpret_cast<uint16_t *>(bits), 2 * wpr);
     dim3 eblock(64), egrid((wpr + 63) / 64, h);
-    erode_bits_kernel<<<egrid, eblock, 0, ctx->stream>>>(bits, wpr, w, h, erode_iters, mask, mask_step);
+    erode_bits_kernel<<<egrid, eblock, 0, ctx->stream>>>(bits, wpr, w, h, erode_iters, mask, mask_step, scatter ? *scatter : SpanoScatter());
     SPANO_CUDA(ctx, cudaGetLastError());
     ctx->launches += 4;
     return 4;

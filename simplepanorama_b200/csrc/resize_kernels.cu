@@ -49,11 +49,11 @@ __global__ void resize_tables_kernel(int sw, int sh, int dw, int dh, AxisEntry *
 }
 
 __global__ void resize_linear_u8_kernel(const uint8_t *src, int sw, int sh, size_t sstep, const AxisEntry *xt,
-                                        const AxisEntry *yt, uint8_t *dst, int dw, int dh, size_t dstep)
+                                        const AxisEntry *yt, uint8_t *dst, int dw, int dh, size_t dstep, int row_begin)
 {
     // 4 consecutive destination pixels per thread, one 32-bit store when the row allows it
     const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int dy = blockIdx.y;
+    const int dy = row_begin + blockIdx.y;
     if (dx0 >= dw || dy >= dh) return;
     const AxisEntry ey = yt[dy];
     const int y0 = min(max(ey.ofs, 0), sh - 1), y1 = min(max(ey.ofs + 1, 0), sh - 1);
@@ -148,16 +148,19 @@ int launch_adjust_intensity(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t s
 }
 
 int launch_resize_mask(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_t sstep, uint8_t *dst, int dw, int dh,
-                       size_t dstep)
+                       size_t dstep, int row_begin, int row_end)
 {
     if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return spano_fail(ctx, SPANO_E_INVALID, "resize: empty image");
+    if (row_end < 0 || row_end > dh) row_end = dh;
+    if (row_begin < 0) row_begin = 0;
+    if (row_end <= row_begin) return 0;
     AxisEntry *tab = nullptr;
     int rc = spano_reserve(ctx, spano_ctx::BUF_RESIZE, (size_t)(dw + dh) * sizeof(AxisEntry), (void **)&tab);
     if (rc) return rc;
     const int n = dw > dh ? dw : dh;
     resize_tables_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sw, sh, dw, dh, tab, tab + dw);
-    dim3 block(128), grid((dw + 511) / 512, dh);
-    resize_linear_u8_kernel<<<grid, block, 0, ctx->stream>>>(src, sw, sh, sstep, tab, tab + dw, dst, dw, dh, dstep);
+    dim3 block(128), grid((dw + 511) / 512, row_end - row_begin);
+    resize_linear_u8_kernel<<<grid, block, 0, ctx->stream>>>(src, sw, sh, sstep, tab, tab + dw, dst, dw, dh, dstep, row_begin);
     SPANO_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
     return 2;

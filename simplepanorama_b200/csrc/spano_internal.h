@@ -49,6 +49,15 @@ struct spano_ctx {
            BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_COUNT };
     DeviceBuffer buf[BUF_COUNT];
     std::vector<void *> owned; // extra allocations freed at destroy / end of call
+    // incremental band blend (spano_dev_blend_begin / add / finish)
+    struct BlendSession {
+        bool open = false;
+        int cw = 0, mx = 0, my = 0, row0 = 0, row1 = 0, bands = 0, radius = 0;
+        float4 *acc = nullptr;
+        // host variant: preview-scale masks uploaded at begin (host pointer -> device copy, step)
+        struct Staged { const uint8_t *host; const uint8_t *dev; size_t step; };
+        std::vector<Staged> staged;
+    } bs;
     // timers
     bool timers_on = false;
     float stage_ms[4] = {0, 0, 0, 0};
@@ -67,18 +76,30 @@ int spano_reserve(spano_ctx *ctx, int which, size_t bytes, void **out);
                               __LINE__);                                                           \
     } while (0)
 
+// Row-range scatter table of the tile-sharded multi-GPU path: a kernel that produces tile rows writes row v to
+// every entry with row0 <= v < row1, at base + v * step (base is the VIRTUAL address of tile row 0, i.e. the
+// slice's storage minus row0 * step).  The bases may be peer-GPU memory (NVLink P2P stores).
+#define SPANO_MAX_SLICES 16
+struct SpanoScatter {
+    int n = 0;
+    int row0[SPANO_MAX_SLICES], row1[SPANO_MAX_SLICES];
+    uint8_t *base[SPANO_MAX_SLICES];
+    size_t step[SPANO_MAX_SLICES];
+};
+
 // ---- kernel launchers (each returns the number of kernels launched, or <0) -------------
 // warp_kernels.cu
 int launch_warp(spano_ctx *ctx, const SpanoProjector &P, const uint8_t *src, int src_w, int src_h, size_t src_step,
                 double gain, int tl_x, int tl_y, int dst_w, int dst_h, int row_begin, int row_end, uint8_t *dst,
-                size_t dst_step, uint8_t *dark, size_t dark_step, float *xmap = nullptr, float *ymap = nullptr);
+                size_t dst_step, uint8_t *dark, size_t dark_step, float *xmap = nullptr, float *ymap = nullptr,
+                const SpanoScatter *scatter = nullptr);
 int launch_remap(spano_ctx *ctx, const uint8_t *src, int src_w, int src_h, size_t src_step, const float *xmap,
                  const float *ymap, int dst_w, int dst_h, uint8_t *dst, size_t dst_step);
 int launch_gain(spano_ctx *ctx, uint8_t *img, int w, int h, size_t step, double gain);
 int launch_dark_flags(spano_ctx *ctx, const uint8_t *bgr, int w, int h, size_t step, uint8_t *dark, size_t dark_step);
 // mask_kernels.cu
 int launch_valid_mask(spano_ctx *ctx, const uint8_t *dark, int w, int h, size_t dark_step, int erode_iters,
-                      uint8_t *mask, size_t mask_step);
+                      uint8_t *mask, size_t mask_step, const SpanoScatter *scatter = nullptr);
 // blend_kernels.cu
 struct BlendTile {
     const uint8_t *tile;   size_t tile_step;   // 8UC3, gain applied
@@ -95,8 +116,9 @@ int launch_normalise(spano_ctx *ctx, const float4 *acc, int canvas_w, int rows, 
                      size_t out_step, int col0 = 0, int col1 = -1);
 int launch_fp32_peak(spano_ctx *ctx, int variant, double *tflops);
 // resize_kernels.cu: cv::resize(CV_8UC1, INTER_LINEAR) of the preview-scale seam masks
+// rows [row_begin,row_end) of the dw x dh result are written at dst + row * dstep (row_end < 0: all rows)
 int launch_resize_mask(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_t sstep, uint8_t *dst, int dw, int dh,
-                       size_t dstep);
+                       size_t dstep, int row_begin = 0, int row_end = -1);
 int launch_adjust_intensity(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, const float *field, int fw, int fh,
                             size_t fpitch_elems);
 // disk_kernels.cu: stereographic centre fix (util::RadialNormalizer state + normalised radius)

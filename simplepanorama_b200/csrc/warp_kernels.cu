@@ -45,6 +45,7 @@ struct WarpParams {
     int apply_gain;
     int src_aligned8; // src pointer and step are multiples of 4: aligned 32-bit window loads allowed
     const float *colA, *colB, *rowA, *rowB;
+    SpanoScatter sc; // n > 0: the tile rows go to these (possibly peer-GPU) slices instead of `dst`
 };
 
 // per-column / per-row trigonometry tables
@@ -242,23 +243,30 @@ __global__ void __launch_bounds__(WARP_BLOCK_X *WARP_BLOCK_Y) warp_kernel(const 
         px[i] = s;
         dark |= d << (8 * i);
     }
-    uint8_t *drow = P.dst + (size_t)v * P.dst_step + (size_t)x0 * 3;
     const bool full = x0 + WARP_PX_PER_THREAD <= P.dst_w;
-    if (!P.dst) {
-        // flags-only pass (validity masks computed on another rank's behalf): no tile store
-    } else if (full && (((uintptr_t)drow) & 3) == 0) {
-        // 4 px = 12 B = three 32-bit words; a warp writes 384 contiguous bytes
-        uint32_t *q = reinterpret_cast<uint32_t *>(drow);
-        q[0] = px[0] | (px[1] << 24);
-        q[1] = (px[1] >> 8) | (px[2] << 16);
-        q[2] = (px[2] >> 16) | (px[3] << 8);
-    } else {
-        for (int i = 0; i < WARP_PX_PER_THREAD && x0 + i < P.dst_w; ++i) {
-            drow[3 * i] = (uint8_t)px[i];
-            drow[3 * i + 1] = (uint8_t)(px[i] >> 8);
-            drow[3 * i + 2] = (uint8_t)(px[i] >> 16);
+    auto store_row = [&](uint8_t *drow) {
+        if (full && (((uintptr_t)drow) & 3) == 0) {
+            // 4 px = 12 B = three 32-bit words; a warp writes 384 contiguous bytes
+            uint32_t *q = reinterpret_cast<uint32_t *>(drow);
+            q[0] = px[0] | (px[1] << 24);
+            q[1] = (px[1] >> 8) | (px[2] << 16);
+            q[2] = (px[2] >> 16) | (px[3] << 8);
+        } else {
+            for (int i = 0; i < WARP_PX_PER_THREAD && x0 + i < P.dst_w; ++i) {
+                drow[3 * i] = (uint8_t)px[i];
+                drow[3 * i + 1] = (uint8_t)(px[i] >> 8);
+                drow[3 * i + 2] = (uint8_t)(px[i] >> 16);
+            }
         }
-    }
+    };
+    if (P.sc.n > 0) {
+        // tile-sharded multi-GPU path: the row goes to every band slice that reads it (its band plus the blur
+        // halo of the neighbours), straight into the owning GPU's memory; the row index is warp-uniform
+        for (int d = 0; d < P.sc.n; ++d)
+            if (v >= P.sc.row0[d] && v < P.sc.row1[d]) store_row(P.sc.base[d] + (size_t)v * P.sc.step[d] + (size_t)x0 * 3);
+    } else if (P.dst) {
+        store_row(P.dst + (size_t)v * P.dst_step + (size_t)x0 * 3);
+    }   // else: flags-only pass (validity masks computed on another rank's behalf), no tile store
     if (P.dark) {
         uint8_t *krow = P.dark + (size_t)v * P.dark_step + x0;
         if (full && (((uintptr_t)krow) & 3) == 0) *reinterpret_cast<uint32_t *>(krow) = dark;
@@ -329,7 +337,7 @@ int launch_remap(spano_ctx *ctx, const uint8_t *src, int src_w, int src_h, size_
 
 int launch_warp(spano_ctx *ctx, const SpanoProjector &proj, const uint8_t *src, int src_w, int src_h, size_t src_step,
                 double gain, int tl_x, int tl_y, int dst_w, int dst_h, int row_begin, int row_end, uint8_t *dst,
-                size_t dst_step, uint8_t *dark, size_t dark_step, float *xmap, float *ymap)
+                size_t dst_step, uint8_t *dark, size_t dark_step, float *xmap, float *ymap, const SpanoScatter *scatter)
 {
     if (row_end <= row_begin) return 0;
     int launches = 0;
@@ -353,6 +361,7 @@ int launch_warp(spano_ctx *ctx, const SpanoProjector &proj, const uint8_t *src, 
     P.colB = tables + dst_w;
     P.rowA = tables + 2 * (size_t)dst_w;
     P.rowB = tables + 2 * (size_t)dst_w + dst_h;
+    if (scatter) P.sc = *scatter;
 
     if (proj.kind != SPANO_STEREOGRAPHIC) {
         const int n = dst_w > dst_h ? dst_w : dst_h;

@@ -51,3 +51,187 @@ def gather_bands(band, bands, canvas_w: int, rank: int, world: int, device=None)
     if rank != 0:
         return None
     return torch.cat([recv[r][: bands[r][1] - bands[r][0]] for r in range(world)], dim=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# Tile-sharded path (include/spano.h, "tile-sharded multi-GPU path"): images shard by owner for the
+# warp + validity mask, the canvas shards by row band for the blend, and the owners store every tile
+# row straight into the memory of the band(s) that read it (NVLink peer stores from the warp / mask
+# kernels).  The plan below is pure host arithmetic, identical on every rank.
+# ---------------------------------------------------------------------------------------------
+from dataclasses import dataclass, field
+
+
+def _al(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
+@dataclass
+class ShardPlan:
+    world: int
+    radius: int
+    canvas_w: int
+    canvas_h: int
+    min_x: int
+    min_y: int
+    corners: list
+    sizes: list
+    bands: list                      # [(row0, row1)] per rank
+    owner: list                      # owner rank of tile j
+    rounds: list                     # [[tile ids]]: round t holds at most one tile per owner
+    slices: list                     # slices[k][j] = (r0, r1) tile rows of j stored at rank k, or None
+    offsets: list                    # offsets[k][j] = (tile_off, valid_off) into rank k's arena, or None
+    arena_bytes: list                # per rank
+    tile_step: list = field(default_factory=list)
+    valid_step: list = field(default_factory=list)
+
+
+def plan_tile_shards(corners, sizes, world: int, sigma: float = 7.0) -> ShardPlan:
+    """corners[j] = (tl_x, tl_y), sizes[j] = (w, h) of every warped tile (spano_warp_roi)."""
+    import math
+    n = len(sizes)
+    radius = int(math.ceil(3 * sigma))
+    xs0 = min(c[0] for c in corners); ys0 = min(c[1] for c in corners)
+    xs1 = max(c[0] + s[0] for c, s in zip(corners, sizes)); ys1 = max(c[1] + s[1] for c, s in zip(corners, sizes))
+    W, H = xs1 - xs0, ys1 - ys0           # == util::get_pan_dimension
+    bands = plan_row_bands(list(zip(corners, sizes)), world, ys0, H)
+    owner = [j % world for j in range(n)]
+    rounds = [list(range(t, min(n, t + world))) for t in range(0, n, world)]
+    tile_step = [_al(3 * w, 16) for (w, h) in sizes]
+    valid_step = [_al(w, 16) for (w, h) in sizes]
+    slices, offsets, arena = [], [], []
+    for k in range(world):
+        b0, b1 = bands[k]
+        sl, of, fill = [], [], 0
+        for j in range(n):
+            (w, h), cy = sizes[j], corners[j][1] - ys0
+            first, last = max(0, b0 - cy), min(h, b1 - cy)
+            if last <= first:
+                sl.append(None); of.append(None)
+                continue
+            r0, r1 = (0, h) if h < 4 * radius else (max(0, first - radius), min(h, last + radius))
+            sl.append((r0, r1))
+            t_off = fill
+            fill = _al(fill + tile_step[j] * (r1 - r0), 256)
+            v_off = fill
+            fill = _al(fill + valid_step[j] * (r1 - r0), 256)
+            of.append((t_off, v_off))
+        slices.append(sl); offsets.append(of); arena.append(max(fill, 256))
+    return ShardPlan(world, radius, W, H, xs0, ys0, list(corners), list(sizes), bands, owner, rounds, slices, offsets, arena,
+                     tile_step, valid_step)
+
+
+def scatter_slices(plan: ShardPlan, j: int, arena_ptrs):
+    """ctypes array of spano_slice: where the rows of tile j go (arena_ptrs[k] = base of rank k's arena as
+    seen from THIS process: its own allocation or a peer mapping)."""
+    from ._lib import Slice
+    out = []
+    for k in range(plan.world):
+        if plan.slices[k][j] is None:
+            continue
+        r0, r1 = plan.slices[k][j]
+        t_off, v_off = plan.offsets[k][j]
+        out.append(Slice(r0, r1, arena_ptrs[k] + t_off, plan.tile_step[j], arena_ptrs[k] + v_off, plan.valid_step[j]))
+    return (Slice * max(1, len(out)))(*out), len(out)
+
+
+def band_slice(plan: ShardPlan, k: int, j: int, arena_ptr: int):
+    """spano_slice of tile j inside rank k's own arena (None when the tile does not touch band k)."""
+    from ._lib import Slice
+    if plan.slices[k][j] is None:
+        return None
+    r0, r1 = plan.slices[k][j]
+    t_off, v_off = plan.offsets[k][j]
+    return Slice(r0, r1, arena_ptr + t_off, plan.tile_step[j], arena_ptr + v_off, plan.valid_step[j])
+
+
+class PeerArenas:
+    """One slice arena per rank, every arena mapped into every process (cudaIpc through the C ABI).
+    ptrs[k] = rank k's arena as addressable from this process."""
+
+    def __init__(self, ctx, plan: ShardPlan, rank: int, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world = ctx, rank, plan.world
+        own = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        ctx.check(ctx.lib.spano_peer_alloc(ctx.h, plan.arena_bytes[rank], C.byref(own), handle))
+        self.own = own.value
+        handles = [None] * plan.world
+        dist.all_gather_object(handles, bytes(handle), group=group)
+        self.ptrs = []
+        for k in range(plan.world):
+            if k == rank:
+                self.ptrs.append(self.own)
+                continue
+            p = C.c_void_p()
+            hb = (C.c_ubyte * 64).from_buffer_copy(handles[k])
+            ctx.check(ctx.lib.spano_peer_open(ctx.h, hb, C.byref(p)))
+            self.ptrs.append(p.value)
+
+    def close(self):
+        import ctypes as C
+        for k, p in enumerate(self.ptrs):
+            if k != self.rank and p:
+                self.ctx.lib.spano_peer_close(self.ctx.h, C.c_void_p(p))
+        if self.own:
+            self.ctx.lib.spano_peer_free(self.ctx.h, C.c_void_p(self.own))
+        self.ptrs, self.own = [], None
+
+
+def scatter_tile(ctx, plan: ShardPlan, j: int, desc, arena_ptrs, kind: int, focal: float, host: bool = False):
+    """Owner side of one image: warp + validity mask, rows stored into the band arenas."""
+    import ctypes as C
+    sl, n = scatter_slices(plan, j, arena_ptrs)
+    fn = ctx.lib.spano_warp_scatter if host else ctx.lib.spano_dev_warp_scatter
+    ctx.check(fn(ctx.h, int(kind), C.c_float(focal), C.byref(desc), n, sl))
+
+
+def blend_add(ctx, plan: ShardPlan, k: int, j: int, desc, arena_ptr: int, host: bool = False):
+    """Band side of one image (no-op when tile j does not touch band k)."""
+    import ctypes as C
+    s = band_slice(plan, k, j, arena_ptr)
+    if s is None:
+        return
+    fn = ctx.lib.spano_blend_add if host else ctx.lib.spano_dev_blend_add
+    ctx.check(fn(ctx.h, C.byref(desc), C.byref(s)))
+
+
+def blend_begin(ctx, plan: ShardPlan, k: int, bands: int, sigma: float, host_descs=None):
+    """host_descs: the spano_image_desc array with HOST mask_cut pointers (host-buffer variant: the preview-scale
+    masks are uploaded right away, ahead of the owners' source uploads)."""
+    r0, r1 = plan.bands[k]
+    if host_descs is not None:
+        ctx.check(ctx.lib.spano_blend_begin(ctx.h, plan.canvas_w, plan.min_x, plan.min_y, r0, r1, int(bands), float(sigma),
+                                            len(host_descs), host_descs))
+    else:
+        ctx.check(ctx.lib.spano_dev_blend_begin(ctx.h, plan.canvas_w, plan.min_x, plan.min_y, r0, r1, int(bands), float(sigma)))
+
+
+def blend_finish(ctx, canvas_ptr: int, canvas_step: int, host: bool = False):
+    import ctypes as C
+    fn = ctx.lib.spano_blend_finish if host else ctx.lib.spano_dev_blend_finish
+    ctx.check(fn(ctx.h, C.c_void_p(canvas_ptr), canvas_step))
+
+
+def gather_bands_into(canvas, band, bands, rank: int, world: int):
+    """Gather the finished bands into rank 0's preallocated (H, W, 3) uint8 `canvas` (NCCL send/recv straight
+    into the canvas rows; rank 0's own band is expected to be a view of `canvas` already).  `band` is this
+    rank's (rows, W, 3) tensor."""
+    import torch.distributed as dist
+    if world == 1:
+        return canvas
+    ops = []
+    if rank == 0:
+        for k in range(1, world):
+            r0, r1 = bands[k]
+            if r1 > r0:
+                ops.append(dist.P2POp(dist.irecv, canvas[r0:r1], k))
+    else:
+        r0, r1 = bands[rank]
+        if r1 > r0:
+            ops.append(dist.P2POp(dist.isend, band, 0))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return canvas if rank == 0 else None

@@ -118,3 +118,49 @@ def test_disk_reproj_geometry_matches_oracle(spano_lib, oracle):
             outs, _, ocorners = oracle.disk_reproj(tiles, corners, ansatz, radius, quad, erode_iters=0)
             assert new_c == ocorners
             assert new_s == [(o.shape[1], o.shape[0]) for o in outs]
+
+
+def test_tile_shard_plan_covers_every_band():
+    """plan_tile_shards (host arithmetic of the tile-sharded multi-GPU path): bands partition the canvas, every
+    tile row a band reads (its rows +- the blur radius, inside the tile) is in that band's slice, arena slots do
+    not overlap, and every round holds at most one tile per owner."""
+    from simplepanorama_b200 import dist
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 3, 4, 8):
+        n = int(rng.integers(1, 30))
+        sizes = [(int(rng.integers(1, 700)), int(rng.integers(1, 500))) for _ in range(n)]
+        corners = [(int(rng.integers(-300, 3000)), int(rng.integers(-200, 400))) for _ in range(n)]
+        sp = dist.plan_tile_shards(corners, sizes, world, 7.0)
+        assert sp.radius == 21
+        assert sp.bands[0][0] == 0 and sp.bands[-1][1] == sp.canvas_h
+        assert all(sp.bands[k][1] == sp.bands[k + 1][0] for k in range(world - 1))
+        for rnd in sp.rounds:
+            assert len({sp.owner[j] for j in rnd}) == len(rnd)
+        assert sorted(j for rnd in sp.rounds for j in rnd) == list(range(n))
+        for k in range(world):
+            b0, b1 = sp.bands[k]
+            spans = []
+            for j in range(n):
+                (w, h), cy = sizes[j], corners[j][1] - sp.min_y
+                first, last = max(0, b0 - cy), min(h, b1 - cy)
+                if last <= first:
+                    assert sp.slices[k][j] is None
+                    continue
+                r0, r1 = sp.slices[k][j]
+                assert 0 <= r0 <= max(0, first - 21) and min(h, last + 21) <= r1 <= h
+                if h < 84:
+                    assert (r0, r1) == (0, h)
+                t_off, v_off = sp.offsets[k][j]
+                spans.append((t_off, t_off + sp.tile_step[j] * (r1 - r0)))
+                spans.append((v_off, v_off + sp.valid_step[j] * (r1 - r0)))
+                assert t_off % 256 == 0 and v_off % 256 == 0 and sp.tile_step[j] >= 3 * w and sp.valid_step[j] >= w
+            spans.sort()
+            assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+            assert not spans or spans[-1][1] <= sp.arena_bytes[k]
+        # every tile row is stored somewhere (the bands cover the canvas)
+        for j in range(n):
+            covered = np.zeros(sizes[j][1], bool)
+            for k in range(world):
+                if sp.slices[k][j] is not None:
+                    covered[sp.slices[k][j][0]:sp.slices[k][j][1]] = True
+            assert covered.all()
