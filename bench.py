@@ -310,6 +310,7 @@ def run_ours(args):
         if with_timers:
             ctx.timers_enable(True)
             ctx.timers_reset()
+            ctx.blend_stats(reset=True)
         count = lambda: ctx.launch_count + (ctx_s.launch_count if ctx_s is not None else 0)
         l0 = count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -321,7 +322,7 @@ def run_ours(args):
         ms = e0.elapsed_time(e1) / steps
         stage = None
         if with_timers:
-            stage = ctx.timers_read()
+            stage = ctx.timers_read() + (ctx.blend_stats(reset=True),)
             ctx.timers_enable(False)
         launches = count() - l0
         if world > 1:
@@ -337,8 +338,10 @@ def run_ours(args):
     value = canvas_mpx / (ms * 1e-3)
 
     # roofline of the dominant kernel (the blend) and of the warp kernel, from the live stage timers
-    stage_ms, stage_n = stage
-    my_T = 0   # tile pixels this rank blended / warped
+    stage_ms, stage_n, (px_done, px_offered) = stage
+    px_done /= args.steps        # tile pixels the blend kernels filtered per step (mask_cut sparsity)
+    px_offered /= args.steps
+    my_T = 0   # tile pixels inside this rank's band
     for (tlx, tly), (w, h) in zip(wl["corners"], wl["sizes"]):
         cy = tly - wl["min_y"]
         a, b = max(row0, cy), min(row1, cy + h)
@@ -376,7 +379,7 @@ def run_ours(args):
     ctx.timers_enable(False)
     warp_s = iso_ms["warp"] * 1e-3 / iso_reps
     mask_iso_ms = iso_ms["mask"] / iso_reps
-    blend_flops = 688.0 * cfg.bands * my_T            # 4 ch x B sigmas x 2 passes x 43 MACs per tile pixel
+    blend_flops = 688.0 * cfg.bands * px_done         # 4 ch x B sigmas x 2 passes x 43 MACs per FILTERED tile pixel
     n_blend = max(1, stage_n["blend"] // args.steps)
     n_warp = max(1, len(iso_tiles))   # one warp_kernel (+ one tiny table kernel) per tile
     roofline = {
@@ -385,11 +388,15 @@ def run_ours(args):
         "frac": (blend_flops / blend_s / 1e12 / fp32_peak) if blend_s > 0 else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
         # (profiles/r1g_blend_march6_raw.csv: 471.6 + 307.8 MB for a 22.39 Mpx tile = 34.8 B/px), scaled to this run's mean tile
-        "traffic": 34.8 * my_T / n_blend, "traffic_unit": "bytes per launch (ncu capture, scaled by tile pixels)",
+        "traffic": 34.8 * px_done / n_blend, "traffic_unit": "bytes per launch (ncu capture, scaled by tile pixels)",
         "peak_source": "FFMA microbenchmark run by this bench (MEASURED_PEAKS.json has no fp32 entry)",
         "launches_per_step": n_blend, "avg_launch_ms": blend_s * 1e3 / n_blend,
         "algorithmic_flop_per_tile_px": 688 * cfg.bands,
-        "hbm": {"achieved": (37.0 * my_T) / blend_s / 1e9 if blend_s > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+        "tile_px_filtered_per_step": px_done, "tile_px_in_band_per_step": px_offered,
+        "active_fraction": (px_done / px_offered) if px_offered else None,
+        "sparsity_note": "tile pixels whose whole 43x43 mask_cut window is zero have zero weight in every band and are skipped "
+                         "(bit-identical canvas); achieved counts only the pixels actually filtered",
+        "hbm": {"achieved": (37.0 * px_done) / blend_s / 1e9 if blend_s > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                 "bytes_per_tile_px": 37, "note": "5 B u8 inputs + 32 B float4 accumulator read-modify-write; not the binding roof"},
     }
     roofline_warp = {
@@ -399,6 +406,16 @@ def run_ours(args):
         "peak_source": hbm_src, "launches_per_step": n_warp, "avg_launch_ms": warp_s * 1e3 / n_warp,
         "algorithmic_bytes_per_tile_px": 7,
     }
+
+    # the same step with the mask_cut sparsity switched off (every tile pixel filtered): what the path costs when the
+    # seam masks are dense (e.g. all-soft masks); reported next to the headline, never instead of it
+    dense = None
+    if world == 1:
+        lib.spano_debug_blend_dense(1)
+        ms_d, _, _ = timed(step_dev, 2, 1)
+        lib.spano_debug_blend_dense(0)
+        dense = {"value": canvas_mpx / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d,
+                 "note": "blend sparsity disabled (spano_debug_blend_dense): all tile pixels filtered"}
 
     e2e = None
     if not args.no_e2e:
@@ -417,7 +434,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config_json(wl, args, world), "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu,
+                "clocks": clocks, "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu, "dense_masks": dense,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
                 "stage_note": "in-step warp/mask times overlap the blend (auxiliary stream); isolated: warp %.3f ms, mask %.3f ms per step" % (warp_s * 1e3, mask_iso_ms),
                 "tile_mpx_per_s": wl["T"] / 1e6 / (ms * 1e-3)}

@@ -282,6 +282,11 @@ int spano_blend_finish(spano_ctx *ctx, uint8_t *canvas, size_t canvas_step);
 int spano_timers_enable(spano_ctx *ctx, int on);
 int spano_timers_reset(spano_ctx *ctx);
 int spano_timers_read(spano_ctx *ctx, float ms[4], long long launches[4]);
+/* Sparsity of the blend: tile pixels whose whole (2R+1)^2 window of mask_cut is zero have zero weight in every
+ * band and add exactly 0 to colour and alpha, so the blend kernel skips them (bit-identical canvas).
+ * processed_px = tile pixels the blend kernels actually filtered since the last reset, offered_px = tile pixels
+ * of the launches (w x rows in the band).  Synchronises the context's stream.                              */
+int spano_blend_stats(spano_ctx *ctx, unsigned long long *processed_px, unsigned long long *offered_px, int reset);
 /* FP32 FMA-pipe microbenchmark (the blend kernel's roofline denominator; MEASURED_PEAKS.json
  * carries no fp32 entry): returns achieved TFLOP/s of a register-resident FFMA loop.      */
 int spano_fp32_peak(spano_ctx *ctx, int variant, double *tflops);

@@ -90,6 +90,7 @@ SYMBOLS = {
     "spano_timers_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "spano_timers_reset": (C.c_int, [C.c_void_p]),
     "spano_timers_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
+    "spano_blend_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]),
     "spano_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
 }
 
@@ -112,6 +113,8 @@ def load() -> C.CDLL:
         fn.argtypes = args
     lib.spano_debug_force_generic.restype = None
     lib.spano_debug_force_generic.argtypes = [C.c_int]
+    lib.spano_debug_blend_dense.restype = None
+    lib.spano_debug_blend_dense.argtypes = [C.c_int]
     _lib = lib
     return lib
 

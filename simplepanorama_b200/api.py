@@ -111,6 +111,12 @@ class Context:
         names = ("warp", "mask", "blend", "normalise")
         return {k: float(ms[i]) for i, k in enumerate(names)}, {k: int(n[i]) for i, k in enumerate(names)}
 
+    def blend_stats(self, reset: bool = False):
+        """(processed tile px, offered tile px) of the blend launches since the last reset (mask_cut sparsity)."""
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        self.check(self.lib.spano_blend_stats(self.h, C.byref(a), C.byref(b), int(reset)))
+        return int(a.value), int(b.value)
+
     def fp32_peak(self, variant: int = 0) -> float:
         v = C.c_double()
         self.check(self.lib.spano_fp32_peak(self.h, int(variant), C.byref(v)))

@@ -30,6 +30,10 @@
 #include <cmath>
 #include <cstdio>
 
+// debug / measurement switch: 1 = ignore the mask_cut sparsity (every tile pixel is processed)
+static int g_blend_dense = 0;
+extern "C" void spano_debug_blend_dense(int on) { g_blend_dense = on; }
+
 namespace {
 
 constexpr int MAXB = SPANO_MAX_BANDS;
@@ -398,21 +402,29 @@ int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
     P.w = Q.w;  P.h = Q.h;
     P.ty_begin = Q.ty_begin;  P.ty_end = Q.ty_end;
     P.acc = Q.acc;  P.canvas_w = Q.canvas_w;  P.ax = Q.ax;  P.ay = Q.ay;
-    // segment height: minimise waves x (rows per CTA + the ~21 row-equivalents the prologue costs)
-    const int rows = Q.ty_end - Q.ty_begin, strips = (Q.w + SW - 1) / SW;
-    int best_seg = (rows + 7) / 8 * 8;
-    double best_cost = 1e30;
-    for (int nseg = 1; nseg <= 64; ++nseg) {
-        int seg = ((rows + nseg - 1) / nseg + 7) / 8 * 8;
-        if (seg < 64 && nseg > 1) break;
-        int n = (rows + seg - 1) / seg;
-        double waves = std::ceil((double)strips * n / sms);
-        double cost = waves * (seg + 40.0);
-        if (cost < best_cost) { best_cost = cost; best_seg = seg; }
+    // sparsity plan (activity of mask_cut per strip -> active output rows -> even split over the CTAs)
+    const int strips = (Q.w + SW - 1) / SW;
+    if (strips > 2048 || sms > 1024) return spano_fail(ctx, SPANO_E_LIMIT, "tile wider than %d px", 2048 * SW);
+    const march::PlanView V(strips, sms);
+    int *plan = nullptr;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_BLENDPLAN, march::PlanView::ints(strips, sms) * sizeof(int), (void **)&plan)) return rc;
+    if (!ctx->blend_stats) {
+        SPANO_CUDA(ctx, cudaMalloc((void **)&ctx->blend_stats, 2 * sizeof(unsigned long long)));
+        SPANO_CUDA(ctx, cudaMemsetAsync(ctx->blend_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        ctx->owned.push_back(ctx->blend_stats);
     }
-    P.seg_rows = best_seg;
-    dim3 grid(strips, (rows + best_seg - 1) / best_seg);
-    march::blend_march_kernel<B, SW><<<grid, march::THREADS, C::SMEM, ctx->stream>>>(P);
+    int *ymin = plan + V.ymin(), *ymax = plan + V.ymax();
+    march::plan_init_kernel<<<(strips + 255) / 256, 256, 0, ctx->stream>>>(ymin, ymax, strips);
+    const int dense = g_blend_dense;
+    if (!dense) {
+        const int ra = std::max(0, Q.ty_begin - march::R), rb = std::min(Q.h, Q.ty_end + march::R);
+        dim3 ag((Q.w + 511) / 512, (rb - ra + 63) / 64);
+        march::activity_kernel<SW><<<ag, 256, 0, ctx->stream>>>(Q.cut, Q.cut_step, Q.w, ra, rb, ymin, ymax);
+    }
+    march::plan_kernel<SW><<<1, 256, 0, ctx->stream>>>(plan, strips, sms, Q.ty_begin, Q.ty_end, dense, ctx->blend_stats, Q.w);
+    P.plan = plan;
+    ctx->launches += dense ? 2 : 3;
+    march::blend_march_kernel<B, SW><<<sms, march::THREADS, C::SMEM, ctx->stream>>>(P);
     return 0;
 }
 

@@ -53,11 +53,150 @@ struct Params {
     const uint8_t *valid; size_t valid_step;
     int w, h;               // tile extent
     int ty_begin, ty_end;   // tile rows to produce
-    int seg_rows;           // rows per CTA segment (multiple of STEP)
     float4 *acc;
     int canvas_w;
     int ax, ay;
+    const int *plan;        // device plan of this launch (see Plan below)
 };
+
+// ---- sparsity plan -----------------------------------------------------------------------------------------
+// A tile pixel whose whole (2R+1)^2 window of mask_cut is zero has weight G_s(mask_cut) = 0 for every band, so
+// it adds exactly 0 to colour and alpha: skipping it leaves the canvas bit-identical.  Seam masks partition the
+// canvas (dist_cut / graph_cut assign every pixel to one image), so most of a tile is such pixels.  Per launch:
+//   activity_kernel : per strip of SW columns, the first / last tile row holding a non-zero mask_cut byte
+//   plan_kernel     : per strip the output rows that can be non-zero (neighbour strips and +-R rows included,
+//                     clipped to the band), their prefix sum in units of rows, and an even split of that total
+//                     over the CTAs: CTA i produces the "virtual rows" [i*per, (i+1)*per) of the concatenation,
+//                     i.e. at most a few (strip, row range) pieces -- perfectly balanced, no wave quantisation.
+// Plan layout (ints): [0] total rows (each strip rounded up to 8)  [1] rows per CTA  [2] CTAs in use  [3] pieces
+//   cta_start[max_cta + 1]   first piece of CTA i (pieces of CTA i: cta_start[i] .. cta_start[i+1])
+//   pieces[3 * (S + max_cta)] {strip, y0, y1} tile rows to produce
+//   scratch: a0[S], a1[S], prefix[S + 1], ymin[S], ymax[S]
+struct PlanView {
+    int S, C;
+    __host__ __device__ static size_t ints(int S, int max_cta) { return 4 + (size_t)(max_cta + 1) + 3 * (size_t)(S + max_cta) + 5 * (size_t)S + 1; }
+    __host__ __device__ PlanView(int strips, int max_cta) : S(strips), C(max_cta) {}
+    __host__ __device__ int cta_start() const { return 4; }
+    __host__ __device__ int pieces() const { return 4 + C + 1; }
+    __host__ __device__ int a0() const { return pieces() + 3 * (S + C); }
+    __host__ __device__ int a1() const { return a0() + S; }
+    __host__ __device__ int prefix() const { return a1() + S; }
+    __host__ __device__ int ymin() const { return prefix() + S + 1; }
+    __host__ __device__ int ymax() const { return ymin() + S; }
+};
+
+// first / last row with a non-zero mask_cut byte per strip, over tile rows [ra, rb).  One warp row pass covers
+// 512 columns (16 per lane); a block of 8 warps covers 64 rows.
+template <int SW>
+__global__ void activity_kernel(const uint8_t *cut, size_t cut_step, int w, int ra, int rb, int *ymin, int *ymax)
+{
+    const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * 512 + lane * 16;
+    int lo = 0x7fffffff, hi = -1;
+    if (x0 < w) {
+        const int nx = min(16, w - x0);
+        for (int i = 0; i < 8; ++i) {
+            const int y = ra + blockIdx.y * 64 + i * 8 + wv;
+            if (y >= rb) break;
+            const uint8_t *p = cut + (size_t)y * cut_step + x0;
+            uint32_t any = 0;
+            if (nx == 16 && (((uintptr_t)p) & 15) == 0) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+                any = v.x | v.y | v.z | v.w;
+            } else {
+                for (int k = 0; k < nx; ++k) any |= __ldg(p + k);
+            }
+            if (any) { lo = min(lo, y); hi = max(hi, y); }
+        }
+    }
+    if (SW == 32) {   // two lanes per strip
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, 1));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, 1));
+        if ((lane & 1) == 0 && hi >= 0) { atomicMin(ymin + x0 / 32, lo); atomicMax(ymax + x0 / 32, hi); }
+    } else {
+        if (hi >= 0) { atomicMin(ymin + x0 / 16, lo); atomicMax(ymax + x0 / 16, hi); }
+    }
+}
+
+__global__ void plan_init_kernel(int *ymin, int *ymax, int S)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) { ymin[s] = 0x7fffffff; ymax[s] = -1; }
+}
+
+// one CTA; S <= 2048 strips, max_cta <= 1024
+template <int SW>
+__global__ void plan_kernel(int *plan, int S, int max_cta, int ty_begin, int ty_end, int dense, unsigned long long *stats, int w)
+{
+    constexpr int NB = (R + SW - 1) / SW;   // neighbour strips whose mask_cut reaches into this strip's window
+    const PlanView V(S, max_cta);
+    const int *ymin = plan + V.ymin(), *ymax = plan + V.ymax();
+    __shared__ int s_pref[2049];
+    __shared__ int s_cnt[1025];
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        int lo = 0x7fffffff, hi = -1;
+        for (int t = max(0, s - NB); t <= min(S - 1, s + NB); ++t) { lo = min(lo, ymin[t]); hi = max(hi, ymax[t]); }
+        int a0 = ty_begin, a1 = ty_end;
+        if (!dense) {
+            if (hi < 0) { a0 = a1 = ty_begin; }
+            else { a0 = max(ty_begin, lo - R); a1 = min(ty_end, hi + R + 1); if (a1 < a0) a1 = a0; }
+        }
+        plan[V.a0() + s] = a0;
+        plan[V.a1() + s] = a1;
+        s_pref[s + 1] = (a1 - a0 + STEP - 1) / STEP * STEP;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_pref[0] = 0;
+        for (int s = 0; s < S; ++s) s_pref[s + 1] += s_pref[s];
+        const int total = s_pref[S];
+        // CTAs in use: all of them once every CTA gets at least 64 rows; rows per CTA rounded up to the step
+        int ncta = min(max_cta, max(1, total / 64));
+        int per = ((total + ncta - 1) / ncta + STEP - 1) / STEP * STEP;
+        if (per < STEP) per = STEP;
+        ncta = total ? (total + per - 1) / per : 0;
+        plan[0] = total;  plan[1] = per;  plan[2] = ncta;
+        if (stats) {
+            atomicAdd(stats, (unsigned long long)total * SW);                       // tile pixels processed (incl. rounding)
+            atomicAdd(stats + 1, (unsigned long long)(ty_end - ty_begin) * w);      // tile pixels of the launch
+        }
+    }
+    __syncthreads();
+    const int total = plan[0], per = plan[1], ncta = plan[2];
+    // CTA i produces the virtual rows [i*per, (i+1)*per): pass 0 counts its pieces, pass 1 writes them
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = threadIdx.x; i < ncta; i += blockDim.x) {
+            int v = i * per;
+            const int vend = min(total, v + per);
+            int a = 0, b = S;        // strip with prefix[a] <= v < prefix[a+1]
+            while (b - a > 1) {
+                const int m = (a + b) >> 1;
+                if (s_pref[m] <= v) a = m; else b = m;
+            }
+            int n = 0;
+            int *out = plan + V.pieces() + 3 * (pass ? s_cnt[i] : 0);
+            for (int strip = a; v < vend && strip < S; ++strip) {
+                const int p0 = s_pref[strip], p1 = s_pref[strip + 1];
+                if (p1 <= v) continue;
+                const int sa0 = plan[V.a0() + strip], sa1 = plan[V.a1() + strip];
+                const int y0 = sa0 + (v - p0), y1 = min(sa1, sa0 + (min(vend, p1) - p0));
+                v = min(vend, p1);
+                if (y1 <= y0) continue;
+                if (pass) { out[3 * n] = strip; out[3 * n + 1] = y0; out[3 * n + 2] = y1; }
+                ++n;
+            }
+            if (!pass) s_cnt[i + 1] = n;
+        }
+        __syncthreads();
+        if (!pass && threadIdx.x == 0) {
+            s_cnt[0] = 0;
+            for (int i = 0; i < ncta; ++i) s_cnt[i + 1] += s_cnt[i];
+            plan[3] = s_cnt[ncta];
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i <= max_cta; i += blockDim.x) plan[V.cta_start() + i] = s_cnt[min(i, ncta)];
+}
 
 // u8 global load that lands zero-extended in a 32-bit register: no dependent instruction (mask /
 // convert) is scheduled behind the load, so its latency can be hidden behind the next phase
@@ -206,11 +345,13 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
     int *xtab = reinterpret_cast<int *>(raw + 4 * STEP * C::RAW_PITCH);   // [NC] reflected tile x of staged column c
 
     const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * SW;
-    const int y0 = P.ty_begin + blockIdx.y * P.seg_rows;
-    const int y1 = min(P.ty_end, y0 + P.seg_rows);
-    const int nsteps = (y1 - y0 + STEP - 1) / STEP;
-    const int ybase = y0 - R;   // tile row of relative row 0
+    // This CTA's pieces {strip, y0, y1} of the plan.  The piece loop is folded into the step loop below (one
+    // loop level: a second one makes ptxas give up the uniform-register taps of the vertical pass).
+    const int S = (P.w + SW - 1) / SW;
+    const PlanView V(S, gridDim.x);
+    int pi = __ldg(P.plan + V.cta_start() + blockIdx.x);
+    const int pend = __ldg(P.plan + V.cta_start() + blockIdx.x + 1);
+    int tx0 = 0, y0 = 0, y1 = 0, nsteps = -1, ybase = 0;
 
     // vertical-pass role
     const int vx = tid % SW, vch = (tid / SW) & 3, vg = tid / (4 * SW);
@@ -227,12 +368,6 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
     const uint8_t *sbase = (sch == 0) ? P.cut : P.tile + (sch - 1);
     const size_t sstep = (sch == 0) ? P.cut_step : P.tile_step;
     int xoff[NPASS];
-#pragma unroll
-    for (int ps = 0; ps < NPASS; ++ps) {
-        const int c = lane + 32 * ps;
-        const int x = reflect_idx(tx0 - R + min(c, C::NC - 1), P.w);
-        xoff[ps] = (sch == 0) ? x : 3 * x;
-    }
     (void)xtab;
     auto prefetch = [&](uint32_t (&dst)[NQ * NPASS], int yrow0) {
 #pragma unroll
@@ -254,12 +389,7 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
         }
     };
 
-    // prefetch registers (raw bytes): chunk 0, consumed in step -7
-    uint32_t pre[NQ * NPASS];
-#pragma unroll
-    for (int k = 0; k < NQ * NPASS; ++k) pre[k] = 0u;
-    prefetch(pre, ybase);
-
+    uint32_t pre[NQ * NPASS];                              // prefetch registers (raw bytes)
     int chunk0 = 0;                                        // circular slot of chunk s (== slot chunk s+7 will reuse)
     // registers of the combine of the previous step (loaded one step ahead so their latency is hidden)
     uint32_t vraw = 0, i0 = 0, i1 = 0, i2 = 0;
@@ -267,9 +397,31 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
     float4 *accp = nullptr;
     bool cdo = false;
 
-    // steps -7..-1 only fill the circular buffer (chunks 0..6); step s >= 0 produces tile rows y0+8s..y0+8s+7
+    // steps -7..-1 only fill the circular buffer (chunks 0..6); step s >= 0 produces tile rows y0+8s..y0+8s+7;
+    // step nsteps only runs the combine of the last rows
+    int s = 0;
 #pragma unroll 1
-    for (int s = -NCHUNK; s <= nsteps; ++s) {
+    for (;; ++s) {
+        if (s > nsteps) {                                  // next piece of this CTA
+            if (pi >= pend) break;
+            const int *pc = P.plan + V.pieces() + 3 * pi;
+            ++pi;
+            tx0 = __ldg(pc) * SW;  y0 = __ldg(pc + 1);  y1 = __ldg(pc + 2);
+            nsteps = (y1 - y0 + STEP - 1) / STEP;
+            ybase = y0 - R;                                // tile row of relative row 0
+#pragma unroll
+            for (int ps = 0; ps < NPASS; ++ps) {
+                const int c = lane + 32 * ps;
+                const int x = reflect_idx(tx0 - R + min(c, C::NC - 1), P.w);
+                xoff[ps] = (sch == 0) ? x : 3 * x;
+            }
+#pragma unroll
+            for (int k = 0; k < NQ * NPASS; ++k) pre[k] = 0u;
+            prefetch(pre, ybase);                          // chunk 0, consumed in step -7
+            chunk0 = 0;
+            cdo = false;
+            s = -NCHUNK;
+        }
         __syncthreads();                                   // A: chunks s..s+6 filtered, G(s-1) published, raw free
         const bool more_rows = s + 1 < nsteps;             // chunk s+7 is needed by step s+1
         if (more_rows) {

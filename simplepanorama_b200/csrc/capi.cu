@@ -253,6 +253,21 @@ extern "C" int spano_timers_enable(spano_ctx *ctx, int on)
     return SPANO_OK;
 }
 
+extern "C" int spano_blend_stats(spano_ctx *ctx, unsigned long long *processed_px, unsigned long long *offered_px, int reset)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    unsigned long long v[2] = {0, 0};
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->blend_stats) {
+        SPANO_CUDA(ctx, cudaMemcpy(v, ctx->blend_stats, sizeof(v), cudaMemcpyDeviceToHost));
+        if (reset) SPANO_CUDA(ctx, cudaMemset(ctx->blend_stats, 0, sizeof(v)));
+    }
+    if (processed_px) *processed_px = v[0];
+    if (offered_px) *offered_px = v[1];
+    return SPANO_OK;
+}
+
 extern "C" int spano_timers_reset(spano_ctx *ctx)
 {
     if (!ctx) return SPANO_E_INVALID;
