@@ -180,6 +180,27 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(torch, index: int):
+    """One process per GPU: run (and first-touch the pinned staging buffers) on the CPU cores of the NUMA node the
+    GPU hangs off, so that N ranks uploading at once do not all pull from one socket's memory.  Best effort."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------
@@ -195,6 +216,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: simplepanorama_b200 has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         tdist.init_process_group("nccl", device_id=dev)
 
@@ -260,7 +282,8 @@ def run_ours(args):
         descs = descs_host if host else descs_dev
         have = row1 > row0
         if have:   # (host variant: queues the small mask uploads ahead of the large source uploads below)
-            sdist.blend_begin(ctx, sp, rank, cfg.bands, cfg.sigma, host_descs=descs_host if host else None)
+            sdist.blend_begin(ctx, sp, rank, cfg.bands, cfg.sigma, host_descs=descs_host if host else None,
+                              host_canvas=(h_canvas.data_ptr(), h_canvas.stride(0)))
         tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)   # every rank has finished blending the previous step's arenas
         aux.wait_stream(stream)
         evs = []
@@ -276,7 +299,7 @@ def run_ours(args):
             tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)   # round t is in every arena
             if have:
                 for j in rnd:
-                    sdist.blend_add(ctx, sp, rank, j, descs[j], arenas.own, host=host)
+                    sdist.blend_add(ctx, sp, rank, j, descs, arenas.own, host=host)
         if have:
             if host:
                 sdist.blend_finish(ctx, h_canvas.data_ptr(), h_canvas.stride(0), host=True)
@@ -434,7 +457,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config_json(wl, args, world), "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu, "dense_masks": dense,
+                "clocks": clocks, "numa_node": numa, "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu, "dense_masks": dense,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
                 "stage_note": "in-step warp/mask times overlap the blend (auxiliary stream); isolated: warp %.3f ms, mask %.3f ms per step" % (warp_s * 1e3, mask_iso_ms),
                 "tile_mpx_per_s": wl["T"] / 1e6 / (ms * 1e-3)}

@@ -266,10 +266,13 @@ int spano_warp_scatter(spano_ctx *ctx, int proj, float scale, const spano_image_
  * spano_blend_begin additionally takes the n images that will be added and uploads their preview-scale
  * mask_cut right away, so that these small copies are queued on the copy engine AHEAD of the owners' large
  * source uploads instead of behind them (spano_blend_add finds them by their mask_cut pointer; an image that
- * was not announced, or a tile-sized mask, is uploaded on demand).                                          */
+ * was not announced, or a tile-sized mask, is uploaded on demand).  `canvas` (HOST, may be NULL) announces the
+ * destination of spano_blend_finish: when it is given and the images are then added in array order, canvas
+ * columns that no later image touches are normalised and downloaded while the remaining images are still being
+ * blended (spano_blend_finish must then be called with the same canvas).                                    */
 int spano_dev_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma);
 int spano_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma,
-                      int n, const spano_image_desc *images);
+                      int n, const spano_image_desc *images, uint8_t *canvas, size_t canvas_step);
 int spano_dev_blend_add(spano_ctx *ctx, const spano_image_desc *im, const spano_slice *slice);
 int spano_dev_blend_finish(spano_ctx *ctx, uint8_t *canvas, size_t canvas_step);
 int spano_blend_add(spano_ctx *ctx, const spano_image_desc *im, const spano_slice *slice);

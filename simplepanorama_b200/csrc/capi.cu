@@ -1049,6 +1049,29 @@ int warp_scatter_impl(spano_ctx *ctx, int proj, float scale, const spano_image_d
     return SPANO_OK;
 }
 
+// host variant: normalise + download the canvas column runs whose last image is `idx` (idx < 0: everything left)
+int blend_flush_runs(spano_ctx *ctx, int idx)
+{
+    spano_ctx::BlendSession &S = ctx->bs;
+    const int rows = S.row1 - S.row0;
+    for (auto &r : S.runs) {
+        if (r.flushed || (idx >= 0 && r.idx != idx)) continue;
+        r.flushed = true;
+        StageTimer t3(ctx, 3);
+        int kn = launch_normalise(ctx, S.acc, S.cw, rows, S.bands, SPANO_OUT_U8, S.d_canvas, S.d_step, r.c0, r.c1);
+        if (kn < 0) return kn;
+        t3.stop(kn);
+        cudaEvent_t e;
+        SPANO_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        S.events.push_back(e);
+        SPANO_CUDA(ctx, cudaEventRecord(e, ctx->stream));
+        SPANO_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, e, 0));
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(S.h_canvas + (size_t)r.c0 * 3, S.h_step, S.d_canvas + (size_t)r.c0 * 3, S.d_step, (size_t)(r.c1 - r.c0) * 3,
+                                          rows, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
+    return SPANO_OK;
+}
+
 int blend_add_impl(spano_ctx *ctx, const spano_image_desc *im, const spano_slice *slice, bool host)
 {
     spano_ctx::BlendSession &S = ctx->bs;
@@ -1109,6 +1132,8 @@ int blend_add_impl(spano_ctx *ctx, const spano_image_desc *im, const spano_slice
     int k = launch_blend_tile(ctx, bt, S.bands, S.radius, S.acc, S.cw, S.row0, S.row1);
     if (k < 0) return k;
     t2.stop(k);
+    if (host && S.h_canvas && im >= S.images && im < S.images + S.n_images)
+        return blend_flush_runs(ctx, (int)(im - S.images));
     return SPANO_OK;
 }
 
@@ -1118,6 +1143,17 @@ int blend_finish_impl(spano_ctx *ctx, uint8_t *canvas, size_t canvas_step, bool 
     if (!S.open) return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_finish without spano_dev_blend_begin");
     if (!canvas || canvas_step < (size_t)S.cw * 3) return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_finish: null canvas or step too small");
     const int rows = S.row1 - S.row0;
+    if (host && S.h_canvas) {
+        // the canvas was announced at begin: most columns are already on their way; flush the rest and wait
+        if (canvas != S.h_canvas || canvas_step != S.h_step) return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_finish: not the canvas announced at spano_blend_begin");
+        if (int rc = blend_flush_runs(ctx, -1)) return rc;
+        S.open = false;
+        SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
+        for (cudaEvent_t e : S.events) cudaEventDestroy(e);
+        S.events.clear();
+        return SPANO_OK;
+    }
     uint8_t *d_canvas = canvas;
     size_t d_step = canvas_step;
     if (host) {
@@ -1164,7 +1200,7 @@ extern "C" int spano_dev_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, in
 }
 
 extern "C" int spano_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma,
-                                 int n, const spano_image_desc *images)
+                                 int n, const spano_image_desc *images, uint8_t *canvas, size_t canvas_step)
 {
     if (!ctx) return SPANO_E_INVALID;
     Guard g(ctx);
@@ -1195,6 +1231,29 @@ extern "C" int spano_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int mi
             S.staged.push_back({im.mask_cut, arena + off[j], st});
         }
     }
+    if (canvas && n > 0) {
+        if (canvas_step < (size_t)S.cw * 3) { S.open = false; return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_begin: canvas_step too small"); }
+        const int rows = S.row1 - S.row0;
+        S.d_step = align_up((size_t)S.cw * 3, 16);
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_CANVAS, S.d_step * rows, (void **)&S.d_canvas)) { S.open = false; return rc; }
+        if (!ctx->d2h_stream) SPANO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        S.images = images;  S.n_images = n;  S.h_canvas = canvas;  S.h_step = canvas_step;
+        // for every canvas column the last announced image (in array order) whose tile covers it inside this band;
+        // columns nobody covers are flushed at finish
+        std::vector<int> last(S.cw, -1);
+        for (int j = 0; j < n; ++j) {
+            const int cy = images[j].tl_y - S.my;
+            if (std::min(images[j].h, S.row1 - cy) <= std::max(0, S.row0 - cy)) continue;
+            const int c0 = std::max(0, images[j].tl_x - S.mx), c1 = std::min(S.cw, images[j].tl_x - S.mx + images[j].w);
+            for (int c = c0; c < c1; ++c) last[c] = j;
+        }
+        for (int c = 0; c < S.cw;) {
+            int e = c + 1;
+            while (e < S.cw && last[e] == last[c]) ++e;
+            S.runs.push_back({c, e, last[c], false});
+            c = e;
+        }
+    }
     return SPANO_OK;
 }
 
@@ -1211,6 +1270,8 @@ int blend_begin_impl(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row
     if (int rc = launch_blend_clear(ctx, S.acc, canvas_w, row1 - row0)) return rc;
     t.stop(0);
     S.staged.clear();
+    S.runs.clear();
+    S.images = nullptr;  S.n_images = 0;  S.h_canvas = nullptr;  S.d_canvas = nullptr;
     S.open = true;
     return SPANO_OK;
 }

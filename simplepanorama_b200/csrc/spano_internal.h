@@ -58,6 +58,17 @@ struct spano_ctx {
         // host variant: preview-scale masks uploaded at begin (host pointer -> device copy, step)
         struct Staged { const uint8_t *host; const uint8_t *dev; size_t step; };
         std::vector<Staged> staged;
+        // host variant with the canvas announced at begin: canvas columns that no later image touches are
+        // normalised and downloaded on the download stream while the remaining images are still blended
+        struct ColRun { int c0, c1, idx; bool flushed; };
+        std::vector<ColRun> runs;
+        const spano_image_desc *images = nullptr;
+        int n_images = 0;
+        uint8_t *h_canvas = nullptr;
+        size_t h_step = 0;
+        uint8_t *d_canvas = nullptr;
+        size_t d_step = 0;
+        std::vector<cudaEvent_t> events;
     } bs;
     // timers
     bool timers_on = false;

@@ -44,30 +44,54 @@ struct WarpParams {
     float inv_gain;
     int apply_gain;
     int src_aligned8; // src pointer and step are multiples of 4: aligned 32-bit window loads allowed
-    const float *colA, *colB, *rowA, *rowB;
+    const float *col, *row;   // tables (see warp_tables_kernel)
+    int wp;                   // column-array pitch
     SpanoScatter sc; // n > 0: the tile rows go to these (possibly peer-GPU) slices instead of `dst`
 };
 
-// per-column / per-row trigonometry tables
+// Per-column / per-row tables.  The projector's trigonometry is separable (u depends on the column, v on the
+// row), and so are most of the products of  (x,y,z) = k_rinv * (x_,y_,z_)  when they are rounded one by one as
+// OpenCV's scalar code does (no contraction):
+//   cylindrical: x_ = sin u, y_ = v, z_ = cos u      ->  x = (m0 x_ + m1 y_) + m2 z_  with every product a pure
+//                column or row quantity: 6 column arrays (m0 sin u, m2 cos u, m3.., m5.., m6.., m8..) and 3 row
+//                arrays (m1 v, m4 v, m7 v); 6 FADD per pixel.
+//   spherical:   x_ = sin(pi-v) sin u, y_ = cos(pi-v), z_ = sin(pi-v) cos u: column arrays sin u, cos u; row arrays
+//                sin(pi-v), m1 y_, m4 y_, m7 y_.
+// Layout: NCOL column arrays of pitch wp = align4(w) floats (float4 loads of a thread's 4 columns), then NROW row
+// arrays of pitch h.
+template <int KIND> struct TableShape { };
+template <> struct TableShape<SPANO_CYLINDRICAL> { static constexpr int NCOL = 6, NROW = 3; };
+template <> struct TableShape<SPANO_SPHERICAL> { static constexpr int NCOL = 2, NROW = 4; };
+template <> struct TableShape<SPANO_STEREOGRAPHIC> { static constexpr int NCOL = 0, NROW = 0; };
+
+struct Mat9 { float m[9]; };
+
 template <int KIND>
-__global__ void warp_tables_kernel(float scale, int tl_x, int tl_y, int w, int h, float *colA, float *colB,
-                                   float *rowA, float *rowB)
+__global__ void warp_tables_kernel(float scale, int tl_x, int tl_y, int w, int h, int wp, Mat9 M, float *col, float *row)
 {
+    const float *m = M.m;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < w) {
-        float u = __fdiv_rn((float)(i + tl_x), scale);
-        colA[i] = sinf(u);
-        colB[i] = cosf(u);
+        const float u = __fdiv_rn((float)(i + tl_x), scale);
+        const float su = sinf(u), cu = cosf(u);
+        if (KIND == SPANO_CYLINDRICAL) {
+            col[i] = __fmul_rn(m[0], su);           col[wp + i] = __fmul_rn(m[2], cu);
+            col[2 * wp + i] = __fmul_rn(m[3], su);  col[3 * wp + i] = __fmul_rn(m[5], cu);
+            col[4 * wp + i] = __fmul_rn(m[6], su);  col[5 * wp + i] = __fmul_rn(m[8], cu);
+        } else {
+            col[i] = su;
+            col[wp + i] = cu;
+        }
     }
     if (i < h) {
-        float v = __fdiv_rn((float)(i + tl_y), scale);
-        if (KIND == SPANO_SPHERICAL) {
-            float t = __fsub_rn(kPiF, v);
-            rowA[i] = sinf(t);
-            rowB[i] = cosf(t);
+        const float v = __fdiv_rn((float)(i + tl_y), scale);
+        if (KIND == SPANO_CYLINDRICAL) {
+            row[i] = __fmul_rn(m[1], v);  row[h + i] = __fmul_rn(m[4], v);  row[2 * h + i] = __fmul_rn(m[7], v);
         } else {
-            rowA[i] = v;
-            rowB[i] = 0.f;
+            const float t = __fsub_rn(kPiF, v);
+            const float y_ = cosf(t);
+            row[i] = sinf(t);
+            row[h + i] = __fmul_rn(m[1], y_);  row[2 * h + i] = __fmul_rn(m[4], y_);  row[3 * h + i] = __fmul_rn(m[7], y_);
         }
     }
 }
@@ -154,11 +178,14 @@ __device__ __forceinline__ uint32_t sample_bilinear(const WarpParams &P, float x
     return B | (G << 8) | (R << 16);
 }
 
+// gray = (3735 B + 19235 G + 9798 R + 2^14) >> 15 (cv::cvtColor BGR2GRAY, 8 bit); dark = gray <= 1, i.e.
+// 3735 B + 19235 G + 9798 R < 3 * 2^14.  The 16-bit weights are split into bytes so two dp4a do the sum.
 __device__ __forceinline__ uint32_t is_dark(uint32_t bgr)
 {
-    const uint32_t B = bgr & 255u, G = (bgr >> 8) & 255u, R = (bgr >> 16) & 255u;
-    const uint32_t gray = (3735u * B + 19235u * G + 9798u * R + (1u << 14)) >> 15;
-    return gray <= 1u ? 1u : 0u;
+    constexpr uint32_t WLO = (3735u & 255u) | ((19235u & 255u) << 8) | ((9798u & 255u) << 16);
+    constexpr uint32_t WHI = (3735u >> 8) | ((19235u >> 8) << 8) | ((9798u >> 8) << 16);
+    const uint32_t sum = __dp4a(bgr, WLO, 0u) + (__dp4a(bgr, WHI, 0u) << 8);
+    return sum < 49152u ? 1u : 0u;
 }
 
 __device__ __forceinline__ uint32_t gain_u8(uint32_t v, float a)
@@ -172,20 +199,25 @@ __device__ __forceinline__ uint32_t gain_bgr(uint32_t bgr, float a)
     return gain_u8(bgr & 255u, a) | (gain_u8((bgr >> 8) & 255u, a) << 8) | (gain_u8((bgr >> 16) & 255u, a) << 16);
 }
 
-// mapBackward, OpenCV expression order, no contraction.
+// mapBackward, OpenCV expression order, no contraction.  One pixel (stereographic, buildMaps) ...
 template <int KIND>
-__device__ __forceinline__ void map_backward(const WarpParams &P, int u_i, int v_i, float &x, float &y)
+__device__ __forceinline__ void project_ray(const WarpParams &P, int u_i, int v_i, float &X, float &Y, float &Z)
 {
-    float x_, y_, z_;
+    const float *m = P.m;
+    if (KIND == SPANO_CYLINDRICAL) {
+        const float *c = P.col + u_i, *r = P.row + v_i;
+        X = __fadd_rn(__fadd_rn(__ldg(c), __ldg(r)), __ldg(c + P.wp));
+        Y = __fadd_rn(__fadd_rn(__ldg(c + 2 * P.wp), __ldg(r + P.dst_h)), __ldg(c + 3 * P.wp));
+        Z = __fadd_rn(__fadd_rn(__ldg(c + 4 * P.wp), __ldg(r + 2 * P.dst_h)), __ldg(c + 5 * P.wp));
+        return;
+    }
+    float x_, z_, my1, my4, my7;
     if (KIND == SPANO_SPHERICAL) {
-        const float sinv = __ldg(P.rowA + v_i), cosv = __ldg(P.rowB + v_i);
-        x_ = __fmul_rn(sinv, __ldg(P.colA + u_i));
-        y_ = cosv;
-        z_ = __fmul_rn(sinv, __ldg(P.colB + u_i));
-    } else if (KIND == SPANO_CYLINDRICAL) {
-        x_ = __ldg(P.colA + u_i);
-        y_ = __ldg(P.rowA + v_i);
-        z_ = __ldg(P.colB + u_i);
+        const float *r = P.row + v_i;
+        const float sinv = __ldg(r);
+        x_ = __fmul_rn(sinv, __ldg(P.col + u_i));
+        z_ = __fmul_rn(sinv, __ldg(P.col + P.wp + u_i));
+        my1 = __ldg(r + P.dst_h);  my4 = __ldg(r + 2 * P.dst_h);  my7 = __ldg(r + 3 * P.dst_h);
     } else {
         const float u = __fdiv_rn((float)(u_i + P.tl_x), P.scale);
         const float v = __fdiv_rn((float)(v_i + P.tl_y), P.scale);
@@ -195,19 +227,74 @@ __device__ __forceinline__ void map_backward(const WarpParams &P, int u_i, int v
         const float t = __fsub_rn(kPiF, pol);
         const float sinv = sinf(t);
         x_ = __fmul_rn(sinv, sinf(az));
-        y_ = cosf(t);
+        const float y_ = cosf(t);
         z_ = __fmul_rn(sinv, cosf(az));
+        my1 = __fmul_rn(m[1], y_);  my4 = __fmul_rn(m[4], y_);  my7 = __fmul_rn(m[7], y_);
     }
-    const float *m = P.m;
-    x = __fadd_rn(__fadd_rn(__fmul_rn(m[0], x_), __fmul_rn(m[1], y_)), __fmul_rn(m[2], z_));
-    y = __fadd_rn(__fadd_rn(__fmul_rn(m[3], x_), __fmul_rn(m[4], y_)), __fmul_rn(m[5], z_));
-    const float z = __fadd_rn(__fadd_rn(__fmul_rn(m[6], x_), __fmul_rn(m[7], y_)), __fmul_rn(m[8], z_));
-    if (z > 0.f) {
-        x = __fdiv_rn(x, z);
-        y = __fdiv_rn(y, z);
+    X = __fadd_rn(__fadd_rn(__fmul_rn(m[0], x_), my1), __fmul_rn(m[2], z_));
+    Y = __fadd_rn(__fadd_rn(__fmul_rn(m[3], x_), my4), __fmul_rn(m[5], z_));
+    Z = __fadd_rn(__fadd_rn(__fmul_rn(m[6], x_), my7), __fmul_rn(m[8], z_));
+}
+
+__device__ __forceinline__ void perspective(float X, float Y, float Z, float &x, float &y)
+{
+    if (Z > 0.f) {
+        x = __fdiv_rn(X, Z);
+        y = __fdiv_rn(Y, Z);
     } else {
         x = y = -1.f;
     }
+}
+
+template <int KIND>
+__device__ __forceinline__ void map_backward(const WarpParams &P, int u_i, int v_i, float &x, float &y)
+{
+    float X, Y, Z;
+    project_ray<KIND>(P, u_i, v_i, X, Y, Z);
+    perspective(X, Y, Z, x, y);
+}
+
+// ... and the 4 consecutive pixels of one warp-kernel thread (x0 is a multiple of 4: float4 table loads; the
+// column arrays are padded to a multiple of 4, pixels beyond dst_w are computed on padding and dropped)
+template <int KIND>
+__device__ __forceinline__ void map_backward4(const WarpParams &P, int x0, int v_i, float (&x)[4], float (&y)[4])
+{
+    if (KIND == SPANO_STEREOGRAPHIC) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) map_backward<KIND>(P, x0 + i, v_i, x[i], y[i]);
+        return;
+    }
+    const float *m = P.m;
+    const float *r = P.row + v_i;
+    float X[4], Y[4], Z[4];
+    if (KIND == SPANO_CYLINDRICAL) {
+        const float4 *c = reinterpret_cast<const float4 *>(P.col + x0);
+        const int q = P.wp >> 2;
+        const float4 a0 = __ldg(c), a2 = __ldg(c + q), a3 = __ldg(c + 2 * q), a5 = __ldg(c + 3 * q), a6 = __ldg(c + 4 * q), a8 = __ldg(c + 5 * q);
+        const float r1 = __ldg(r), r4 = __ldg(r + P.dst_h), r7 = __ldg(r + 2 * P.dst_h);
+        const float A0[4] = {a0.x, a0.y, a0.z, a0.w}, A2[4] = {a2.x, a2.y, a2.z, a2.w}, A3[4] = {a3.x, a3.y, a3.z, a3.w};
+        const float A5[4] = {a5.x, a5.y, a5.z, a5.w}, A6[4] = {a6.x, a6.y, a6.z, a6.w}, A8[4] = {a8.x, a8.y, a8.z, a8.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            X[i] = __fadd_rn(__fadd_rn(A0[i], r1), A2[i]);
+            Y[i] = __fadd_rn(__fadd_rn(A3[i], r4), A5[i]);
+            Z[i] = __fadd_rn(__fadd_rn(A6[i], r7), A8[i]);
+        }
+    } else {
+        const float4 su = __ldg(reinterpret_cast<const float4 *>(P.col + x0));
+        const float4 cu = __ldg(reinterpret_cast<const float4 *>(P.col + P.wp + x0));
+        const float sinv = __ldg(r), my1 = __ldg(r + P.dst_h), my4 = __ldg(r + 2 * P.dst_h), my7 = __ldg(r + 3 * P.dst_h);
+        const float SU[4] = {su.x, su.y, su.z, su.w}, CU[4] = {cu.x, cu.y, cu.z, cu.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float x_ = __fmul_rn(sinv, SU[i]), z_ = __fmul_rn(sinv, CU[i]);
+            X[i] = __fadd_rn(__fadd_rn(__fmul_rn(m[0], x_), my1), __fmul_rn(m[2], z_));
+            Y[i] = __fadd_rn(__fadd_rn(__fmul_rn(m[3], x_), my4), __fmul_rn(m[5], z_));
+            Z[i] = __fadd_rn(__fadd_rn(__fmul_rn(m[6], x_), my7), __fmul_rn(m[8], z_));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) perspective(X[i], Y[i], Z[i], x[i], y[i]);
 }
 
 constexpr int WARP_PX_PER_THREAD = 4;
@@ -229,14 +316,14 @@ __global__ void __launch_bounds__(WARP_BLOCK_X *WARP_BLOCK_Y) warp_kernel(const 
 
     uint32_t px[WARP_PX_PER_THREAD];
     uint32_t dark = 0;
+    float mx[WARP_PX_PER_THREAD], my[WARP_PX_PER_THREAD];
+    map_backward4<KIND>(P, x0, v, mx, my);
 #pragma unroll
     for (int i = 0; i < WARP_PX_PER_THREAD; ++i) {
         const int u = x0 + i;
         uint32_t s = 0, d = 1;
         if (u < P.dst_w) {
-            float x, y;
-            map_backward<KIND>(P, u, v, x, y);
-            s = sample_bilinear(P, x, y);
+            s = sample_bilinear(P, mx[i], my[i]);
             d = is_dark(s);
             s = (uint32_t)s_gain[s & 255u] | ((uint32_t)s_gain[(s >> 8) & 255u] << 8) | ((uint32_t)s_gain[(s >> 16) & 255u] << 16);
         }
@@ -342,7 +429,8 @@ int launch_warp(spano_ctx *ctx, const SpanoProjector &proj, const uint8_t *src, 
     if (row_end <= row_begin) return 0;
     int launches = 0;
     float *tables = nullptr;
-    const size_t tab_floats = 2 * (size_t)dst_w + 2 * (size_t)dst_h;
+    const int wp = (dst_w + 3) & ~3;
+    const size_t tab_floats = 6 * (size_t)wp + 4 * (size_t)dst_h;
     int rc = spano_reserve(ctx, spano_ctx::BUF_TABLES, tab_floats * sizeof(float), (void **)&tables);
     if (rc) return rc;
     WarpParams P;
@@ -357,23 +445,20 @@ int launch_warp(spano_ctx *ctx, const SpanoProjector &proj, const uint8_t *src, 
     P.inv_gain = (float)(1.0 / gain);
     P.apply_gain = (gain != 1.0);
     P.src_aligned8 = ((((uintptr_t)src) | src_step) & 3) == 0;
-    P.colA = tables;
-    P.colB = tables + dst_w;
-    P.rowA = tables + 2 * (size_t)dst_w;
-    P.rowB = tables + 2 * (size_t)dst_w + dst_h;
+    P.col = tables;
+    P.row = tables + 6 * (size_t)wp;
+    P.wp = wp;
     if (scatter) P.sc = *scatter;
 
     if (proj.kind != SPANO_STEREOGRAPHIC) {
         const int n = dst_w > dst_h ? dst_w : dst_h;
         const int tb = 256;
+        Mat9 M;
+        for (int i = 0; i < 9; ++i) M.m[i] = proj.k_rinv[i];
         if (proj.kind == SPANO_SPHERICAL)
-            warp_tables_kernel<SPANO_SPHERICAL><<<(n + tb - 1) / tb, tb, 0, ctx->stream>>>(
-                proj.scale, tl_x, tl_y, dst_w, dst_h, tables, tables + dst_w, tables + 2 * (size_t)dst_w,
-                tables + 2 * (size_t)dst_w + dst_h);
+            warp_tables_kernel<SPANO_SPHERICAL><<<(n + tb - 1) / tb, tb, 0, ctx->stream>>>(proj.scale, tl_x, tl_y, dst_w, dst_h, wp, M, tables, tables + 6 * (size_t)wp);
         else
-            warp_tables_kernel<SPANO_CYLINDRICAL><<<(n + tb - 1) / tb, tb, 0, ctx->stream>>>(
-                proj.scale, tl_x, tl_y, dst_w, dst_h, tables, tables + dst_w, tables + 2 * (size_t)dst_w,
-                tables + 2 * (size_t)dst_w + dst_h);
+            warp_tables_kernel<SPANO_CYLINDRICAL><<<(n + tb - 1) / tb, tb, 0, ctx->stream>>>(proj.scale, tl_x, tl_y, dst_w, dst_h, wp, M, tables, tables + 6 * (size_t)wp);
         ++launches;
     }
     if (xmap) { // maps only

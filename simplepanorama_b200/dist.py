@@ -187,23 +187,28 @@ def scatter_tile(ctx, plan: ShardPlan, j: int, desc, arena_ptrs, kind: int, foca
     ctx.check(fn(ctx.h, int(kind), C.c_float(focal), C.byref(desc), n, sl))
 
 
-def blend_add(ctx, plan: ShardPlan, k: int, j: int, desc, arena_ptr: int, host: bool = False):
-    """Band side of one image (no-op when tile j does not touch band k)."""
+def blend_add(ctx, plan: ShardPlan, k: int, j: int, descs, arena_ptr: int, host: bool = False):
+    """Band side of image j of the spano_image_desc array `descs` (no-op when tile j does not touch band k)."""
     import ctypes as C
+    from ._lib import ImageDesc
     s = band_slice(plan, k, j, arena_ptr)
     if s is None:
         return
     fn = ctx.lib.spano_blend_add if host else ctx.lib.spano_dev_blend_add
-    ctx.check(fn(ctx.h, C.byref(desc), C.byref(s)))
+    # element j by address, so that the library can recognise it as one of the images announced at begin
+    pj = C.cast(C.addressof(descs) + j * C.sizeof(ImageDesc), C.POINTER(ImageDesc))
+    ctx.check(fn(ctx.h, pj, C.byref(s)))
 
 
-def blend_begin(ctx, plan: ShardPlan, k: int, bands: int, sigma: float, host_descs=None):
+def blend_begin(ctx, plan: ShardPlan, k: int, bands: int, sigma: float, host_descs=None, host_canvas=(0, 0)):
     """host_descs: the spano_image_desc array with HOST mask_cut pointers (host-buffer variant: the preview-scale
-    masks are uploaded right away, ahead of the owners' source uploads)."""
+    masks are uploaded right away, ahead of the owners' source uploads).  host_canvas = (pointer, step) announces
+    the destination of blend_finish so that finished canvas columns are downloaded while blending continues."""
+    import ctypes as C
     r0, r1 = plan.bands[k]
     if host_descs is not None:
         ctx.check(ctx.lib.spano_blend_begin(ctx.h, plan.canvas_w, plan.min_x, plan.min_y, r0, r1, int(bands), float(sigma),
-                                            len(host_descs), host_descs))
+                                            len(host_descs), host_descs, C.c_void_p(host_canvas[0] or None), host_canvas[1]))
     else:
         ctx.check(ctx.lib.spano_dev_blend_begin(ctx.h, plan.canvas_w, plan.min_x, plan.min_y, r0, r1, int(bands), float(sigma)))
 

@@ -44,12 +44,15 @@ def _run_sharded(ctx, cfg, gains, images, plan, cuts, world, host):
         r0, r1 = sp.bands[k]
         if r1 <= r0:
             continue
-        # host variant: announce the images for even bands only, so both the staged and the on-demand mask paths run
-        dist.blend_begin(ctx, sp, k, cfg.bands, cfg.sigma, host_descs=descs if (host and k % 2 == 0) else None)
+        # host variant: announce the images (and the canvas, for the early column download) for even bands only, so
+        # both the staged / early-flush and the on-demand paths run
+        out = torch.zeros((r1 - r0, sp.canvas_w, 3), dtype=torch.uint8).pin_memory() if host else None
+        announce = host and k % 2 == 0
+        dist.blend_begin(ctx, sp, k, cfg.bands, cfg.sigma, host_descs=descs if announce else None,
+                         host_canvas=(out.data_ptr(), out.stride(0)) if announce else (0, 0))
         for j in range(cfg.n):
-            dist.blend_add(ctx, sp, k, j, descs[j], ptrs[k], host=host)
+            dist.blend_add(ctx, sp, k, j, descs, ptrs[k], host=host)
         if host:
-            out = torch.empty((r1 - r0, sp.canvas_w, 3), dtype=torch.uint8).pin_memory()
             dist.blend_finish(ctx, out.data_ptr(), out.stride(0), host=True)
             parts.append(out.numpy().copy())
         else:
