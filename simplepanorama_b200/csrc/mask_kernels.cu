@@ -99,26 +99,32 @@ __global__ void ccl_merge_kernel(const uint8_t *dark, size_t dark_step, int w, i
     const uint32_t id0 = (uint32_t)((size_t)y * w + x0) + 1u;
     // bit i+1 of the extended words = pixel i; bit 0 = the pixel left of the group
     const uint32_t left_px = (x0 > 0 && row[x0 - 1]) ? 1u : 0u;
-    const uint32_t ext = (bits << 1) | left_px;
     uint32_t up_ext = 0;
     if (y > 0) {
         const uint8_t *up = row - dark_step;
         up_ext = (load_group(up, x0, w) << 1) | ((x0 > 0 && up[x0 - 1]) ? 1u : 0u);
     }
     const bool border_row = (y == 0 || y == h - 1);
+    const uint32_t up = up_ext >> 1;                       // bit i = the pixel above pixel i is dark
+    // one iteration per RUN of dark pixels (ccl_init linked every pixel of a run to the run's first pixel)
     for (uint32_t m = bits; m;) {
-        const uint32_t i = __ffs(m) - 1;
-        m &= m - 1;
+        const uint32_t i = __ffs(m) - 1;                   // first pixel of the run
+        const uint32_t len = __ffs(~(m >> i)) - 1;         // m < 2^16, so a zero bit always follows
+        const uint32_t runmask = ((1u << len) - 1u) << i;
+        m &= ~runmask;
         const uint32_t id = id0 + i;
-        const int x = x0 + (int)i;
-        if (border_row || x == 0 || x == w - 1) unite(L, id, 0u);
-        const bool left = (ext >> i) & 1u;                 // pixel x-1 dark
-        if (left && i == 0) unite(L, id, id - 1u);         // runs are pre-linked only inside a group
-        if ((up_ext >> (i + 1)) & 1u) {                    // pixel above dark
-            // chained: my left neighbour is dark, in my group, and the pixel above it is dark too --
-            // then it links (or chains) to the row above and both rows' runs are already connected
-            const bool chained = left && i != 0 && ((up_ext >> i) & 1u);
-            if (!chained) unite(L, id, id - (uint32_t)w);
+        const int xa = x0 + (int)i, xb = xa + (int)len - 1;
+        if (border_row || xa == 0 || xb == w - 1) unite(L, id, 0u);
+        if (i == 0 && left_px) unite(L, id, id - 1u);      // runs are pre-linked only inside a group
+        // every maximal segment of dark pixels above the run is (part of) one run of the row above; a segment that
+        // starts at the group's first pixel with a dark pixel above-left belongs to the upper run the left
+        // neighbour group already sees -- and if this run also continues to the left, that link is made there
+        for (uint32_t um = up & runmask; um;) {
+            const uint32_t j = __ffs(um) - 1;
+            const uint32_t ulen = __ffs(~(um >> j)) - 1;
+            um &= ~(((1u << ulen) - 1u) << j);
+            const bool chained = (j == 0) && left_px && (up_ext & 1u);
+            if (!chained) unite(L, id, id0 + j - (uint32_t)w);
         }
     }
 }
@@ -135,10 +141,12 @@ __global__ void resolve_bits_kernel(const uint8_t *dark, size_t dark_step, int w
         const int x0 = gx * GPX;
         const uint32_t bits = load_group(dark + (size_t)y * dark_step, x0, w);
         const uint32_t id0 = (uint32_t)((size_t)y * w + x0) + 1u;
-        for (uint32_t m = bits; m;) {
+        for (uint32_t m = bits; m;) {                      // one root lookup per run: its pixels share the run's first pixel
             const uint32_t i = __ffs(m) - 1;
-            m &= m - 1;
-            if (find_root(L, id0 + i) == 0u) out |= 1u << i;
+            const uint32_t len = __ffs(~(m >> i)) - 1;
+            const uint32_t runmask = ((1u << len) - 1u) << i;
+            m &= ~runmask;
+            if (find_root(L, id0 + i) == 0u) out |= runmask;
         }
     }
     bits16[(size_t)y * halfwords_per_row + gx] = (uint16_t)out;

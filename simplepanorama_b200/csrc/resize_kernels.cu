@@ -48,45 +48,58 @@ __global__ void resize_tables_kernel(int sw, int sh, int dw, int dh, AxisEntry *
     }
 }
 
-// One thread = 16 consecutive destination pixels of one row (one 16-byte store when the row allows it).
-// Seam masks are mostly 0 (dist_cut / graph_cut assign every canvas pixel to one image), and
-// a destination pixel whose four source taps are 0 is 0 whatever the coefficients: such groups skip the arithmetic.
-__global__ void resize_linear_u8_kernel(const uint8_t *src, int sw, int sh, size_t sstep, const AxisEntry *xt,
-                                        const AxisEntry *yt, uint8_t *dst, int dw, int dh, size_t dstep, int row_begin)
+// One thread = 4 consecutive destination pixels (one 32-bit store) of RESIZE_ROWS consecutive rows: the x-table
+// entries are loaded once and stay in registers, the rows are independent of each other (their loads overlap), and
+// the y-table entry of a row is the same for the whole block.  Seam masks are mostly 0 (SURVEY.md appendix A:
+// dist_cut / graph_cut assign every canvas pixel to one image) and a destination pixel whose four source taps are 0
+// is 0 whatever the coefficients, so such groups skip the arithmetic.
+constexpr int RESIZE_ROWS = 16;
+
+__global__ void __launch_bounds__(256) resize_linear_u8_kernel(const uint8_t *src, int sw, int sh, size_t sstep, const AxisEntry *xt,
+                                                               const AxisEntry *yt, uint8_t *dst, int dw, int dh, size_t dstep,
+                                                               int row_begin, int row_end)
 {
-    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    const int dy = row_begin + blockIdx.y;
-    if (dx0 >= dw || dy >= dh) return;
-    const AxisEntry ey = yt[dy];
-    const int y0 = min(max(ey.ofs, 0), sh - 1), y1 = min(max(ey.ofs + 1, 0), sh - 1);
-    const uint8_t *r0p = src + (size_t)y0 * sstep, *r1p = src + (size_t)y1 * sstep;
-    const int nx = min(16, dw - dx0);
-    uint8_t *d = dst + (size_t)dy * dstep + dx0;
-    const bool vec = nx == 16 && (((uintptr_t)d) & 15) == 0;
-    // source columns this group reads (the x table is monotonic)
-    const int sx0 = xt[dx0].ofs, sx1 = min(xt[dx0 + nx - 1].ofs + 1, sw - 1);
-    uint32_t any = 0;
-    for (int x = sx0; x <= sx1; ++x) any |= (uint32_t)__ldg(r0p + x) | (uint32_t)__ldg(r1p + x);
-    if (!any) {
-        if (vec) *reinterpret_cast<uint4 *>(d) = make_uint4(0u, 0u, 0u, 0u);
-        else
-            for (int i = 0; i < nx; ++i) d[i] = 0;
-        return;
-    }
-    uint32_t packed[4] = {0, 0, 0, 0};
+    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (dx0 >= dw) return;
+    AxisEntry ex[4];
+    int x1[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int dx = min(dx0 + i, dw - 1);
-        const AxisEntry ex = xt[dx];
-        const int x0 = ex.ofs, x1 = min(ex.ofs + 1, sw - 1);
-        const int r0 = (int)__ldg(r0p + x0) * ex.c0 + (int)__ldg(r0p + x1) * ex.c1;
-        const int r1 = (int)__ldg(r1p + x0) * ex.c0 + (int)__ldg(r1p + x1) * ex.c1;
-        const int v = ((((int)ey.c0 * (r0 >> 4)) >> 16) + (((int)ey.c1 * (r1 >> 4)) >> 16) + 2) >> 2;
-        packed[i >> 2] |= (uint32_t)min(255, max(0, v)) << (8 * (i & 3));
+    for (int i = 0; i < 4; ++i) {
+        ex[i] = xt[min(dx0 + i, dw - 1)];
+        x1[i] = min(ex[i].ofs + 1, sw - 1);
     }
-    if (vec) *reinterpret_cast<uint4 *>(d) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-    else
-        for (int i = 0; i < nx; ++i) d[i] = (uint8_t)(packed[i >> 2] >> (8 * (i & 3)));
+    const int y_first = row_begin + blockIdx.y * RESIZE_ROWS;
+    const bool vec = dx0 + 4 <= dw && ((((uintptr_t)dst) | dstep) & 3) == 0;
+#pragma unroll 4
+    for (int r = 0; r < RESIZE_ROWS; ++r) {
+        const int dy = y_first + r;
+        if (dy >= row_end) break;
+        const AxisEntry ey = yt[dy];
+        const int y0 = min(max(ey.ofs, 0), sh - 1), y1 = min(max(ey.ofs + 1, 0), sh - 1);
+        const uint8_t *r0p = src + (size_t)y0 * sstep, *r1p = src + (size_t)y1 * sstep;
+        int a0[4], a1[4], b0[4], b1[4];
+        int any = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a0[i] = __ldg(r0p + ex[i].ofs);  a1[i] = __ldg(r0p + x1[i]);
+            b0[i] = __ldg(r1p + ex[i].ofs);  b1[i] = __ldg(r1p + x1[i]);
+            any |= a0[i] | a1[i] | b0[i] | b1[i];
+        }
+        uint32_t packed = 0;
+        if (any) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int h0 = a0[i] * ex[i].c0 + a1[i] * ex[i].c1;
+                const int h1 = b0[i] * ex[i].c0 + b1[i] * ex[i].c1;
+                const int v = ((((int)ey.c0 * (h0 >> 4)) >> 16) + (((int)ey.c1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                packed |= (uint32_t)min(255, max(0, v)) << (8 * i);
+            }
+        }
+        uint8_t *d = dst + (size_t)dy * dstep + dx0;
+        if (vec) *reinterpret_cast<uint32_t *>(d) = packed;
+        else
+            for (int i = 0; i < 4 && dx0 + i < dw; ++i) d[i] = (uint8_t)(packed >> (8 * i));
+    }
 }
 
 // ---- test::adjust_intensity (reference src/test/_test.cpp:110-122): float-bilinear up-scaling of the
@@ -173,8 +186,8 @@ int launch_resize_mask(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_
     if (rc) return rc;
     const int n = dw > dh ? dw : dh;
     resize_tables_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sw, sh, dw, dh, tab, tab + dw);
-    dim3 block(64), grid((dw + 1023) / 1024, row_end - row_begin);
-    resize_linear_u8_kernel<<<grid, block, 0, ctx->stream>>>(src, sw, sh, sstep, tab, tab + dw, dst, dw, dh, dstep, row_begin);
+    dim3 block(256), grid((dw + 1023) / 1024, (row_end - row_begin + RESIZE_ROWS - 1) / RESIZE_ROWS);
+    resize_linear_u8_kernel<<<grid, block, 0, ctx->stream>>>(src, sw, sh, sstep, tab, tab + dw, dst, dw, dh, dstep, row_begin, row_end);
     SPANO_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
     return 2;
