@@ -410,8 +410,8 @@ def run_ours(args):
         "achieved": blend_flops / blend_s / 1e12 if blend_s > 0 else None, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": (blend_flops / blend_s / 1e12 / fp32_peak) if blend_s > 0 else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
-        # (profiles/r1g_blend_march6_raw.csv: 471.6 + 307.8 MB for a 22.39 Mpx tile = 34.8 B/px), scaled to this run's mean tile
-        "traffic": 34.8 * px_done / n_blend, "traffic_unit": "bytes per launch (ncu capture, scaled by tile pixels)",
+        # (profiles/r1j_blend_march6_sparse_raw.csv: 149.7 + 54.9 MB for 6.54 Mpx filtered = 31.3 B/px), scaled to this run
+        "traffic": 31.3 * px_done / n_blend, "traffic_unit": "bytes per launch (ncu capture profiles/r1j_blend_march6_sparse_raw.csv, scaled by filtered tile pixels)",
         "peak_source": "FFMA microbenchmark run by this bench (MEASURED_PEAKS.json has no fp32 entry)",
         "launches_per_step": n_blend, "avg_launch_ms": blend_s * 1e3 / n_blend,
         "algorithmic_flop_per_tile_px": 688 * cfg.bands,
@@ -425,7 +425,7 @@ def run_ours(args):
     roofline_warp = {
         "kernel": "warp_kernel", "bound": "hbm", "achieved": 7.0 * warp_T / warp_s / 1e9 if warp_s > 0 else None,
         "peak": hbm_peak, "unit": "GB/s", "frac": (7.0 * warp_T / warp_s / 1e9 / hbm_peak) if warp_s > 0 else None,
-        "traffic": 5.32 * warp_T / n_warp, "traffic_unit": "bytes per launch (ncu capture profiles/r1_warp_mask_raw.csv: 72.2 + 47.0 MB for 22.4 Mpx; part of the tile is still dirty in L2 at kernel end)",
+        "traffic": 5.32 * warp_T / n_warp, "traffic_unit": "bytes per launch (ncu capture profiles/r1j_warp_raw.csv: 72.3 + 47.1 MB for 22.46 Mpx; part of the tile is still dirty in L2 at kernel end)",
         "peak_source": hbm_src, "launches_per_step": n_warp, "avg_launch_ms": warp_s * 1e3 / n_warp,
         "algorithmic_bytes_per_tile_px": 7,
     }
