@@ -7,7 +7,8 @@
 One "step" = one full pass of the hot path over the synthetic image set: every source image is
 warped (inverse projection + fixed-point bilinear + gain), its validity mask is built, all tiles are
 multiband-blended and the canvas is normalised to 8 bit.  At N > 1 the canvas is cut into row bands
-(one per GPU) and the finished 8-bit bands are gathered to rank 0 inside the timed region.
+(one per GPU); every rank's normalise kernel stores its finished 8-bit band straight into the canvas on rank 0
+(NVLink peer stores) inside the timed region.
 
 `value`  : canvas Mpx / step time with sources, K/R, gains and mask_cut already resident in HBM.
 `e2e`    : the same through the host-buffer C-ABI call a user makes (spano_composite): pinned host
@@ -54,8 +55,9 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, enabled: bool = True):
         self.index = index
+        self.enabled = enabled
         self.samples = []
         self.stop = threading.Event()
         self.th = threading.Thread(target=self.run, daemon=True)
@@ -69,15 +71,17 @@ class ClockSampler:
                     self.samples.append([s.strip() for s in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.25)
 
     def __enter__(self):
-        self.th.start()
+        if self.enabled:
+            self.th.start()
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.th.join(timeout=6)
+        if self.enabled:
+            self.th.join(timeout=6)
 
     def summary(self):
         if not self.samples:
@@ -93,14 +97,22 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------
-def build_workload(args):
+class _Shape:
+    """stands in for a source image this rank does not hold (geometry only)"""
+    def __init__(self, h, w):
+        self.shape = (h, w, 3)
+
+
+def build_workload(args, rank=0, world=1):
     from simplepanorama_b200 import api, synth
     cfg = synth.config(args.workload, args.scale)
     K, R, gains = synth.cameras(cfg)
     from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:   # numpy releases the GIL
-        images = list(ex.map(lambda j: synth.make_image(cfg, j, gains[j]), range(cfg.n)))
-        plan = api.plan_tiles(images, R, K, cfg.kind, cfg.focal)   # host geometry only
+    workers = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
+    with ThreadPoolExecutor(max_workers=workers) as ex:   # numpy releases the GIL
+        # at N > 1 a rank synthesises only the sources it owns (image j belongs to rank j % N)
+        images = list(ex.map(lambda j: synth.make_image(cfg, j, gains[j]) if j % world == rank else None, range(cfg.n)))
+        plan = api.plan_tiles([im if im is not None else _Shape(cfg.height, cfg.width) for im in images], R, K, cfg.kind, cfg.focal)   # host geometry only
         corners = [p[2] for p in plan]
         sizes = [p[3] for p in plan]
         # mask_cut stays at preview scale (1/8), as stitch_parameters::return_full receives it; the up-scaling to
@@ -220,7 +232,7 @@ def run_ours(args):
     if world > 1:
         tdist.init_process_group("nccl", device_id=dev)
 
-    wl = build_workload(args)
+    wl = build_workload(args, rank, world)
     cfg = wl["cfg"]
     ctx = api.Context(local)
     # a dedicated (non-default) stream shared by torch and the library, so that torch.cuda.Event
@@ -244,16 +256,11 @@ def run_ours(args):
     mine = set(owned) if world > 1 else set(range(cfg.n))
 
     # host (pinned) and device copies of the inputs; at N > 1 a rank holds only the sources it owns
-    h_img = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() if j in mine else None for j, a in enumerate(wl["images"])]
+    h_img = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() if (j in mine and a is not None) else None for j, a in enumerate(wl["images"])]
     h_cut = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in wl["cuts"]]
     d_img = [t.to(dev, non_blocking=True) if t is not None else None for t in h_img]
     d_cut = [t.to(dev, non_blocking=True) for t in h_cut]
-    if world > 1 and rank == 0:
-        d_full = torch.empty((wl["H"], wl["W"], 3), dtype=torch.uint8, device=dev)
-        d_canvas = d_full[row0:row1] if row1 > row0 else d_full[:1]
-    else:
-        d_full = None
-        d_canvas = torch.empty((max(1, row1 - row0), wl["W"], 3), dtype=torch.uint8, device=dev)
+    d_canvas = torch.empty((max(1, row1 - row0), wl["W"], 3), dtype=torch.uint8, device=dev) if world == 1 else None
     h_canvas = torch.empty((max(1, row1 - row0), wl["W"], 3), dtype=torch.uint8).pin_memory()
     torch.cuda.synchronize()
 
@@ -270,22 +277,36 @@ def run_ours(args):
     lib = ctx.lib
     import ctypes as C
 
-    ctx_s = aux = arenas = tok = None
+    ctx_s = aux = arenas = tok = peer_canvas = None
     if world > 1:
         ctx_s = api.Context(local)                     # owner-side work runs on its own stream / context
         aux = torch.cuda.Stream(device=dev)
         ctx_s.set_stream(aux.cuda_stream)
         arenas = sdist.PeerArenas(ctx, sp, rank)
+        peer_canvas = sdist.PeerCanvas(ctx, sp, rank)   # the canvas lives on rank 0; every rank stores its band into it
         tok = torch.zeros(1, device=dev)
 
+    trace = {"enqueue_ms": [], "phases": []}
+
     def step_sharded(host):
+        t_cpu0 = time.perf_counter()
+        try:
+            return _step_sharded(host)
+        finally:
+            trace["enqueue_ms"].append((time.perf_counter() - t_cpu0) * 1e3)
+
+    def _step_sharded(host):
         descs = descs_host if host else descs_dev
         have = row1 > row0
+        pe = [torch.cuda.Event(enable_timing=True) for _ in range(6)]   # phase marks (main stream; [4], [5] on aux)
+        pe[0].record(stream)
         if have:   # (host variant: queues the small mask uploads ahead of the large source uploads below)
             sdist.blend_begin(ctx, sp, rank, cfg.bands, cfg.sigma, host_descs=descs_host if host else None,
                               host_canvas=(h_canvas.data_ptr(), h_canvas.stride(0)))
         tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)   # every rank has finished blending the previous step's arenas
+        pe[1].record(stream)
         aux.wait_stream(stream)
+        pe[4].record(aux)
         evs = []
         for rnd in sp.rounds:
             for j in rnd:
@@ -294,6 +315,7 @@ def run_ours(args):
             ev = torch.cuda.Event()
             ev.record(aux)
             evs.append(ev)
+        pe[5].record(aux)
         for t, rnd in enumerate(sp.rounds):
             stream.wait_event(evs[t])
             tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)   # round t is in every arena
@@ -304,9 +326,11 @@ def run_ours(args):
             if host:
                 sdist.blend_finish(ctx, h_canvas.data_ptr(), h_canvas.stride(0), host=True)
             else:
-                sdist.blend_finish(ctx, d_canvas.data_ptr(), d_canvas.stride(0))
-        if not host:
-            return sdist.gather_bands_into(d_full, d_canvas[: row1 - row0], bands, rank, world)
+                # the normalise kernel writes the finished 8-bit band straight into rank 0's canvas (NVLink peer stores)
+                sdist.blend_finish(ctx, peer_canvas.band_ptr(row0), peer_canvas.step)
+        pe[2].record(stream)
+        pe[3].record(stream)
+        trace["phases"].append(pe)
 
     def step_dev():
         if world > 1:
@@ -355,10 +379,17 @@ def run_ours(args):
         return ms, launches, stage
 
     canvas_mpx = wl["W"] * wl["H"] / 1e6
-    with ClockSampler(local) as clk:
+    phase_ms = None
+    with ClockSampler(local, enabled=(rank == 0)) as clk:   # one nvidia-smi poller per job, not per rank
         ms, launches, stage = timed(step_dev, args.steps, args.warmup, with_timers=True)
     clocks = clk.summary()
     value = canvas_mpx / (ms * 1e-3)
+    if world > 1 and trace["phases"]:
+        torch.cuda.synchronize()
+        pe = trace["phases"][-1]     # last timed step of the device-resident run
+        phase_ms = {"step_start_barrier": pe[0].elapsed_time(pe[1]), "rounds_barriers_blend_normalise": pe[1].elapsed_time(pe[2]),
+                    "owner_stream_warp_mask_scatter": pe[4].elapsed_time(pe[5])}
+        trace["phases"].clear()
 
     # roofline of the dominant kernel (the blend) and of the warp kernel, from the live stage timers
     stage_ms, stage_n, (px_done, px_offered) = stage
@@ -440,6 +471,24 @@ def run_ours(args):
         dense = {"value": canvas_mpx / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d,
                  "note": "blend sparsity disabled (spano_debug_blend_dense): all tile pixels filtered"}
 
+    # checksum of the finished canvas (rank 0): identical at every N -- the multi-GPU canvas is bit-identical to the
+    # single-GPU one
+    checksum = None
+    if rank == 0:
+        step_dev()
+        barrier()
+        if world == 1:
+            cv = d_canvas
+        else:
+            cv = torch.empty((wl["H"], peer_canvas.step), dtype=torch.uint8, device=dev)
+            C.CDLL("libcudart.so.12").cudaMemcpy(C.c_void_p(cv.data_ptr()), C.c_void_p(peer_canvas.ptr), C.c_size_t(peer_canvas.bytes), 3)
+            cv = cv[:, : 3 * wl["W"]]
+        flat = cv.reshape(-1).to(torch.int64)
+        checksum = int((flat * (torch.arange(flat.numel(), device=dev, dtype=torch.int64) % 65521 + 1)).sum().item() % (1 << 61))
+    elif world > 1:
+        step_dev()
+        barrier()
+
     e2e = None
     if not args.no_e2e:
         ms_e, _, _ = timed(step_host, max(1, min(args.steps, 3)), 1)
@@ -457,7 +506,9 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config_json(wl, args, world), "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": clocks, "numa_node": numa, "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu, "dense_masks": dense,
+                "clocks": clocks, "numa_node": numa,
+                "canvas_checksum": checksum, "cpu_enqueue_ms_per_step": (float(np.median(trace["enqueue_ms"])) if trace["enqueue_ms"] else None),
+                "phase_ms_rank0": phase_ms, "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu, "dense_masks": dense,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
                 "stage_note": "in-step warp/mask times overlap the blend (auxiliary stream); isolated: warp %.3f ms, mask %.3f ms per step" % (warp_s * 1e3, mask_iso_ms),
                 "tile_mpx_per_s": wl["T"] / 1e6 / (ms * 1e-3)}
@@ -466,6 +517,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         tdist.barrier()
         arenas.close()
+        peer_canvas.close()
         tdist.destroy_process_group()
 
 

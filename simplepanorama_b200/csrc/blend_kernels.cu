@@ -55,6 +55,7 @@ struct BlendParams {
     int canvas_w;
     int ax, ay;        // tile corner relative to acc origin (canvas x, canvas y - row0)
     int radius;
+    const int *plan = nullptr; // marching kernel: plan made beforehand (launch_blend_plan), else made at launch
 };
 
 // cv::borderInterpolate(p, len, BORDER_REFLECT)
@@ -383,6 +384,32 @@ int launch_fast(spano_ctx *ctx, const BlendParams &P, dim3 grid)
     return 0;
 }
 
+// activity + plan kernels of one tile launch into `plan` (device, march::PlanView::ints(strips, sms) ints)
+template <int SW>
+int make_plan(spano_ctx *ctx, const BlendParams &Q, int sms, int *plan)
+{
+    const int strips = (Q.w + SW - 1) / SW;
+    if (strips > 2048 || sms > 1024) return spano_fail(ctx, SPANO_E_LIMIT, "tile wider than %d px", 2048 * SW);
+    const march::PlanView V(strips, sms);
+    if (!ctx->blend_stats) {
+        SPANO_CUDA(ctx, cudaMalloc((void **)&ctx->blend_stats, 2 * sizeof(unsigned long long)));
+        SPANO_CUDA(ctx, cudaMemsetAsync(ctx->blend_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        ctx->owned.push_back(ctx->blend_stats);
+    }
+    int *ymin = plan + V.ymin(), *ymax = plan + V.ymax();
+    march::plan_init_kernel<<<(strips + 255) / 256, 256, 0, ctx->stream>>>(ymin, ymax, strips);
+    const int dense = g_blend_dense;
+    if (!dense) {
+        const int ra = std::max(0, Q.ty_begin - march::R), rb = std::min(Q.h, Q.ty_end + march::R);
+        dim3 ag((Q.w + 511) / 512, (rb - ra + 63) / 64);
+        march::activity_kernel<SW><<<ag, 256, 0, ctx->stream>>>(Q.cut, Q.cut_step, Q.w, ra, rb, ymin, ymax);
+    }
+    march::plan_kernel<SW><<<1, 256, 0, ctx->stream>>>(plan, strips, sms, Q.ty_begin, Q.ty_end, dense, ctx->blend_stats, Q.w);
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += dense ? 2 : 3;
+    return 0;
+}
+
 template <int B>
 int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
 {
@@ -402,28 +429,17 @@ int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
     P.w = Q.w;  P.h = Q.h;
     P.ty_begin = Q.ty_begin;  P.ty_end = Q.ty_end;
     P.acc = Q.acc;  P.canvas_w = Q.canvas_w;  P.ax = Q.ax;  P.ay = Q.ay;
-    // sparsity plan (activity of mask_cut per strip -> active output rows -> even split over the CTAs)
-    const int strips = (Q.w + SW - 1) / SW;
-    if (strips > 2048 || sms > 1024) return spano_fail(ctx, SPANO_E_LIMIT, "tile wider than %d px", 2048 * SW);
-    const march::PlanView V(strips, sms);
-    int *plan = nullptr;
-    if (int rc = spano_reserve(ctx, spano_ctx::BUF_BLENDPLAN, march::PlanView::ints(strips, sms) * sizeof(int), (void **)&plan)) return rc;
-    if (!ctx->blend_stats) {
-        SPANO_CUDA(ctx, cudaMalloc((void **)&ctx->blend_stats, 2 * sizeof(unsigned long long)));
-        SPANO_CUDA(ctx, cudaMemsetAsync(ctx->blend_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
-        ctx->owned.push_back(ctx->blend_stats);
+    // sparsity plan (activity of mask_cut per strip -> active output rows -> even split over the CTAs), unless the
+    // caller already made it (fused path: on the auxiliary stream, one image ahead)
+    if (Q.plan) {
+        P.plan = Q.plan;
+    } else {
+        int *plan = nullptr;
+        const int strips = (Q.w + SW - 1) / SW;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_BLENDPLAN, march::PlanView::ints(strips, sms) * sizeof(int), (void **)&plan)) return rc;
+        if (int rc = make_plan<SW>(ctx, Q, sms, plan)) return rc;
+        P.plan = plan;
     }
-    int *ymin = plan + V.ymin(), *ymax = plan + V.ymax();
-    march::plan_init_kernel<<<(strips + 255) / 256, 256, 0, ctx->stream>>>(ymin, ymax, strips);
-    const int dense = g_blend_dense;
-    if (!dense) {
-        const int ra = std::max(0, Q.ty_begin - march::R), rb = std::min(Q.h, Q.ty_end + march::R);
-        dim3 ag((Q.w + 511) / 512, (rb - ra + 63) / 64);
-        march::activity_kernel<SW><<<ag, 256, 0, ctx->stream>>>(Q.cut, Q.cut_step, Q.w, ra, rb, ymin, ymax);
-    }
-    march::plan_kernel<SW><<<1, 256, 0, ctx->stream>>>(plan, strips, sms, Q.ty_begin, Q.ty_end, dense, ctx->blend_stats, Q.w);
-    P.plan = plan;
-    ctx->launches += dense ? 2 : 3;
     march::blend_march_kernel<B, SW><<<sms, march::THREADS, C::SMEM, ctx->stream>>>(P);
     return 0;
 }
@@ -488,8 +504,35 @@ int launch_blend_clear(spano_ctx *ctx, float4 *acc, int canvas_w, int rows)
 static int g_force_generic = 0;
 extern "C" void spano_debug_force_generic(int on) { g_force_generic = on; }
 
+static bool march_path(int radius) { return radius == FR && g_force_generic == 0; }
+
+size_t blend_plan_bytes(spano_ctx *ctx, int w, int bands, int radius)
+{
+    if (!march_path(radius) || w <= 0) return 0;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int SW = bands <= 6 ? 32 : 16;
+    return march::PlanView::ints((w + SW - 1) / SW, sms) * sizeof(int);
+}
+
+int launch_blend_plan(spano_ctx *ctx, const BlendTile &t, int bands, int radius, int row0, int row1, int *plan)
+{
+    int ty_begin = row0 - t.cy, ty_end = row1 - t.cy;
+    if (ty_begin < 0) ty_begin = 0;
+    if (ty_end > t.h) ty_end = t.h;
+    if (ty_end <= ty_begin || t.w <= 0 || !march_path(radius)) return 0;
+    BlendParams P;
+    P.cut = t.cut;  P.cut_step = t.cut_step;
+    P.w = t.w;  P.h = t.h;
+    P.ty_begin = ty_begin;  P.ty_end = ty_end;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int rc = bands <= 6 ? make_plan<32>(ctx, P, sms, plan) : make_plan<16>(ctx, P, sms, plan);
+    return rc ? rc : 3;
+}
+
 int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius, float4 *acc, int canvas_w, int row0,
-                      int row1)
+                      int row1, const int *plan)
 {
     // tile rows that fall into canvas rows [row0,row1)
     int ty_begin = row0 - t.cy, ty_end = row1 - t.cy;
@@ -505,6 +548,7 @@ int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius,
     P.acc = acc;  P.canvas_w = canvas_w;
     P.ax = t.cx;  P.ay = t.cy - row0;
     P.radius = radius;
+    P.plan = plan;
     int rc = 0;
     const bool fast = (radius == FR) && g_force_generic != 1;
     if (fast && g_force_generic == 0) {

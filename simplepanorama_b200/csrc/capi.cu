@@ -687,7 +687,7 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
     // Tiles that touch canvas rows [row0,row1) take part.  BORDER_REFLECT is resolved inside each tile,
     // so a band needs the full extent of exactly those tiles and nothing from neighbouring bands.
     std::vector<int> use;
-    size_t src_max = 0, tile_max = 0, mask_max = 0, small_max = 0, field_max = 0;
+    size_t src_max = 0, tile_max = 0, mask_max = 0, small_max = 0, field_max = 0, plan_max = 0;
     bool any_small = false;
     for (int j = 0; j < n; ++j) {
         if (int rc = check_image_args(ctx, im[j].src_bgr, im[j].src_w, im[j].src_h, im[j].src_step, 3, "source")) return rc;
@@ -715,6 +715,12 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
     }
     const int radius = launch_blend_setup(ctx, bands, sigma);
     if (radius < 0) return radius;
+    for (int j : use) plan_max = std::max(plan_max, blend_plan_bytes(ctx, im[j].w, bands, radius));
+    int *d_plan[2] = {nullptr, nullptr};
+    if (plan_max) {
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_BLENDPLAN, plan_max, (void **)&d_plan[0])) return rc;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_BLENDPLAN2, plan_max, (void **)&d_plan[1])) return rc;
+    }
     float4 *acc = nullptr;
     if (int rc = spano_reserve(ctx, spano_ctx::BUF_ACC, (size_t)cw * rows * sizeof(float4), (void **)&acc)) return rc;
     uint8_t *d_tile = nullptr, *d_valid = nullptr, *d_srcbuf[2] = {nullptr, nullptr}, *d_cutbuf[2] = {nullptr, nullptr};
@@ -879,13 +885,20 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
                 int kk = launch_adjust_intensity(ctx, tile_b, im[j].w, im[j].h, t_step, fld, im[j].intensity_w, im[j].intensity_h, fpitch);
                 if (kk < 0) return kk;
             }
+            if (d_plan[b]) {
+                // the blend's sparsity plan (activity of mask_cut -> pieces) is made here, one image ahead, so that
+                // the blends follow each other back to back on the main stream
+                const BlendTile pt{tile_b, t_step, cut, c_step, valid, v_step, im[j].w, im[j].h, im[j].tl_x - mx, im[j].tl_y - my};
+                int kk = launch_blend_plan(ctx, pt, bands, radius, row0, row1, d_plan[b]);
+                if (kk < 0) return kk;
+            }
             SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_warped[b], aux));
         }
         // ---- main stream: blend tile b into the accumulator ----
         SPANO_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_warped[b], 0));
         StageTimer t2(ctx, 2);
         const BlendTile bt{tile_b, t_step, cut, c_step, valid, v_step, im[j].w, im[j].h, im[j].tl_x - mx, im[j].tl_y - my};
-        int k = launch_blend_tile(ctx, bt, bands, radius, acc, cw, row0, row1);
+        int k = launch_blend_tile(ctx, bt, bands, radius, acc, cw, row0, row1, d_plan[b]);
         if (k < 0) return k;
         t2.stop(k);
         SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_blended[b], main_stream));

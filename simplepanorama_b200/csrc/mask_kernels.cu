@@ -87,18 +87,37 @@ __global__ void ccl_init_kernel(const uint8_t *dark, size_t dark_step, int w, in
     }
 }
 
+// blockDim.x == 32: a warp = 32 consecutive groups (512 pixels) of ONE row.
 __global__ void ccl_merge_kernel(const uint8_t *dark, size_t dark_step, int w, int h, int groups, uint32_t *L)
 {
+    const int lane = threadIdx.x;
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (gx >= groups || y >= h) return;
+    const bool in = gx < groups && y < h;
     const int x0 = gx * GPX;
-    const uint8_t *row = dark + (size_t)y * dark_step;
-    const uint32_t bits = load_group(row, x0, w);
-    if (!bits) return;
+    const uint8_t *row = dark + (size_t)(in ? y : 0) * dark_step;
+    const uint32_t bits = in ? load_group(row, x0, w) : 0u;
     const uint32_t id0 = (uint32_t)((size_t)y * w + x0) + 1u;
-    // bit i+1 of the extended words = pixel i; bit 0 = the pixel left of the group
-    const uint32_t left_px = (x0 > 0 && row[x0 - 1]) ? 1u : 0u;
+    const uint32_t left_px = (in && (bits & 1u) && x0 > 0 && row[x0 - 1]) ? 1u : 0u;   // only matters when pixel 0 is dark
+
+    // A run that enters a group from the left is linked straight to the first pixel of that run as far back as this
+    // warp can see it, not to its left neighbour: a horizontal run of G groups then hangs off G/32 links instead of
+    // a chain of G.  tail = first pixel of the run that leaves this group through its right edge; a fully dark group
+    // that continues its left neighbour's run inherits the neighbour's tail (segmented copy scan over the lanes).
+    const bool cont = left_px != 0u;
+    uint32_t tail = 0u;
+    if (bits & 0x8000u) tail = id0 + (16u - (uint32_t)__clz(~(bits << 16)));   // start of the run that holds pixel 15
+    bool open = (bits == 0xFFFFu) && cont && lane > 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t2 = __shfl_up_sync(0xffffffffu, tail, d);
+        const int o2 = __shfl_up_sync(0xffffffffu, (int)open, d);
+        if (lane >= d && open) { tail = t2; open = o2 != 0; }
+    }
+    const uint32_t prev_tail = __shfl_up_sync(0xffffffffu, tail, 1);
+    if (!bits) return;
+    const uint32_t left_target = (lane > 0) ? prev_tail : id0 - 1u;
+
     uint32_t up_ext = 0;
     if (y > 0) {
         const uint8_t *up = row - dark_step;
@@ -115,15 +134,15 @@ __global__ void ccl_merge_kernel(const uint8_t *dark, size_t dark_step, int w, i
         const uint32_t id = id0 + i;
         const int xa = x0 + (int)i, xb = xa + (int)len - 1;
         if (border_row || xa == 0 || xb == w - 1) unite(L, id, 0u);
-        if (i == 0 && left_px) unite(L, id, id - 1u);      // runs are pre-linked only inside a group
+        if (i == 0 && cont) unite(L, id, left_target);     // runs are pre-linked only inside a group
         // every maximal segment of dark pixels above the run is (part of) one run of the row above; a segment that
         // starts at the group's first pixel with a dark pixel above-left belongs to the upper run the left
-        // neighbour group already sees -- and if this run also continues to the left, that link is made there
+        // neighbour group already sees -- and this run continues to the left, so that link is made there
         for (uint32_t um = up & runmask; um;) {
             const uint32_t j = __ffs(um) - 1;
             const uint32_t ulen = __ffs(~(um >> j)) - 1;
             um &= ~(((1u << ulen) - 1u) << j);
-            const bool chained = (j == 0) && left_px && (up_ext & 1u);
+            const bool chained = (j == 0) && cont && (up_ext & 1u);
             if (!chained) unite(L, id, id0 + j - (uint32_t)w);
         }
     }

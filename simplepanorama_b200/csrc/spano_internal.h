@@ -46,7 +46,7 @@ struct spano_ctx {
     long long launches = 0;
     // grow-only scratch buffers, indexed by role
     enum { BUF_LABELS = 0, BUF_DARK, BUF_MASK0, BUF_TABLES, BUF_ACC, BUF_TILE, BUF_TILEMASK, BUF_CUTMASK, BUF_SRC,
-           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_BLENDPLAN, BUF_COUNT };
+           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_BLENDPLAN, BUF_BLENDPLAN2, BUF_COUNT };
     DeviceBuffer buf[BUF_COUNT];
     std::vector<void *> owned; // extra allocations freed at destroy / end of call
     unsigned long long *blend_stats = nullptr; // device: [0] tile pixels the blend processed, [1] tile pixels offered
@@ -122,8 +122,12 @@ struct BlendTile {
 };
 int launch_blend_setup(spano_ctx *ctx, int bands, double sigma);
 int launch_blend_clear(spano_ctx *ctx, float4 *acc, int canvas_w, int rows);
+// `plan`: device plan made beforehand with launch_blend_plan for the same tile, band and row range (marching
+// kernel only; blend_plan_bytes() == 0 when another kernel will run); nullptr = plan at launch.
 int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius, float4 *acc, int canvas_w, int row0,
-                      int row1);
+                      int row1, const int *plan = nullptr);
+size_t blend_plan_bytes(spano_ctx *ctx, int w, int bands, int radius);
+int launch_blend_plan(spano_ctx *ctx, const BlendTile &t, int bands, int radius, int row0, int row1, int *plan);
 int launch_normalise(spano_ctx *ctx, const float4 *acc, int canvas_w, int rows, int bands, int out_kind, void *out,
                      size_t out_step, int col0 = 0, int col1 = -1);
 int launch_fp32_peak(spano_ctx *ctx, int variant, double *tflops);

@@ -179,6 +179,47 @@ class PeerArenas:
         self.ptrs, self.own = [], None
 
 
+class PeerCanvas:
+    """The final 8-bit canvas lives on rank 0 and is mapped into every process: each rank's normalise kernel
+    (spano_dev_blend_finish) stores its finished band straight into rank 0's memory over NVLink, so there is no
+    gather collective -- only the barrier that ends the step.  ptr = canvas base as addressable from this process."""
+
+    def __init__(self, ctx, plan: ShardPlan, rank: int, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        self.ctx, self.rank = ctx, rank
+        self.step = _al(3 * plan.canvas_w, 16)
+        self.bytes = self.step * plan.canvas_h
+        self.own = None
+        handle = None
+        if rank == 0:
+            own = C.c_void_p()
+            hb = (C.c_ubyte * 64)()
+            ctx.check(ctx.lib.spano_peer_alloc(ctx.h, self.bytes, C.byref(own), hb))
+            self.own = own.value
+            handle = bytes(hb)
+        box = [handle]
+        dist.broadcast_object_list(box, src=0, group=group)
+        if rank == 0:
+            self.ptr = self.own
+        else:
+            p = C.c_void_p()
+            hb = (C.c_ubyte * 64).from_buffer_copy(box[0])
+            ctx.check(ctx.lib.spano_peer_open(ctx.h, hb, C.byref(p)))
+            self.ptr = p.value
+
+    def band_ptr(self, row0: int) -> int:
+        return self.ptr + row0 * self.step
+
+    def close(self):
+        import ctypes as C
+        if self.rank == 0 and self.own:
+            self.ctx.lib.spano_peer_free(self.ctx.h, C.c_void_p(self.own))
+        elif self.ptr:
+            self.ctx.lib.spano_peer_close(self.ctx.h, C.c_void_p(self.ptr))
+        self.ptr = self.own = None
+
+
 def scatter_tile(ctx, plan: ShardPlan, j: int, desc, arena_ptrs, kind: int, focal: float, host: bool = False):
     """Owner side of one image: warp + validity mask, rows stored into the band arenas."""
     import ctypes as C
