@@ -285,6 +285,10 @@ def run_ours(args):
         arenas = sdist.PeerArenas(ctx, sp, rank)
         peer_canvas = sdist.PeerCanvas(ctx, sp, rank)   # the canvas lives on rank 0; every rank stores its band into it
         tok = torch.zeros(1, device=dev)
+        # one barrier per group of rounds: every round for up to 12 rounds, coarser for many small images (each barrier
+        # is an all-reduce every rank has to reach on the CPU as well)
+        per = max(1, -(-len(sp.rounds) // 12))
+        groups = [sp.rounds[i:i + per] for i in range(0, len(sp.rounds), per)]
 
     trace = {"enqueue_ms": [], "phases": []}
 
@@ -308,20 +312,22 @@ def run_ours(args):
         aux.wait_stream(stream)
         pe[4].record(aux)
         evs = []
-        for rnd in sp.rounds:
-            for j in rnd:
-                if sp.owner[j] == rank:
-                    sdist.scatter_tile(ctx_s, sp, j, descs[j], arenas.ptrs, cfg.kind, cfg.focal, host=host)
+        for g in groups:
+            for rnd in g:
+                for j in rnd:
+                    if sp.owner[j] == rank:
+                        sdist.scatter_tile(ctx_s, sp, j, descs[j], arenas.ptrs, cfg.kind, cfg.focal, host=host)
             ev = torch.cuda.Event()
             ev.record(aux)
             evs.append(ev)
         pe[5].record(aux)
-        for t, rnd in enumerate(sp.rounds):
+        for t, g in enumerate(groups):
             stream.wait_event(evs[t])
-            tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)   # round t is in every arena
+            tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)   # the rounds of group t are in every arena
             if have:
-                for j in rnd:
-                    sdist.blend_add(ctx, sp, rank, j, descs, arenas.own, host=host)
+                for rnd in g:
+                    for j in rnd:
+                        sdist.blend_add(ctx, sp, rank, j, descs, arenas.own, host=host)
         if have:
             if host:
                 sdist.blend_finish(ctx, h_canvas.data_ptr(), h_canvas.stride(0), host=True)

@@ -122,6 +122,18 @@ int spano_resize_mask(spano_ctx *ctx, const uint8_t *src, int src_w, int src_h, 
 int spano_adjust_intensity(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, const float *field, int field_w,
                            int field_h, size_t field_step);
 
+/* ---- seam search by distance (preview scale) ---------------------------------
+ * spano_distance_transform = cv::distanceTransform(mask, dist, cv::DIST_L2, cv::DIST_MASK_5, CV_32F) on CV_8UC1
+ * (reference src/math/_distance_cut.cpp:63, src/math/_blending.cpp:110): distance of every pixel to the nearest
+ * zero pixel with the 5x5 chamfer metrics (1, 1.4, 2.1969), float32 two-pass arithmetic, FLT_MAX where the mask
+ * has no zero pixel at all.  dist_step in BYTES.  Bit-exact with the pinned OpenCV build.
+ * spano_dist_cut = dcut::dist_cut(masks, top_lefts) (src/math/_distance_cut.cpp:7-51 with distance_transform
+ * :57-73): cut[i] = masks[i], zeroed where an overlapping image j has a strictly larger distance/255.
+ * HOST buffers.                                                                                            */
+int spano_distance_transform(spano_ctx *ctx, const uint8_t *mask, int w, int h, size_t step, float *dist, size_t dist_step);
+int spano_dist_cut(spano_ctx *ctx, int n, const uint8_t *const *masks, const size_t *mask_steps, const int *tl_x,
+                   const int *tl_y, const int *w, const int *h, uint8_t *const *cut, const size_t *cut_steps);
+
 /* a6 alone: `img / gain` on CV_8UC3, in place. */
 int spano_apply_gain(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, double gain);
 

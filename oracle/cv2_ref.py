@@ -177,7 +177,8 @@ def blend_to_u8(blend: np.ndarray) -> np.ndarray:
 def dist_cut(masks, corners):
     """dcut::dist_cut (src/math/_distance_cut.cpp:7-73): chamfer-5 L2 distance compare in overlaps.
     Produces the `mask_cut[]` INPUT of the hot path (not part of the accelerated path)."""
-    D = [cv2.distanceTransform(m, cv2.DIST_L2, cv2.DIST_MASK_5) / np.float32(255.0) for m in masks]
+    # `transformed / 255` is a cv::MatExpr: convertTo with alpha = 1/255., i.e. a float multiplication by (float)(1/255.)
+    D = [cv2.distanceTransform(m, cv2.DIST_L2, cv2.DIST_MASK_5) * np.float32(1.0 / 255.0) for m in masks]
     out = [m.copy() for m in masks]
     n = len(masks)
     for i in range(n):

@@ -214,3 +214,23 @@ def return_full(images, R, K, kind, focal, gains, masks_cut, bands, sigma, want_
     if want_float:
         return out, blend, gained, msks, corners
     return out, gained, msks, corners
+
+
+def distance_transform(mask):
+    """cv::distanceTransform(mask, DIST_L2, DIST_MASK_5, CV_32F)."""
+    m = np.ascontiguousarray(mask, np.uint8)
+    out = np.empty(m.shape, np.float32)
+    lib().orc_distance_transform(m.ctypes.data_as(C.c_void_p), m.shape[1], m.shape[0], C.c_size_t(m.strides[0]), _p(out, C.c_float))
+    return out
+
+
+def dist_cut(masks, corners):
+    """dcut::dist_cut -> list of cut masks."""
+    n = len(masks)
+    ms = [np.ascontiguousarray(m, np.uint8) for m in masks]
+    outs = [np.empty(m.shape, np.uint8) for m in ms]
+    arr = lambda xs: (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+    tlx = np.array([c[0] for c in corners], np.int32); tly = np.array([c[1] for c in corners], np.int32)
+    w = np.array([m.shape[1] for m in ms], np.int32); h = np.array([m.shape[0] for m in ms], np.int32)
+    lib().orc_dist_cut(n, arr(ms), _p(tlx, C.c_int), _p(tly, C.c_int), _p(w, C.c_int), _p(h, C.c_int), arr(outs))
+    return outs

@@ -740,3 +740,86 @@ void orc_adjust_intensity(uint8_t *bgr, int w, int h, size_t step, const float *
         }
     free(f);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * cv::distanceTransform(src, dst, DIST_L2, DIST_MASK_5, CV_32F) and dcut::dist_cut
+ * (reference src/math/_distance_cut.cpp:7-73; also used by blnd::simple_blend, src/math/_blending.cpp:110).
+ * OpenCV is not vendored by the reference; the build it is pinned to here (cv2 4.13.0 with IPP) evaluates the
+ * 5x5 chamfer transform as the two raster passes of Borgefors' algorithm in float32 with the metrics
+ * (1, 1.4, 2.1969) and FLT_MAX outside the image -- pinned by tests/golden/dist.npz (oracle/gen_golden_dist.py):
+ * bit for bit on every vector except the one with distances beyond 32 px, where on a thin band of pixels (float
+ * ties of `left neighbour + 1`) IPP's unpublished evaluation order ends one ulp above the two-pass minimum; the
+ * tests bound that to <= 1 ulp on < 1 % of the pixels.  (OpenCV's own non-IPP fallback works in 16.16 fixed point
+ * and differs from this build by ~1e-5 absolute; the pin decides.)
+ * --------------------------------------------------------------------------------------------- */
+void orc_distance_transform(const uint8_t *src, int w, int h, size_t step, float *dst)
+{
+    const float A = 1.0f, B = 1.4f, Cc = 2.1969f, INF = 3.402823466e+38f;
+    const int P = w + 4;
+    float *tmp = (float *)malloc((size_t)P * (h + 4) * sizeof(float));
+    for (size_t i = 0; i < (size_t)P * (h + 4); ++i) tmp[i] = INF;
+    float *T = tmp + 2 * P + 2;
+#define MINF(a, b) ((b) < (a) ? (b) : (a))
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            float *p = T + (size_t)y * P + x;
+            if (!src[(size_t)y * step + x]) { *p = 0.f; continue; }
+            float v = p[-2 * P - 1] + Cc, t;
+            t = p[-2 * P + 1] + Cc; v = MINF(v, t);
+            t = p[-P - 2] + Cc;     v = MINF(v, t);
+            t = p[-P - 1] + B;      v = MINF(v, t);
+            t = p[-P] + A;          v = MINF(v, t);
+            t = p[-P + 1] + B;      v = MINF(v, t);
+            t = p[-P + 2] + Cc;     v = MINF(v, t);
+            t = p[-1] + A;          v = MINF(v, t);
+            *p = v;
+        }
+    for (int y = h - 1; y >= 0; --y)
+        for (int x = w - 1; x >= 0; --x) {
+            float *p = T + (size_t)y * P + x;
+            float v = *p, t;
+            t = p[2 * P + 1] + Cc; v = MINF(v, t);
+            t = p[2 * P - 1] + Cc; v = MINF(v, t);
+            t = p[P + 2] + Cc;     v = MINF(v, t);
+            t = p[P + 1] + B;      v = MINF(v, t);
+            t = p[P] + A;          v = MINF(v, t);
+            t = p[P - 1] + B;      v = MINF(v, t);
+            t = p[P - 2] + Cc;     v = MINF(v, t);
+            t = p[1] + A;          v = MINF(v, t);
+            *p = v;
+            dst[(size_t)y * w + x] = v;
+        }
+#undef MINF
+    free(tmp);
+}
+
+/* dcut::dist_cut, src/math/_distance_cut.cpp:7-51: masks[i] contiguous w[i] x h[i]; cut[i] likewise.
+ * `transformed / 255` is a cv::MatExpr, i.e. a multiplication by (float)(1/255.). */
+void orc_dist_cut(int n, const uint8_t *const *masks, const int *tl_x, const int *tl_y, const int *w, const int *h,
+                  uint8_t *const *cut)
+{
+    const float s = (float)(1.0 / 255.0);
+    float **D = (float **)malloc((size_t)n * sizeof(float *));
+    for (int i = 0; i < n; ++i) {
+        D[i] = (float *)malloc((size_t)w[i] * h[i] * sizeof(float));
+        orc_distance_transform(masks[i], w[i], h[i], (size_t)w[i], D[i]);
+        for (size_t k = 0; k < (size_t)w[i] * h[i]; ++k) D[i][k] = D[i][k] * s;
+    }
+    for (int i = 0; i < n; ++i) {
+        memcpy(cut[i], masks[i], (size_t)w[i] * h[i]);
+        for (int j = 0; j < n; ++j) {
+            if (i == j) continue;
+            const int x0 = tl_x[i] > tl_x[j] ? tl_x[i] : tl_x[j], y0 = tl_y[i] > tl_y[j] ? tl_y[i] : tl_y[j];
+            const int xa = tl_x[i] + w[i], xb = tl_x[j] + w[j], ya = tl_y[i] + h[i], yb = tl_y[j] + h[j];
+            const int x1 = xa < xb ? xa : xb, y1 = ya < yb ? ya : yb;
+            if (x1 <= x0 || y1 <= y0) continue;
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x) {
+                    const float diff = D[i][(size_t)(y - tl_y[i]) * w[i] + (x - tl_x[i])] - D[j][(size_t)(y - tl_y[j]) * w[j] + (x - tl_x[j])];
+                    if (-diff > 0.f) cut[i][(size_t)(y - tl_y[i]) * w[i] + (x - tl_x[i])] = 0;   /* threshold(-diff,0,1) -> 1 - 1 = 0 */
+                }
+        }
+    }
+    for (int i = 0; i < n; ++i) free(D[i]);
+    free(D);
+}

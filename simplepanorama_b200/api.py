@@ -27,7 +27,7 @@ from ._lib import (CYLINDRICAL, OUT_F32, OUT_U8, SPHERICAL, STEREOGRAPHIC, Image
 __all__ = [
     "SPHERICAL", "CYLINDRICAL", "STEREOGRAPHIC", "Context", "ProjData", "SpanoError", "adjusted_camera", "warp_roi",
     "project", "get_proj_parameters", "create_surrounding_mask", "validity_mask", "apply_gain", "get_pan_dimension",
-    "multi_blend", "blend", "return_full", "default_context",
+    "multi_blend", "blend", "return_full", "default_context", "distance_transform", "dist_cut",
 ]
 
 
@@ -391,6 +391,33 @@ def resize_mask(mask, size_wh, ctx: Context | None = None) -> np.ndarray:
     ctx.check(ctx.lib.spano_resize_mask(ctx.h, m.ctypes.data, m.shape[1], m.shape[0], m.strides[0], out.ctypes.data, dw, dh,
                                         out.strides[0]))
     return out
+
+
+def distance_transform(mask, ctx: Context | None = None) -> np.ndarray:
+    """cv::distanceTransform(mask, dist, DIST_L2, DIST_MASK_5, CV_32F) on CV_8UC1 (5x5 chamfer, float32)."""
+    ctx = ctx or default_context()
+    m = _u8img(mask, 1, "mask")
+    out = np.empty(m.shape, np.float32)
+    ctx.check(ctx.lib.spano_distance_transform(ctx.h, m.ctypes.data, m.shape[1], m.shape[0], m.strides[0], out.ctypes.data,
+                                               out.strides[0]))
+    return out
+
+
+def dist_cut(masks, top_lefts, ctx: Context | None = None):
+    """dcut::dist_cut (src/math/_distance_cut.cpp:7-51): the seam masks that hand every overlap pixel to the image
+    whose validity mask is deepest there (ties stay with both)."""
+    ctx = ctx or default_context()
+    n = len(masks)
+    if n == 0 or n != len(top_lefts):
+        raise SpanoError(_lib.E_INVALID, "Input consistency!")
+    ms = [_u8img(a, 1, f"masks[{i}]") for i, a in enumerate(masks)]
+    outs = [np.empty(m.shape, np.uint8) for m in ms]
+    ptr = lambda arrs: (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    steps = lambda arrs: (C.c_size_t * n)(*[a.strides[0] for a in arrs])
+    tlx = np.array([c[0] for c in top_lefts], np.int32); tly = np.array([c[1] for c in top_lefts], np.int32)
+    w = np.array([m.shape[1] for m in ms], np.int32); h = np.array([m.shape[0] for m in ms], np.int32)
+    ctx.check(ctx.lib.spano_dist_cut(ctx.h, n, ptr(ms), steps(ms), _ip(tlx), _ip(tly), _ip(w), _ip(h), ptr(outs), steps(outs)))
+    return outs
 
 
 def adjust_intensity(img, field, ctx: Context | None = None) -> np.ndarray:

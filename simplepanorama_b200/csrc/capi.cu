@@ -1317,3 +1317,81 @@ extern "C" int spano_blend_finish(spano_ctx *ctx, uint8_t *canvas, size_t canvas
     Guard g(ctx);
     return blend_finish_impl(ctx, canvas, canvas_step, true);
 }
+
+// ---------------------------------------------------------------------------------------------
+// seam search by distance: cv::distanceTransform (5x5 chamfer) and dcut::dist_cut, host buffers
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// uploads n masks into one arena, runs the distance transforms; returns device pointers (masks, dists) and pitches
+int upload_and_transform(spano_ctx *ctx, int n, const uint8_t *const *masks, const size_t *mask_steps, const int *w, const int *h,
+                         std::vector<const uint8_t *> &d_masks, std::vector<size_t> &m_steps, std::vector<float *> &d_dist,
+                         std::vector<size_t> &d_steps, size_t extra_bytes, uint8_t **extra)
+{
+    size_t total = 0;
+    std::vector<size_t> off_m(n), off_d(n);
+    d_masks.resize(n); m_steps.resize(n); d_dist.resize(n); d_steps.resize(n);
+    for (int k = 0; k < n; ++k) {
+        if (int rc = check_image_args(ctx, masks[k], w[k], h[k], mask_steps[k], 1, "mask")) return rc;
+        m_steps[k] = align_up((size_t)w[k], 16);
+        d_steps[k] = align_up((size_t)w[k], 4);
+        off_m[k] = total;  total += align_up(m_steps[k] * h[k], 256);
+        off_d[k] = total;  total += align_up(d_steps[k] * h[k] * sizeof(float), 256);
+    }
+    const size_t off_extra = total;
+    total += extra_bytes;
+    uint8_t *arena = nullptr;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_DT_ARENA, total, (void **)&arena)) return rc;
+    for (int k = 0; k < n; ++k) {
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(arena + off_m[k], m_steps[k], masks[k], mask_steps[k], (size_t)w[k], h[k], cudaMemcpyHostToDevice, ctx->stream));
+        d_masks[k] = arena + off_m[k];
+        d_dist[k] = reinterpret_cast<float *>(arena + off_d[k]);
+    }
+    if (extra) *extra = arena + off_extra;
+    int rc = launch_distance_transform(ctx, n, d_masks.data(), m_steps.data(), w, h, d_dist.data(), d_steps.data());
+    return rc < 0 ? rc : 0;
+}
+
+} // namespace
+
+extern "C" int spano_distance_transform(spano_ctx *ctx, const uint8_t *mask, int w, int h, size_t step, float *dist, size_t dist_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (!dist || dist_step < (size_t)std::max(w, 0) * sizeof(float)) return spano_fail(ctx, SPANO_E_INVALID, "spano_distance_transform: null output or step too small");
+    std::vector<const uint8_t *> dm; std::vector<size_t> ms, ds; std::vector<float *> dd;
+    if (int rc = upload_and_transform(ctx, 1, &mask, &step, &w, &h, dm, ms, dd, ds, 0, nullptr)) return rc;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(dist, dist_step, dd[0], ds[0] * sizeof(float), (size_t)w * sizeof(float), h, cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}
+
+extern "C" int spano_dist_cut(spano_ctx *ctx, int n, const uint8_t *const *masks, const size_t *mask_steps, const int *tl_x,
+                              const int *tl_y, const int *w, const int *h, uint8_t *const *cut, const size_t *cut_steps)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (n <= 0 || !masks || !mask_steps || !tl_x || !tl_y || !w || !h || !cut || !cut_steps)
+        return spano_fail(ctx, SPANO_E_INVALID, "spano_dist_cut: null/empty argument");
+    size_t cut_bytes = 0;
+    std::vector<size_t> off_c(n), c_steps(n);
+    for (int k = 0; k < n; ++k) {
+        if (w[k] <= 0 || h[k] <= 0) return spano_fail(ctx, SPANO_E_INVALID, "spano_dist_cut: empty mask %d", k);
+        if (!cut[k] || cut_steps[k] < (size_t)w[k]) return spano_fail(ctx, SPANO_E_INVALID, "spano_dist_cut: output %d null or step too small", k);
+        c_steps[k] = align_up((size_t)w[k], 16);
+        off_c[k] = cut_bytes;
+        cut_bytes += align_up(c_steps[k] * h[k], 256);
+    }
+    std::vector<const uint8_t *> dm; std::vector<size_t> ms, ds; std::vector<float *> dd;
+    uint8_t *d_cut_arena = nullptr;
+    if (int rc = upload_and_transform(ctx, n, masks, mask_steps, w, h, dm, ms, dd, ds, cut_bytes, &d_cut_arena)) return rc;
+    std::vector<uint8_t *> d_cut(n);
+    for (int k = 0; k < n; ++k) d_cut[k] = d_cut_arena + off_c[k];
+    std::vector<const float *> cd(dd.begin(), dd.end());
+    int rc = launch_dist_cut(ctx, n, dm.data(), ms.data(), cd.data(), ds.data(), tl_x, tl_y, w, h, d_cut.data(), c_steps.data());
+    if (rc < 0) return rc;
+    for (int k = 0; k < n; ++k)
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(cut[k], cut_steps[k], d_cut[k], c_steps[k], (size_t)w[k], h[k], cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}

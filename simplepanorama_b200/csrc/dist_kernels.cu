@@ -1,0 +1,179 @@
+// dist_kernels.cu -- chamfer distance transform and the distance-based seam cut (sm_100a).
+//
+// Replaces, at preview scale,
+//   cv::distanceTransform(mask, dist, cv::DIST_L2, cv::DIST_MASK_5, CV_32F)   (reference src/math/_distance_cut.cpp:63,
+//                                                                              src/math/_blending.cpp:110)
+//   dcut::distance_transform + dcut::dist_cut                                 (src/math/_distance_cut.cpp:7-73)
+//
+// Arithmetic contract.  The OpenCV build the reference is pinned to here (cv2 4.13 + IPP) evaluates the 5x5 chamfer
+// transform as the classic two raster passes in FLOAT32 with the metrics a = 1, b = 1.4, c = 2.1969:
+//   forward  (top-left -> bottom-right)  t = min over {(-2,-1),(-2,+1),(-1,-2),(-1,+2)} + c, {(-1,-1),(-1,+1)} + b,
+//                                                     {(-1,0),(0,-1)} + a;   t = 0 where the mask is 0
+//   backward (bottom-right -> top-left)  the mirrored mask, applied to the forward result
+// with FLT_MAX outside the image (FLT_MAX + metric == FLT_MAX).  Float addition does not associate, so the value of
+// a pixel is the rounding history of one particular shortest path and a relaxation to a fixed point could differ in
+// the last bit: the kernel therefore reproduces the DATA FLOW of the two passes exactly and only reorders
+// independent pixels -- pixel (y, x) of the forward pass depends on (y, x-1), (y-1, x-2..x+2) and (y-2, x+-1), all of
+// which lie on earlier anti-diagonals  x + 3 y = const, so a wavefront over t = x + 3 y runs every pixel of a
+// diagonal in parallel (one CTA per image, one barrier per diagonal).  Bit-exact against cv2 (tests/golden/dist.npz).
+#include "spano_internal.h"
+#include <cfloat>
+
+namespace {
+
+constexpr float CH_A = 1.0f, CH_B = 1.4f, CH_C = 2.1969f;
+
+struct DtJob {
+    const uint8_t *src;
+    size_t sstep;
+    int w, h;
+    float *tmp;   // (h + 4) x (w + 4) floats, 2-pixel frame
+    float *dst;
+    size_t dstep; // floats
+};
+
+__global__ void __launch_bounds__(1024) chamfer_dt_kernel(const DtJob *jobs)
+{
+    const DtJob J = jobs[blockIdx.x];
+    const int w = J.w, h = J.h, P = w + 4;
+    float *T = J.tmp + 2 * P + 2;   // T[y * P + x], valid for y, x in [-2, h + 1] x [-2, w + 1]
+    // frame
+    for (int i = threadIdx.x; i < (h + 4) * P; i += blockDim.x) {
+        const int y = i / P - 2, x = i % P - 2;
+        if (y < 0 || y >= h || x < 0 || x >= w) J.tmp[i] = FLT_MAX;
+    }
+    __syncthreads();
+    const int steps = (w - 1) + 3 * (h - 1);
+    // forward pass
+    for (int t = 0; t <= steps; ++t) {
+        const int y_lo = max(0, (t - (w - 1) + 2) / 3), y_hi = min(h - 1, t / 3);
+        for (int y = y_lo + threadIdx.x; y <= y_hi; y += blockDim.x) {
+            const int x = t - 3 * y;
+            float v = 0.f;
+            if (J.src[(size_t)y * J.sstep + x]) {
+                const float *p = T + y * P + x;
+                v = __fadd_rn(p[-2 * P - 1], CH_C);
+                v = fminf(v, __fadd_rn(p[-2 * P + 1], CH_C));
+                v = fminf(v, __fadd_rn(p[-P - 2], CH_C));
+                v = fminf(v, __fadd_rn(p[-P - 1], CH_B));
+                v = fminf(v, __fadd_rn(p[-P], CH_A));
+                v = fminf(v, __fadd_rn(p[-P + 1], CH_B));
+                v = fminf(v, __fadd_rn(p[-P + 2], CH_C));
+                v = fminf(v, __fadd_rn(p[-1], CH_A));
+            }
+            T[y * P + x] = v;
+        }
+        __syncthreads();
+    }
+    // backward pass: the same wavefront on the point-mirrored image
+    for (int t = 0; t <= steps; ++t) {
+        const int y_lo = max(0, (t - (w - 1) + 2) / 3), y_hi = min(h - 1, t / 3);
+        for (int ym = y_lo + threadIdx.x; ym <= y_hi; ym += blockDim.x) {
+            const int y = h - 1 - ym, x = w - 1 - (t - 3 * ym);
+            float *p = T + y * P + x;
+            float v = *p;
+            v = fminf(v, __fadd_rn(p[2 * P + 1], CH_C));
+            v = fminf(v, __fadd_rn(p[2 * P - 1], CH_C));
+            v = fminf(v, __fadd_rn(p[P + 2], CH_C));
+            v = fminf(v, __fadd_rn(p[P + 1], CH_B));
+            v = fminf(v, __fadd_rn(p[P], CH_A));
+            v = fminf(v, __fadd_rn(p[P - 1], CH_B));
+            v = fminf(v, __fadd_rn(p[P - 2], CH_C));
+            v = fminf(v, __fadd_rn(p[1], CH_A));
+            *p = v;
+            J.dst[(size_t)y * J.dstep + x] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// dcut::dist_cut for one image i: a pixel keeps its mask value unless some overlapping image j has a strictly larger
+// (scaled) distance there.  `others` lists the overlapping images.
+struct CutOther {
+    const float *dist;   // DT of image j (unscaled)
+    size_t dstep;        // floats
+    int dx, dy;          // pixel (x, y) of image i is pixel (x + dx, y + dy) of image j
+    int w, h;
+};
+
+__global__ void dist_cut_kernel(const uint8_t *mask, size_t mstep, const float *dist, size_t dstep, int w, int h,
+                                const CutOther *others, int n_others, uint8_t *cut, size_t cstep)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const float s = (float)(1.0 / 255.0);   // `transformed / 255` is a MatExpr: multiplication by (float)(1/255.)
+    const float di = __fmul_rn(dist[(size_t)y * dstep + x], s);
+    uint8_t v = mask[(size_t)y * mstep + x];
+    for (int k = 0; k < n_others; ++k) {
+        const CutOther o = others[k];
+        const int xj = x + o.dx, yj = y + o.dy;
+        if (xj < 0 || yj < 0 || xj >= o.w || yj >= o.h) continue;
+        const float dj = __fmul_rn(o.dist[(size_t)yj * o.dstep + xj], s);
+        if (di < dj) v = 0;                 // threshold(-(Di - Dj), 0, 1, BINARY) == 1  <=>  Di < Dj
+    }
+    cut[(size_t)y * cstep + x] = v;
+}
+
+} // namespace
+
+// n images on the device: masks[k] (w[k] x h[k], step mstep[k]) -> dist[k] (float, pitch dstep[k] floats)
+int launch_distance_transform(spano_ctx *ctx, int n, const uint8_t *const *masks, const size_t *msteps, const int *w, const int *h,
+                              float *const *dist, const size_t *dsteps)
+{
+    if (n <= 0) return 0;
+    size_t tmp_floats = 0;
+    for (int k = 0; k < n; ++k) {
+        if (w[k] <= 0 || h[k] <= 0) return spano_fail(ctx, SPANO_E_INVALID, "distance transform: empty image");
+        tmp_floats += (size_t)(w[k] + 4) * (h[k] + 4);
+    }
+    float *tmp = nullptr;
+    DtJob *d_jobs = nullptr;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_DT_TMP, tmp_floats * sizeof(float), (void **)&tmp)) return rc;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_DT_JOBS, (size_t)n * sizeof(DtJob), (void **)&d_jobs)) return rc;
+    std::vector<DtJob> jobs(n);
+    size_t off = 0;
+    for (int k = 0; k < n; ++k) {
+        jobs[k] = DtJob{masks[k], msteps[k], w[k], h[k], tmp + off, dist[k], dsteps[k]};
+        off += (size_t)(w[k] + 4) * (h[k] + 4);
+    }
+    SPANO_CUDA(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), (size_t)n * sizeof(DtJob), cudaMemcpyHostToDevice, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `jobs` is a local
+    chamfer_dt_kernel<<<n, 1024, 0, ctx->stream>>>(d_jobs);
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return 1;
+}
+
+int launch_dist_cut(spano_ctx *ctx, int n, const uint8_t *const *masks, const size_t *msteps, const float *const *dist,
+                    const size_t *dsteps, const int *tl_x, const int *tl_y, const int *w, const int *h, uint8_t *const *cut,
+                    const size_t *csteps)
+{
+    if (n <= 0) return 0;
+    std::vector<CutOther> table;
+    std::vector<int> first(n + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) {
+            if (i == j) continue;
+            const int x0 = std::max(tl_x[i], tl_x[j]), y0 = std::max(tl_y[i], tl_y[j]);
+            const int x1 = std::min(tl_x[i] + w[i], tl_x[j] + w[j]), y1 = std::min(tl_y[i] + h[i], tl_y[j] + h[j]);
+            if (x1 <= x0 || y1 <= y0) continue;   // cv::Rect & cv::Rect is empty
+            table.push_back(CutOther{dist[j], dsteps[j], tl_x[i] - tl_x[j], tl_y[i] - tl_y[j], w[j], h[j]});
+        }
+        first[i + 1] = (int)table.size();
+    }
+    CutOther *d_table = nullptr;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_DT_JOBS2, std::max<size_t>(1, table.size()) * sizeof(CutOther), (void **)&d_table)) return rc;
+    if (!table.empty()) {
+        SPANO_CUDA(ctx, cudaMemcpyAsync(d_table, table.data(), table.size() * sizeof(CutOther), cudaMemcpyHostToDevice, ctx->stream));
+        SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    for (int i = 0; i < n; ++i) {
+        dim3 block(256), grid((w[i] + 255) / 256, h[i]);
+        dist_cut_kernel<<<grid, block, 0, ctx->stream>>>(masks[i], msteps[i], dist[i], dsteps[i], w[i], h[i], d_table + first[i],
+                                                         first[i + 1] - first[i], cut[i], csteps[i]);
+    }
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += n;
+    return n;
+}

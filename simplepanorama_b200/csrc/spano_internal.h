@@ -46,7 +46,7 @@ struct spano_ctx {
     long long launches = 0;
     // grow-only scratch buffers, indexed by role
     enum { BUF_LABELS = 0, BUF_DARK, BUF_MASK0, BUF_TABLES, BUF_ACC, BUF_TILE, BUF_TILEMASK, BUF_CUTMASK, BUF_SRC,
-           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_BLENDPLAN, BUF_BLENDPLAN2, BUF_COUNT };
+           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_BLENDPLAN, BUF_BLENDPLAN2, BUF_DT_TMP, BUF_DT_JOBS, BUF_DT_JOBS2, BUF_DT_ARENA, BUF_COUNT };
     DeviceBuffer buf[BUF_COUNT];
     std::vector<void *> owned; // extra allocations freed at destroy / end of call
     unsigned long long *blend_stats = nullptr; // device: [0] tile pixels the blend processed, [1] tile pixels offered
@@ -137,6 +137,12 @@ int launch_resize_mask(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_
                        size_t dstep, int row_begin = 0, int row_end = -1);
 int launch_adjust_intensity(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, const float *field, int fw, int fh,
                             size_t fpitch_elems);
+// dist_kernels.cu: 5x5 chamfer distance transform (cv::distanceTransform DIST_L2 / DIST_MASK_5) and dcut::dist_cut
+int launch_distance_transform(spano_ctx *ctx, int n, const uint8_t *const *masks, const size_t *msteps, const int *w, const int *h,
+                              float *const *dist, const size_t *dsteps);
+int launch_dist_cut(spano_ctx *ctx, int n, const uint8_t *const *masks, const size_t *msteps, const float *const *dist,
+                    const size_t *dsteps, const int *tl_x, const int *tl_y, const int *w, const int *h, uint8_t *const *cut,
+                    const size_t *csteps);
 // disk_kernels.cu: stereographic centre fix (util::RadialNormalizer state + normalised radius)
 struct SpanoDiskParams {
     float cx, cy, scale;

@@ -132,9 +132,14 @@ def seam_masks(corners, sizes, soft: int = 8, only: int | None = None, coarse: b
         for i in range(n):
             if i == j or x1[i] <= x0[j] or x0[i] >= x1[j] or y1[i] <= y0[j] or y0[i] >= y1[j]:
                 continue
-            inside = (GX >= x0[i]) & (GX < x1[i]) & (GY >= y0[i]) & (GY < y1[i])
-            di = (GX - cx[i]) ** 2 + (GY - cy[i]) ** 2
-            keep &= ~(inside & ((di < dj) | ((di == dj) & (i < j))))
+            # only the grid cells inside tile i's rectangle can change (same comparisons, evaluated on that window)
+            kx = np.nonzero((gx >= x0[i]) & (gx < x1[i]))[0]
+            ky = np.nonzero((gy >= y0[i]) & (gy < y1[i]))[0]
+            if kx.size == 0 or ky.size == 0:
+                continue
+            sl = (slice(ky[0], ky[-1] + 1), slice(kx[0], kx[-1] + 1))
+            di = (GX[sl] - cx[i]) ** 2 + (GY[sl] - cy[i]) ** 2
+            keep[sl] &= ~((di < dj[sl]) | ((di == dj[sl]) & (i < j)))
         if coarse:   # the preview-scale binary mask itself (what dist_cut / graph_cut hand to return_full)
             out.append(np.ascontiguousarray(keep.astype(np.uint8) * 255))
         else:
