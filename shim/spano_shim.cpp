@@ -171,3 +171,37 @@ void adjust_intensity(std::vector<cv::Mat> &images, const std::vector<cv::Mat> &
 }
 
 } // namespace test
+
+namespace dcut {
+
+// src/math/_distance_cut.cpp:57-73
+std::vector<cv::Mat> distance_transform(const std::vector<cv::Mat> &masks)
+{
+    std::vector<cv::Mat> ret;
+    for (const cv::Mat &m : masks) {
+        cv::Mat d(m.rows, m.cols, CV_32FC1);
+        check(spano_distance_transform(ctx(), m.data, m.cols, m.rows, m.step, d.ptr<float>(), d.step));
+        ret.push_back(d / 255);
+    }
+    return ret;
+}
+
+// src/math/_distance_cut.cpp:7-51 (called from stitch_parameters::set_config when conf.cut is on)
+std::vector<cv::Mat> dist_cut(const std::vector<cv::Mat> &masks, const std::vector<cv::Point> &top_lefts)
+{
+    const int n = (int)masks.size();
+    std::vector<const uint8_t *> m(n);
+    std::vector<uint8_t *> o(n);
+    std::vector<size_t> ms(n), os(n);
+    std::vector<int> x(n), y(n), w(n), h(n);
+    std::vector<cv::Mat> cut(n);
+    for (int i = 0; i < n; ++i) {
+        cut[i].create(masks[i].rows, masks[i].cols, masks[i].type());
+        m[i] = masks[i].data; ms[i] = masks[i].step; o[i] = cut[i].data; os[i] = cut[i].step;
+        x[i] = top_lefts[i].x; y[i] = top_lefts[i].y; w[i] = masks[i].cols; h[i] = masks[i].rows;
+    }
+    check(spano_dist_cut(ctx(), n, m.data(), ms.data(), x.data(), y.data(), w.data(), h.data(), o.data(), os.data()));
+    return cut;
+}
+
+} // namespace dcut
