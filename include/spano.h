@@ -134,6 +134,19 @@ int spano_distance_transform(spano_ctx *ctx, const uint8_t *mask, int w, int h, 
 int spano_dist_cut(spano_ctx *ctx, int n, const uint8_t *const *masks, const size_t *mask_steps, const int *tl_x,
                    const int *tl_y, const int *w, const int *h, uint8_t *const *cut, const size_t *cut_steps);
 
+/* ---- the other two branches of stitch_parameters::blend (src/classes/_panorama.cpp:220-240) ---------------
+ * spano_simple_blend = blnd::simple_blend(images, masks, top_lefts) (src/math/_blending.cpp:83-153): feathering with
+ * alpha = normalize(distanceTransform(mask)), images over-composited in order, -> CV_8UC3 canvas.
+ * spano_no_blend = blnd::no_blend (src/math/_blending.cpp:157-182): masked copy in order -> CV_8UC3 canvas.
+ * tiles 8UC3, masks 8UC1 (validity masks, or mask_cut for no_blend when conf.cut); out = canvas_w x canvas_h from
+ * spano_pan_dimension.  HOST buffers.                                                                      */
+int spano_simple_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps, const uint8_t *const *masks,
+                       const size_t *mask_steps, const int *tl_x, const int *tl_y, const int *w, const int *h, uint8_t *out,
+                       size_t out_step);
+int spano_no_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps, const uint8_t *const *masks,
+                   const size_t *mask_steps, const int *tl_x, const int *tl_y, const int *w, const int *h, uint8_t *out,
+                   size_t out_step);
+
 /* a6 alone: `img / gain` on CV_8UC3, in place. */
 int spano_apply_gain(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, double gain);
 

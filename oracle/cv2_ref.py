@@ -217,3 +217,39 @@ def return_full(images, R, K, kind, focal, gains, masks_cut_fullres, bands, sigm
         timers["warp_s"] = t1 - t0
         timers["blend_s"] = t2 - t1
     return out, pd
+
+
+def simple_blend(images, masks, top_lefts) -> np.ndarray:
+    """blnd::simple_blend (src/math/_blending.cpp:83-153) through the same OpenCV entry points
+    (distanceTransform, normalize(NORM_MINMAX), convertTo, mul, subtract) -> CV_8UC3 canvas."""
+    W, H, min_x, min_y = get_pan_dimension(top_lefts, images)
+    acc_c = np.zeros((H, W, 3), np.float32)
+    acc_a = np.zeros((H, W), np.float32)
+    for img, mask, tl in zip(images, masks, top_lefts):
+        x0, y0 = tl[0] - min_x, tl[1] - min_y
+        h, w = img.shape[:2]
+        dt = cv2.distanceTransform(np.ascontiguousarray(mask), cv2.DIST_L2, cv2.DIST_MASK_5)
+        mask_float = cv2.normalize(dt, None, 0.0, 1.0, cv2.NORM_MINMAX)
+        img_float = img.astype(np.float32) * np.float32(1.0 / 255.0)          # convertTo(CV_32F, 1/255.)
+        one_minus = cv2.subtract(np.float64(1.0), acc_a[y0:y0 + h, x0:x0 + w]).astype(np.float32)
+        new_color = img_float * mask_float[..., None]
+        acc_c[y0:y0 + h, x0:x0 + w] += new_color * one_minus[..., None]
+        acc_a[y0:y0 + h, x0:x0 + w] += mask_float * one_minus
+    res = np.zeros((H, W, 3), np.float32)
+    pos = acc_a > 0
+    inv = np.zeros_like(acc_a)
+    inv[pos] = np.float32(1.0) / acc_a[pos]                                   # Vec3f / float == * (1.f / a)
+    res[pos] = acc_c[pos] * inv[pos][..., None]
+    return np.clip(np.rint(res * np.float32(255.0)), 0, 255).astype(np.uint8)  # convertTo(CV_8UC3, 255.0)
+
+
+def no_blend(images, masks, top_lefts) -> np.ndarray:
+    """blnd::no_blend (src/math/_blending.cpp:157-182): images[i].copyTo(panorama(roi), masks[i]) in order."""
+    W, H, min_x, min_y = get_pan_dimension(top_lefts, images)
+    pano = np.zeros((H, W, 3), np.uint8)
+    for img, mask, tl in zip(images, masks, top_lefts):
+        x0, y0 = tl[0] - min_x, tl[1] - min_y
+        h, w = img.shape[:2]
+        roi = pano[y0:y0 + h, x0:x0 + w]
+        cv2.copyTo(img, mask, roi)
+    return pano

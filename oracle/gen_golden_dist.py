@@ -56,6 +56,15 @@ def main():
     for i, (m, c) in enumerate(zip(ms, cuts)):
         out[f"cut_mask_{i}"] = m
         out[f"cut_ref_{i}"] = c
+    # simple_blend / no_blend (the other two branches of stitch_parameters::blend) on the same geometry
+    tiles = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for (w, h) in sizes]
+    bmasks = list(ms)
+    bmasks[2] = np.full_like(ms[2], 255)                # a mask without any zero pixel: distance FLT_MAX, alpha 0
+    for i, (t, m) in enumerate(zip(tiles, bmasks)):
+        out[f"blend_tile_{i}"] = t
+        out[f"blend_mask_{i}"] = m
+    out["simple_ref"] = cv2_ref.simple_blend(tiles, bmasks, corners)
+    out["noblend_ref"] = cv2_ref.no_blend(tiles, bmasks, corners)
     path = os.path.join(ROOT, "tests", "golden", "dist.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes, cv2", cv2.__version__)

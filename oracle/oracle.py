@@ -234,3 +234,27 @@ def dist_cut(masks, corners):
     w = np.array([m.shape[1] for m in ms], np.int32); h = np.array([m.shape[0] for m in ms], np.int32)
     lib().orc_dist_cut(n, arr(ms), _p(tlx, C.c_int), _p(tly, C.c_int), _p(w, C.c_int), _p(h, C.c_int), arr(outs))
     return outs
+
+
+def _simple_or_no_blend(fn, tiles, masks, corners):
+    n = len(tiles)
+    ts = [np.ascontiguousarray(t, np.uint8) for t in tiles]
+    ms = [np.ascontiguousarray(m, np.uint8) for m in masks]
+    sizes = [(t.shape[1], t.shape[0]) for t in ts]
+    W, H, _, _ = pan_dimension(corners, sizes)
+    out = np.empty((H, W, 3), np.uint8)
+    arr = lambda xs: (C.c_void_p * n)(*[x.ctypes.data for x in xs])
+    tlx = np.array([c[0] for c in corners], np.int32); tly = np.array([c[1] for c in corners], np.int32)
+    w = np.array([s[0] for s in sizes], np.int32); h = np.array([s[1] for s in sizes], np.int32)
+    fn(n, arr(ts), arr(ms), _p(tlx, C.c_int), _p(tly, C.c_int), _p(w, C.c_int), _p(h, C.c_int), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def simple_blend(tiles, masks, corners):
+    """blnd::simple_blend -> CV_8UC3 canvas."""
+    return _simple_or_no_blend(lib().orc_simple_blend, tiles, masks, corners)
+
+
+def no_blend(tiles, masks, corners):
+    """blnd::no_blend -> CV_8UC3 canvas."""
+    return _simple_or_no_blend(lib().orc_no_blend, tiles, masks, corners)

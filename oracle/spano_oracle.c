@@ -823,3 +823,74 @@ void orc_dist_cut(int n, const uint8_t *const *masks, const int *tl_x, const int
     for (int i = 0; i < n; ++i) free(D[i]);
     free(D);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * blnd::simple_blend (src/math/_blending.cpp:83-153) and blnd::no_blend (:157-182): the SIMPLE_BLEND and NO_BLEND
+ * branches of stitch_parameters::blend (src/classes/_panorama.cpp:220-240).
+ * simple_blend: per image, in order: alpha = normalize(distanceTransform(mask), 0, 1, NORM_MINMAX);
+ *   color += (img/255 * alpha) * (1 - acc_alpha);  acc_alpha += alpha * (1 - acc_alpha);
+ *   result = acc_alpha > 0 ? color * (1.f / acc_alpha) : 0;  convertTo(CV_8UC3, 255).
+ * cv::normalize(NORM_MINMAX): scale = 1/(max - min) in double (0 when max - min <= DBL_EPSILON), shift = -min*scale,
+ * then convertTo(float(scale), float(shift)).  Tiles/masks contiguous; out = canvas_w x canvas_h x 3 bytes.
+ * --------------------------------------------------------------------------------------------- */
+void orc_simple_blend(int n, const uint8_t *const *tiles, const uint8_t *const *masks, const int *tl_x, const int *tl_y,
+                      const int *w, const int *h, uint8_t *out)
+{
+    int dim[6];
+    orc_pan_dimension(n, tl_x, tl_y, w, h, dim);
+    const int W = dim[0], H = dim[1], mx = dim[2], my = dim[3];
+    float *col = (float *)calloc((size_t)W * H * 3, sizeof(float));
+    float *alp = (float *)calloc((size_t)W * H, sizeof(float));
+    for (int i = 0; i < n; ++i) {
+        const size_t np = (size_t)w[i] * h[i];
+        float *dt = (float *)malloc(np * sizeof(float));
+        orc_distance_transform(masks[i], w[i], h[i], (size_t)w[i], dt);
+        float smin = dt[0], smax = dt[0];
+        for (size_t k = 1; k < np; ++k) { if (dt[k] < smin) smin = dt[k]; if (dt[k] > smax) smax = dt[k]; }
+        const double range = (double)smax - (double)smin;
+        const double scale = range > DBL_EPSILON ? 1.0 / range : 0.0;
+        const float a = (float)scale, b = (float)(0.0 - (double)smin * scale);
+        const float inv255 = (float)(1.0 / 255.0);
+        for (int y = 0; y < h[i]; ++y)
+            for (int x = 0; x < w[i]; ++x) {
+                const size_t k = (size_t)y * w[i] + x;
+                const size_t c = (size_t)(y + tl_y[i] - my) * W + (x + tl_x[i] - mx);
+                const float m = dt[k] * a + b;
+                const float om = 1.0f - alp[c];
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float v = (float)tiles[i][k * 3 + ch] * inv255;
+                    col[c * 3 + ch] += (v * m) * om;
+                }
+                alp[c] += m * om;
+            }
+        free(dt);
+    }
+    for (size_t c = 0; c < (size_t)W * H; ++c) {
+        const float a = alp[c];
+        for (int ch = 0; ch < 3; ++ch) {
+            float v = 0.f;
+            if (a > 0) v = col[c * 3 + ch] * (1.f / a);
+            double r = nearbyint((double)(v * 255.0f));
+            out[c * 3 + ch] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+        }
+    }
+    free(col);
+    free(alp);
+}
+
+void orc_no_blend(int n, const uint8_t *const *tiles, const uint8_t *const *masks, const int *tl_x, const int *tl_y,
+                  const int *w, const int *h, uint8_t *out)
+{
+    int dim[6];
+    orc_pan_dimension(n, tl_x, tl_y, w, h, dim);
+    const int W = dim[0], H = dim[1], mx = dim[2], my = dim[3];
+    memset(out, 0, (size_t)W * H * 3);
+    for (int i = 0; i < n; ++i)
+        for (int y = 0; y < h[i]; ++y)
+            for (int x = 0; x < w[i]; ++x) {
+                const size_t k = (size_t)y * w[i] + x;
+                if (!masks[i][k]) continue;   /* Mat::copyTo(dst, mask): where mask != 0 */
+                const size_t c = (size_t)(y + tl_y[i] - my) * W + (x + tl_x[i] - mx);
+                out[c * 3] = tiles[i][k * 3]; out[c * 3 + 1] = tiles[i][k * 3 + 1]; out[c * 3 + 2] = tiles[i][k * 3 + 2];
+            }
+}

@@ -156,6 +156,39 @@ cv::Mat multi_blend(const std::vector<cv::Mat> &images, const std::vector<cv::Ma
     return out;
 }
 
+static cv::Mat simple_or_no(bool simple, const std::vector<cv::Mat> &images, const std::vector<cv::Mat> &masks,
+                            const std::vector<cv::Point> &top_lefts)
+{
+    if (images.empty() || images.size() != masks.size() || images.size() != top_lefts.size())
+        throw std::runtime_error("Input consistency!");
+    const int n = (int)images.size();
+    std::vector<const uint8_t *> t(n), m(n);
+    std::vector<size_t> ts(n), ms(n);
+    std::vector<int> x(n), y(n), w(n), h(n);
+    for (int i = 0; i < n; ++i) {
+        t[i] = images[i].data; ts[i] = images[i].step; m[i] = masks[i].data; ms[i] = masks[i].step;
+        x[i] = top_lefts[i].x; y[i] = top_lefts[i].y; w[i] = images[i].cols; h[i] = images[i].rows;
+    }
+    int cw, ch, mx, my;
+    check(spano_pan_dimension(n, x.data(), y.data(), w.data(), h.data(), &cw, &ch, &mx, &my));
+    cv::Mat out(ch, cw, CV_8UC3);
+    check((simple ? spano_simple_blend : spano_no_blend)(ctx(), n, t.data(), ts.data(), m.data(), ms.data(), x.data(), y.data(),
+                                                         w.data(), h.data(), out.data, out.step));
+    return out;
+}
+
+// src/math/_blending.cpp:83-153 (stitch_parameters::blend, SIMPLE_BLEND)
+cv::Mat simple_blend(const std::vector<cv::Mat> &images, const std::vector<cv::Mat> &masks, const std::vector<cv::Point> &top_lefts)
+{
+    return simple_or_no(true, images, masks, top_lefts);
+}
+
+// src/math/_blending.cpp:157-182 (stitch_parameters::blend, NO_BLEND)
+cv::Mat no_blend(const std::vector<cv::Mat> &images, const std::vector<cv::Mat> &masks, const std::vector<cv::Point> &top_lefts)
+{
+    return simple_or_no(false, images, masks, top_lefts);
+}
+
 } // namespace blnd
 
 namespace test {

@@ -59,6 +59,8 @@ SYMBOLS = {
     "spano_adjust_intensity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
     "spano_distance_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
     "spano_dist_cut": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_intp, c_intp, c_intp, c_intp, c_u8pp, c_sizep]),
+    "spano_simple_blend": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_u8pp, c_sizep, c_intp, c_intp, c_intp, c_intp, C.c_void_p, C.c_size_t]),
+    "spano_no_blend": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_u8pp, c_sizep, c_intp, c_intp, c_intp, c_intp, C.c_void_p, C.c_size_t]),
     "spano_apply_gain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double]),
     "spano_disk_reproj_size": (C.c_int, [C.c_void_p, C.c_int, c_intp, c_intp, c_intp, c_intp, C.c_int, C.c_int, C.c_float,
                                          C.c_int, c_intp, c_intp, c_intp, c_intp]),

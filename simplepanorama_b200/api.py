@@ -27,7 +27,7 @@ from ._lib import (CYLINDRICAL, OUT_F32, OUT_U8, SPHERICAL, STEREOGRAPHIC, Image
 __all__ = [
     "SPHERICAL", "CYLINDRICAL", "STEREOGRAPHIC", "Context", "ProjData", "SpanoError", "adjusted_camera", "warp_roi",
     "project", "get_proj_parameters", "create_surrounding_mask", "validity_mask", "apply_gain", "get_pan_dimension",
-    "multi_blend", "blend", "return_full", "default_context", "distance_transform", "dist_cut",
+    "multi_blend", "blend", "return_full", "default_context", "distance_transform", "dist_cut", "simple_blend", "no_blend",
 ]
 
 
@@ -391,6 +391,37 @@ def resize_mask(mask, size_wh, ctx: Context | None = None) -> np.ndarray:
     ctx.check(ctx.lib.spano_resize_mask(ctx.h, m.ctypes.data, m.shape[1], m.shape[0], m.strides[0], out.ctypes.data, dw, dh,
                                         out.strides[0]))
     return out
+
+
+def _simple_or_no_blend(name, images, masks, top_lefts, ctx):
+    ctx = ctx or default_context()
+    n = len(images)
+    if n == 0 or n != len(masks) or n != len(top_lefts):
+        raise SpanoError(_lib.E_INVALID, "Input consistency!")
+    imgs = [_u8img(a, 3, f"images[{i}]") for i, a in enumerate(images)]
+    ms = [_u8img(a, 1, f"masks[{i}]") for i, a in enumerate(masks)]
+    for i in range(n):
+        if ms[i].shape != imgs[i].shape[:2]:
+            raise SpanoError(_lib.E_INVALID, f"mask {i} does not match its tile size")
+    W, H, _, _ = get_pan_dimension(top_lefts, imgs)
+    ptr = lambda arrs: (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    steps = lambda arrs: (C.c_size_t * n)(*[a.strides[0] for a in arrs])
+    tlx = np.array([c[0] for c in top_lefts], np.int32); tly = np.array([c[1] for c in top_lefts], np.int32)
+    w = np.array([im.shape[1] for im in imgs], np.int32); h = np.array([im.shape[0] for im in imgs], np.int32)
+    out = np.empty((H, W, 3), np.uint8)
+    fn = getattr(ctx.lib, name)
+    ctx.check(fn(ctx.h, n, ptr(imgs), steps(imgs), ptr(ms), steps(ms), _ip(tlx), _ip(tly), _ip(w), _ip(h), out.ctypes.data, out.strides[0]))
+    return out
+
+
+def simple_blend(images, masks, top_lefts, ctx: Context | None = None) -> np.ndarray:
+    """blnd::simple_blend (stitch_parameters::blend, SIMPLE_BLEND) -> CV_8UC3 canvas."""
+    return _simple_or_no_blend("spano_simple_blend", images, masks, top_lefts, ctx)
+
+
+def no_blend(images, masks, top_lefts, ctx: Context | None = None) -> np.ndarray:
+    """blnd::no_blend (stitch_parameters::blend, NO_BLEND) -> CV_8UC3 canvas."""
+    return _simple_or_no_blend("spano_no_blend", images, masks, top_lefts, ctx)
 
 
 def distance_transform(mask, ctx: Context | None = None) -> np.ndarray:

@@ -1395,3 +1395,96 @@ extern "C" int spano_dist_cut(spano_ctx *ctx, int n, const uint8_t *const *masks
     SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SPANO_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// blnd::simple_blend / blnd::no_blend, host buffers
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+int simple_or_no_blend(spano_ctx *ctx, bool simple, int n, const uint8_t *const *tiles, const size_t *tile_steps, const uint8_t *const *masks,
+                       const size_t *mask_steps, const int *tl_x, const int *tl_y, const int *w, const int *h, uint8_t *out, size_t out_step)
+{
+    if (n <= 0 || !tiles || !tile_steps || !masks || !mask_steps || !tl_x || !tl_y || !w || !h || !out)
+        return spano_fail(ctx, SPANO_E_INVALID, "Input consistency!");
+    int cw, chh, mx, my;
+    spano_pan_dimension(n, tl_x, tl_y, w, h, &cw, &chh, &mx, &my);
+    if (out_step < (size_t)cw * 3) return spano_fail(ctx, SPANO_E_INVALID, "out_step too small");
+    // tiles + canvas (+ accumulator) in one arena after the masks / distance maps
+    size_t extra = 0;
+    std::vector<size_t> off_t(n), t_steps(n);
+    for (int k = 0; k < n; ++k) {
+        if (int rc = check_image_args(ctx, tiles[k], w[k], h[k], tile_steps[k], 3, "tile")) return rc;
+        t_steps[k] = align_up((size_t)w[k] * 3, 16);
+        off_t[k] = extra;
+        extra += align_up(t_steps[k] * h[k], 256);
+    }
+    const size_t o_step = align_up((size_t)cw * 3, 16);
+    const size_t off_out = extra;
+    extra += align_up(o_step * chh, 256);
+    const size_t off_acc = extra;
+    if (simple) extra += (size_t)cw * chh * sizeof(float4);
+    std::vector<const uint8_t *> dm; std::vector<size_t> ms, ds; std::vector<float *> dd;
+    uint8_t *arena = nullptr;
+    if (simple) {
+        if (int rc = upload_and_transform(ctx, n, masks, mask_steps, w, h, dm, ms, dd, ds, extra, &arena)) return rc;
+    } else {
+        // masks only (no distance transform)
+        size_t total = 0;
+        std::vector<size_t> off_m(n);
+        dm.resize(n); ms.resize(n);
+        for (int k = 0; k < n; ++k) {
+            if (int rc = check_image_args(ctx, masks[k], w[k], h[k], mask_steps[k], 1, "mask")) return rc;
+            ms[k] = align_up((size_t)w[k], 16);
+            off_m[k] = total;
+            total += align_up(ms[k] * h[k], 256);
+        }
+        uint8_t *base = nullptr;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_DT_ARENA, total + extra, (void **)&base)) return rc;
+        for (int k = 0; k < n; ++k) {
+            SPANO_CUDA(ctx, cudaMemcpy2DAsync(base + off_m[k], ms[k], masks[k], mask_steps[k], (size_t)w[k], h[k], cudaMemcpyHostToDevice, ctx->stream));
+            dm[k] = base + off_m[k];
+        }
+        arena = base + total;
+    }
+    std::vector<const uint8_t *> d_tiles(n);
+    std::vector<int> ax(n), ay(n);
+    for (int k = 0; k < n; ++k) {
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(arena + off_t[k], t_steps[k], tiles[k], tile_steps[k], (size_t)w[k] * 3, h[k], cudaMemcpyHostToDevice, ctx->stream));
+        d_tiles[k] = arena + off_t[k];
+        ax[k] = tl_x[k] - mx;
+        ay[k] = tl_y[k] - my;
+    }
+    uint8_t *d_out = arena + off_out;
+    int rc;
+    if (simple) {
+        std::vector<const float *> cd(dd.begin(), dd.end());
+        rc = launch_simple_blend(ctx, n, d_tiles.data(), t_steps.data(), cd.data(), ds.data(), ax.data(), ay.data(), w, h,
+                                 reinterpret_cast<float4 *>(arena + off_acc), cw, chh, d_out, o_step);
+    } else {
+        rc = launch_no_blend(ctx, n, d_tiles.data(), t_steps.data(), dm.data(), ms.data(), ax.data(), ay.data(), w, h, cw, chh, d_out, o_step);
+    }
+    if (rc < 0) return rc;
+    SPANO_CUDA(ctx, cudaMemcpy2DAsync(out, out_step, d_out, o_step, (size_t)cw * 3, chh, cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}
+
+} // namespace
+
+extern "C" int spano_simple_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps, const uint8_t *const *masks,
+                                  const size_t *mask_steps, const int *tl_x, const int *tl_y, const int *w, const int *h, uint8_t *out,
+                                  size_t out_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return simple_or_no_blend(ctx, true, n, tiles, tile_steps, masks, mask_steps, tl_x, tl_y, w, h, out, out_step);
+}
+
+extern "C" int spano_no_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps, const uint8_t *const *masks,
+                              const size_t *mask_steps, const int *tl_x, const int *tl_y, const int *w, const int *h, uint8_t *out,
+                              size_t out_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return simple_or_no_blend(ctx, false, n, tiles, tile_steps, masks, mask_steps, tl_x, tl_y, w, h, out, out_step);
+}

@@ -115,7 +115,116 @@ __global__ void dist_cut_kernel(const uint8_t *mask, size_t mstep, const float *
     cut[(size_t)y * cstep + x] = v;
 }
 
+// ---- blnd::simple_blend (reference src/math/_blending.cpp:83-153) and blnd::no_blend (:157-182) -----------------
+// min / max of a distance map (non-negative floats order like their bit patterns)
+__global__ void minmax_kernel(const float *dist, size_t dstep, int w, int h, uint32_t *mm)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    uint32_t lo = 0xffffffffu, hi = 0u;
+    if (x < w && y < h) lo = hi = __float_as_uint(dist[(size_t)y * dstep + x]);
+    for (int d = 16; d; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(mm, lo); atomicMax(mm + 1, hi); }
+}
+
+// one image of simple_blend: alpha = normalize(dist, 0, 1, NORM_MINMAX); over-composite into acc {B,G,R,alpha}
+__global__ void simple_accumulate_kernel(const uint8_t *tile, size_t tstep, const float *dist, size_t dstep, int w, int h,
+                                         const uint32_t *mm, float4 *acc, int canvas_w, int ax, int ay)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    // cv::normalize(NORM_MINMAX, 0, 1): scale and shift in double, applied as floats (convertTo)
+    const float smin = __uint_as_float(mm[0]), smax = __uint_as_float(mm[1]);
+    const double range = (double)smax - (double)smin;
+    const double scale = range > 2.220446049250313e-16 ? 1.0 / range : 0.0;
+    const float a = (float)scale, b = (float)(0.0 - (double)smin * scale);
+    const float m = __fadd_rn(__fmul_rn(dist[(size_t)y * dstep + x], a), b);
+    float4 *p = acc + (size_t)(ay + y) * canvas_w + (ax + x);
+    float4 c = *p;
+    const float om = __fsub_rn(1.0f, c.w);
+    const uint8_t *t = tile + (size_t)y * tstep + (size_t)x * 3;
+    const float inv255 = (float)(1.0 / 255.0);
+    c.x = __fadd_rn(c.x, __fmul_rn(__fmul_rn(__fmul_rn((float)t[0], inv255), m), om));
+    c.y = __fadd_rn(c.y, __fmul_rn(__fmul_rn(__fmul_rn((float)t[1], inv255), m), om));
+    c.z = __fadd_rn(c.z, __fmul_rn(__fmul_rn(__fmul_rn((float)t[2], inv255), m), om));
+    c.w = __fadd_rn(c.w, __fmul_rn(m, om));
+    *p = c;
+}
+
+__global__ void simple_finish_kernel(const float4 *acc, int canvas_w, int canvas_h, uint8_t *out, size_t ostep)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= canvas_w || y >= canvas_h) return;
+    const float4 c = acc[(size_t)y * canvas_w + x];
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    if (c.w > 0.f) {
+        const float ia = __fdiv_rn(1.f, c.w);   // Vec3f / float == Vec3f * (1.f / a)
+        r0 = __fmul_rn(c.x, ia); r1 = __fmul_rn(c.y, ia); r2 = __fmul_rn(c.z, ia);
+    }
+    uint8_t *o = out + (size_t)y * ostep + (size_t)x * 3;
+    o[0] = (uint8_t)min(255, max(0, __float2int_rn(__fmul_rn(r0, 255.f))));
+    o[1] = (uint8_t)min(255, max(0, __float2int_rn(__fmul_rn(r1, 255.f))));
+    o[2] = (uint8_t)min(255, max(0, __float2int_rn(__fmul_rn(r2, 255.f))));
+}
+
+// images[i].copyTo(panorama(roi), masks[i]): later images overwrite earlier ones where their mask is non-zero
+__global__ void no_blend_kernel(const uint8_t *tile, size_t tstep, const uint8_t *mask, size_t mstep, int w, int h, uint8_t *out,
+                                size_t ostep, int ax, int ay)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w || y >= h || !mask[(size_t)y * mstep + x]) return;
+    const uint8_t *t = tile + (size_t)y * tstep + (size_t)x * 3;
+    uint8_t *o = out + (size_t)(ay + y) * ostep + (size_t)(ax + x) * 3;
+    o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
+}
+
 } // namespace
+
+// blnd::simple_blend on device buffers: tiles/masks/dist per image (dist = distance transforms already computed),
+// acc = canvas_w x canvas_h float4 scratch, out = 8UC3 canvas.  Images are composited in order.
+int launch_simple_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tsteps, const float *const *dist,
+                        const size_t *dsteps, const int *ax, const int *ay, const int *w, const int *h, float4 *acc, int canvas_w,
+                        int canvas_h, uint8_t *out, size_t ostep)
+{
+    uint32_t *mm = nullptr;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_DT_JOBS2, (size_t)std::max(1, n) * 2 * sizeof(uint32_t), (void **)&mm)) return rc;
+    std::vector<uint32_t> init(2 * (size_t)n);
+    for (int i = 0; i < n; ++i) { init[2 * i] = 0xffffffffu; init[2 * i + 1] = 0u; }
+    SPANO_CUDA(ctx, cudaMemcpyAsync(mm, init.data(), init.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SPANO_CUDA(ctx, cudaMemsetAsync(acc, 0, (size_t)canvas_w * canvas_h * sizeof(float4), ctx->stream));
+    for (int i = 0; i < n; ++i) {
+        dim3 block(256), grid((w[i] + 255) / 256, h[i]);
+        minmax_kernel<<<grid, block, 0, ctx->stream>>>(dist[i], dsteps[i], w[i], h[i], mm + 2 * i);
+        simple_accumulate_kernel<<<grid, block, 0, ctx->stream>>>(tiles[i], tsteps[i], dist[i], dsteps[i], w[i], h[i], mm + 2 * i, acc,
+                                                                   canvas_w, ax[i], ay[i]);
+    }
+    dim3 block(256), grid((canvas_w + 255) / 256, canvas_h);
+    simple_finish_kernel<<<grid, block, 0, ctx->stream>>>(acc, canvas_w, canvas_h, out, ostep);
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2 * n + 1;
+    return 2 * n + 1;
+}
+
+int launch_no_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tsteps, const uint8_t *const *masks,
+                    const size_t *msteps, const int *ax, const int *ay, const int *w, const int *h, int canvas_w, int canvas_h,
+                    uint8_t *out, size_t ostep)
+{
+    SPANO_CUDA(ctx, cudaMemset2DAsync(out, ostep, 0, (size_t)canvas_w * 3, canvas_h, ctx->stream));
+    for (int i = 0; i < n; ++i) {
+        dim3 block(256), grid((w[i] + 255) / 256, h[i]);
+        no_blend_kernel<<<grid, block, 0, ctx->stream>>>(tiles[i], tsteps[i], masks[i], msteps[i], w[i], h[i], out, ostep, ax[i], ay[i]);
+    }
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += n;
+    return n;
+}
 
 // n images on the device: masks[k] (w[k] x h[k], step mstep[k]) -> dist[k] (float, pitch dstep[k] floats)
 int launch_distance_transform(spano_ctx *ctx, int n, const uint8_t *const *masks, const size_t *msteps, const int *w, const int *h,

@@ -143,6 +143,12 @@ int launch_distance_transform(spano_ctx *ctx, int n, const uint8_t *const *masks
 int launch_dist_cut(spano_ctx *ctx, int n, const uint8_t *const *masks, const size_t *msteps, const float *const *dist,
                     const size_t *dsteps, const int *tl_x, const int *tl_y, const int *w, const int *h, uint8_t *const *cut,
                     const size_t *csteps);
+int launch_simple_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tsteps, const float *const *dist,
+                        const size_t *dsteps, const int *ax, const int *ay, const int *w, const int *h, float4 *acc, int canvas_w,
+                        int canvas_h, uint8_t *out, size_t ostep);
+int launch_no_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tsteps, const uint8_t *const *masks,
+                    const size_t *msteps, const int *ax, const int *ay, const int *w, const int *h, int canvas_w, int canvas_h,
+                    uint8_t *out, size_t ostep);
 // disk_kernels.cu: stereographic centre fix (util::RadialNormalizer state + normalised radius)
 struct SpanoDiskParams {
     float cx, cy, scale;

@@ -66,3 +66,29 @@ def test_dist_errors(ctx):
         api.dist_cut([np.zeros((4, 4), np.uint8)], [(0, 0), (1, 1)], ctx)
     with pytest.raises(api.SpanoError):
         api.distance_transform(np.zeros((0, 0), np.uint8), ctx)
+
+
+def test_simple_and_no_blend(ctx, oracle, golden):
+    """The SIMPLE_BLEND and NO_BLEND branches of stitch_parameters::blend: <= 1 LSB / bit-exact."""
+    from simplepanorama_b200 import api
+    g = golden("dist.npz")
+    corners = [tuple(int(v) for v in c) for c in g["cut_corners"]]
+    tiles = [g[f"blend_tile_{i}"] for i in range(len(corners))]
+    masks = [g[f"blend_mask_{i}"] for i in range(len(corners))]
+    s = api.simple_blend(tiles, masks, corners, ctx)
+    assert np.abs(s.astype(int) - g["simple_ref"].astype(int)).max() <= 1
+    assert np.abs(s.astype(int) - oracle.simple_blend(tiles, masks, corners).astype(int)).max() <= 1
+    assert np.array_equal(api.no_blend(tiles, masks, corners, ctx), g["noblend_ref"])
+    # a real configuration: warped tiles + validity masks of cfg1 at 1/4 scale
+    from simplepanorama_b200 import synth
+    cfg = synth.config("cfg1", 0.25)
+    K, R, gains = synth.cameras(cfg)
+    images = synth.make_images(cfg, gains, 0)
+    pd = api.get_proj_parameters(images, R, K, [1.0] * cfg.n, cfg.kind, cfg.focal, True, ctx)
+    got = api.simple_blend(pd.imgs, pd.msks, pd.corners, ctx)
+    ref = oracle.simple_blend(pd.imgs, pd.msks, pd.corners)
+    assert got.shape == ref.shape and np.abs(got.astype(int) - ref.astype(int)).max() <= 1
+    cuts = api.dist_cut(pd.msks, pd.corners, ctx)
+    assert np.array_equal(api.no_blend(pd.imgs, cuts, pd.corners, ctx), oracle.no_blend(pd.imgs, cuts, pd.corners))
+    with pytest.raises(api.SpanoError):
+        api.simple_blend(tiles, masks[:-1], corners, ctx)       # "Input consistency!"

@@ -29,3 +29,19 @@ def test_dist_cut_matches_reference_restatement(oracle, golden):
     # the cut only ever removes pixels, and the disjoint image is untouched
     assert all(np.all((c == m) | (c == 0)) for c, m in zip(cuts, masks))
     assert np.array_equal(cuts[4], masks[4])
+
+
+def _blend_case(g):
+    corners = [tuple(int(v) for v in c) for c in g["cut_corners"]]
+    tiles = [g[f"blend_tile_{i}"] for i in range(len(corners))]
+    masks = [g[f"blend_mask_{i}"] for i in range(len(corners))]
+    return tiles, masks, corners
+
+
+def test_simple_and_no_blend_match_opencv(oracle, golden):
+    """blnd::simple_blend / blnd::no_blend restated in C against the same loops driven through cv2 (golden)."""
+    g = golden("dist.npz")
+    tiles, masks, corners = _blend_case(g)
+    s = oracle.simple_blend(tiles, masks, corners)
+    assert np.abs(s.astype(int) - g["simple_ref"].astype(int)).max() <= 1      # <= 1 LSB on the 8-bit canvas
+    assert np.array_equal(oracle.no_blend(tiles, masks, corners), g["noblend_ref"])
