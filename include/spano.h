@@ -147,6 +147,19 @@ int spano_no_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const siz
                    const size_t *mask_steps, const int *tl_x, const int *tl_y, const int *w, const int *h, uint8_t *out,
                    size_t out_step);
 
+/* ---- gain::get_overlapp_intensity (src/math/_gain_compensation.cpp:7-75), the reduction that feeds the gain solve:
+ * for every pair i <= j with adj[i*n+j] > 0 or i == j (the reference adds the identity): the number of pixels of the
+ * overlap rectangle that are valid in both createSurroundingMask(img, true, 1) masks, and the sums of both 8-bit
+ * gray images (cv::cvtColor BGR2GRAY) over those pixels.  Exact integers, returned as doubles like OverlapInfo.
+ * `out` must hold n (n + 1) / 2 entries; *n_out receives the number written (the reference's push_back order).
+ * HOST buffers.                                                                                             */
+typedef struct spano_overlap_info {
+    int i, j;
+    double area, I_i, I_j;
+} spano_overlap_info;
+int spano_overlap_intensity(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps, const int *tl_x,
+                            const int *tl_y, const int *w, const int *h, const double *adj, spano_overlap_info *out, int *n_out);
+
 /* a6 alone: `img / gain` on CV_8UC3, in place. */
 int spano_apply_gain(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, double gain);
 

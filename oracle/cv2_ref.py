@@ -253,3 +253,32 @@ def no_blend(images, masks, top_lefts) -> np.ndarray:
         roi = pano[y0:y0 + h, x0:x0 + w]
         cv2.copyTo(img, mask, roi)
     return pano
+
+
+def get_overlapp_intensity(warped_images, corners, adj):
+    """gain::get_overlapp_intensity (src/math/_gain_compensation.cpp:7-75) through cv2 (cvtColor, bitwise_and,
+    countNonZero, sum) -> list of (i, j, area, I_i, I_j)."""
+    n = len(warped_images)
+    adj = np.asarray(adj, np.float64) + np.eye(n)
+    grays = [cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) for img in warped_images]
+    masks = [create_surrounding_mask(img) for img in warped_images]
+    res = []
+    for i in range(n):
+        for j in range(i, n):
+            if not adj[i, j] > 0:
+                continue
+            hi, wi = grays[i].shape; hj, wj = grays[j].shape
+            x0 = max(corners[i][0], corners[j][0]); y0 = max(corners[i][1], corners[j][1])
+            x1 = min(corners[i][0] + wi, corners[j][0] + wj); y1 = min(corners[i][1] + hi, corners[j][1] + hj)
+            if x1 <= x0 or y1 <= y0:
+                res.append((i, j, 0.0, 0.0, 0.0))
+                continue
+            si = (slice(y0 - corners[i][1], y1 - corners[i][1]), slice(x0 - corners[i][0], x1 - corners[i][0]))
+            sj = (slice(y0 - corners[j][1], y1 - corners[j][1]), slice(x0 - corners[j][0], x1 - corners[j][0]))
+            comb = cv2.bitwise_and(np.ascontiguousarray(masks[i][si]), np.ascontiguousarray(masks[j][sj]))
+            area = float(cv2.countNonZero(comb))
+            gi = np.ascontiguousarray(grays[i][si]); gj = np.ascontiguousarray(grays[j][sj])
+            Ii = cv2.sumElems(cv2.bitwise_and(gi, gi, mask=comb))[0]
+            Ij = cv2.sumElems(cv2.bitwise_and(gj, gj, mask=comb))[0]
+            res.append((i, j, area, float(Ii), float(Ij)))
+    return res

@@ -65,6 +65,19 @@ def main():
         out[f"blend_mask_{i}"] = m
     out["simple_ref"] = cv2_ref.simple_blend(tiles, bmasks, corners)
     out["noblend_ref"] = cv2_ref.no_blend(tiles, bmasks, corners)
+    # gain::get_overlapp_intensity on warped-like tiles (dark outside a curved region, a few dark blobs inside)
+    wt = []
+    for t, m in zip(tiles, ms):
+        t2 = np.maximum(t, 8)
+        t2[m == 0] = 0
+        wt.append(np.ascontiguousarray(t2))
+    adj = np.zeros((len(wt), len(wt)))
+    adj[0, 1] = adj[1, 0] = adj[0, 3] = adj[3, 0] = adj[1, 2] = adj[2, 1] = adj[1, 3] = adj[3, 1] = 1
+    adj[2, 4] = adj[4, 2] = 1                             # adjacent in the graph, but the rectangles do not overlap
+    for i, t in enumerate(wt):
+        out[f"ov_tile_{i}"] = t
+    out["ov_adj"] = adj
+    out["ov_ref"] = np.array(cv2_ref.get_overlapp_intensity(wt, corners, adj), np.float64)
     path = os.path.join(ROOT, "tests", "golden", "dist.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes, cv2", cv2.__version__)

@@ -258,3 +258,18 @@ def simple_blend(tiles, masks, corners):
 def no_blend(tiles, masks, corners):
     """blnd::no_blend -> CV_8UC3 canvas."""
     return _simple_or_no_blend(lib().orc_no_blend, tiles, masks, corners)
+
+
+def overlap_intensity(tiles, corners, adj):
+    """gain::get_overlapp_intensity -> list of (i, j, area, I_i, I_j)."""
+    n = len(tiles)
+    ts = [np.ascontiguousarray(t, np.uint8) for t in tiles]
+    arr = (C.c_void_p * n)(*[t.ctypes.data for t in ts])
+    tlx = np.array([c[0] for c in corners], np.int32); tly = np.array([c[1] for c in corners], np.int32)
+    w = np.array([t.shape[1] for t in ts], np.int32); h = np.array([t.shape[0] for t in ts], np.int32)
+    a = np.ascontiguousarray(adj, np.float64)
+    out = np.zeros((n * (n + 1) // 2, 5), np.float64)
+    lib().orc_overlap_intensity.restype = C.c_int
+    cnt = lib().orc_overlap_intensity(n, arr, _p(tlx, C.c_int), _p(tly, C.c_int), _p(w, C.c_int), _p(h, C.c_int), _p(a, C.c_double),
+                                      _p(out, C.c_double))
+    return [(int(r[0]), int(r[1]), float(r[2]), float(r[3]), float(r[4])) for r in out[:cnt]]

@@ -894,3 +894,39 @@ void orc_no_blend(int n, const uint8_t *const *tiles, const uint8_t *const *mask
                 out[c * 3] = tiles[i][k * 3]; out[c * 3 + 1] = tiles[i][k * 3 + 1]; out[c * 3 + 2] = tiles[i][k * 3 + 2];
             }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * gain::get_overlapp_intensity (src/math/_gain_compensation.cpp:7-75): for every pair i <= j with (adj + I)(i,j) > 0:
+ * area = countNonZero(mask_i & mask_j) over the overlap rectangle, I_i / I_j = sums of the 8-bit gray images there;
+ * masks = createSurroundingMask(img, true, 1) (no erosion).  out[k*5] = {i, j, area, I_i, I_j}; returns the count.
+ * --------------------------------------------------------------------------------------------- */
+int orc_overlap_intensity(int n, const uint8_t *const *tiles, const int *tl_x, const int *tl_y, const int *w, const int *h,
+                          const double *adj, double *out)
+{
+    uint8_t **gray = (uint8_t **)malloc((size_t)n * sizeof(uint8_t *)), **mask = (uint8_t **)malloc((size_t)n * sizeof(uint8_t *));
+    for (int i = 0; i < n; ++i) {
+        gray[i] = (uint8_t *)malloc((size_t)w[i] * h[i]);
+        mask[i] = (uint8_t *)malloc((size_t)w[i] * h[i]);
+        orc_gray_u8(tiles[i], w[i], h[i], (size_t)w[i] * 3, gray[i]);
+        orc_surrounding_mask(tiles[i], w[i], h[i], (size_t)w[i] * 3, 0, mask[i]);
+    }
+    int count = 0;
+    for (int i = 0; i < n; ++i)
+        for (int j = i; j < n; ++j) {
+            if (!(adj[(size_t)i * n + j] + (i == j ? 1.0 : 0.0) > 0)) continue;
+            double area = 0, si = 0, sj = 0;
+            const int x0 = tl_x[i] > tl_x[j] ? tl_x[i] : tl_x[j], y0 = tl_y[i] > tl_y[j] ? tl_y[i] : tl_y[j];
+            const int xa = tl_x[i] + w[i], xb = tl_x[j] + w[j], ya = tl_y[i] + h[i], yb = tl_y[j] + h[j];
+            const int x1 = xa < xb ? xa : xb, y1 = ya < yb ? ya : yb;
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x) {
+                    const size_t ki = (size_t)(y - tl_y[i]) * w[i] + (x - tl_x[i]), kj = (size_t)(y - tl_y[j]) * w[j] + (x - tl_x[j]);
+                    if (mask[i][ki] & mask[j][kj]) { area += 1; si += gray[i][ki]; sj += gray[j][kj]; }
+                }
+            out[count * 5] = i; out[count * 5 + 1] = j; out[count * 5 + 2] = area; out[count * 5 + 3] = si; out[count * 5 + 4] = sj;
+            ++count;
+        }
+    for (int i = 0; i < n; ++i) { free(gray[i]); free(mask[i]); }
+    free(gray); free(mask);
+    return count;
+}

@@ -238,3 +238,29 @@ std::vector<cv::Mat> dist_cut(const std::vector<cv::Mat> &masks, const std::vect
 }
 
 } // namespace dcut
+
+namespace gain {
+
+// src/math/_gain_compensation.cpp:7-75 (struct OverlapInfo {int i, j; double area, I_i, I_j;} from _gain_compensation.h)
+std::vector<OverlapInfo> get_overlapp_intensity(const std::vector<cv::Mat> &warped_images, const std::vector<cv::Point> &corners,
+                                                const cv::Mat &adj_pass)
+{
+    const int n = (int)warped_images.size();
+    std::vector<const uint8_t *> t(n);
+    std::vector<size_t> ts(n);
+    std::vector<int> x(n), y(n), w(n), h(n);
+    for (int i = 0; i < n; ++i) {
+        t[i] = warped_images[i].data; ts[i] = warped_images[i].step;
+        x[i] = corners[i].x; y[i] = corners[i].y; w[i] = warped_images[i].cols; h[i] = warped_images[i].rows;
+    }
+    cv::Mat adj;
+    adj_pass.convertTo(adj, CV_64F);               // contiguous n x n doubles
+    std::vector<spano_overlap_info> out((size_t)n * (n + 1) / 2);
+    int count = 0;
+    check(spano_overlap_intensity(ctx(), n, t.data(), ts.data(), x.data(), y.data(), w.data(), h.data(), adj.ptr<double>(), out.data(), &count));
+    std::vector<OverlapInfo> results;
+    for (int k = 0; k < count; ++k) results.push_back({out[k].i, out[k].j, out[k].area, out[k].I_i, out[k].I_j});
+    return results;
+}
+
+} // namespace gain

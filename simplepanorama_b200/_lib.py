@@ -39,6 +39,11 @@ class Slice(C.Structure):
                 ("valid", C.c_void_p), ("valid_step", C.c_size_t)]
 
 
+class OverlapInfo(C.Structure):
+    """struct spano_overlap_info == gain::OverlapInfo"""
+    _fields_ = [("i", C.c_int), ("j", C.c_int), ("area", C.c_double), ("I_i", C.c_double), ("I_j", C.c_double)]
+
+
 # every symbol include/spano.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "spano_version": (C.c_int, []),
@@ -61,6 +66,8 @@ SYMBOLS = {
     "spano_dist_cut": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_intp, c_intp, c_intp, c_intp, c_u8pp, c_sizep]),
     "spano_simple_blend": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_u8pp, c_sizep, c_intp, c_intp, c_intp, c_intp, C.c_void_p, C.c_size_t]),
     "spano_no_blend": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_u8pp, c_sizep, c_intp, c_intp, c_intp, c_intp, C.c_void_p, C.c_size_t]),
+    "spano_overlap_intensity": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_intp, c_intp, c_intp, c_intp, C.POINTER(C.c_double),
+                                          C.POINTER(OverlapInfo), c_intp]),
     "spano_apply_gain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_double]),
     "spano_disk_reproj_size": (C.c_int, [C.c_void_p, C.c_int, c_intp, c_intp, c_intp, c_intp, C.c_int, C.c_int, C.c_float,
                                          C.c_int, c_intp, c_intp, c_intp, c_intp]),

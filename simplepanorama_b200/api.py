@@ -27,7 +27,7 @@ from ._lib import (CYLINDRICAL, OUT_F32, OUT_U8, SPHERICAL, STEREOGRAPHIC, Image
 __all__ = [
     "SPHERICAL", "CYLINDRICAL", "STEREOGRAPHIC", "Context", "ProjData", "SpanoError", "adjusted_camera", "warp_roi",
     "project", "get_proj_parameters", "create_surrounding_mask", "validity_mask", "apply_gain", "get_pan_dimension",
-    "multi_blend", "blend", "return_full", "default_context", "distance_transform", "dist_cut", "simple_blend", "no_blend",
+    "multi_blend", "blend", "return_full", "default_context", "distance_transform", "dist_cut", "simple_blend", "no_blend", "get_overlapp_intensity",
 ]
 
 
@@ -422,6 +422,26 @@ def simple_blend(images, masks, top_lefts, ctx: Context | None = None) -> np.nda
 def no_blend(images, masks, top_lefts, ctx: Context | None = None) -> np.ndarray:
     """blnd::no_blend (stitch_parameters::blend, NO_BLEND) -> CV_8UC3 canvas."""
     return _simple_or_no_blend("spano_no_blend", images, masks, top_lefts, ctx)
+
+
+def get_overlapp_intensity(warped_images, corners, adj, ctx: Context | None = None):
+    """gain::get_overlapp_intensity (src/math/_gain_compensation.cpp:7-75): list of (i, j, area, I_i, I_j) for every
+    pair i <= j that is adjacent in `adj` (the identity is added, as the reference does)."""
+    ctx = ctx or default_context()
+    n = len(warped_images)
+    a = np.ascontiguousarray(adj, np.float64)
+    if n == 0 or n != len(corners) or a.shape != (n, n):
+        raise SpanoError(_lib.E_INVALID, "Input consistency!")
+    imgs = [_u8img(t, 3, f"warped_images[{i}]") for i, t in enumerate(warped_images)]
+    ptr = (C.c_void_p * n)(*[t.ctypes.data for t in imgs])
+    steps = (C.c_size_t * n)(*[t.strides[0] for t in imgs])
+    tlx = np.array([c[0] for c in corners], np.int32); tly = np.array([c[1] for c in corners], np.int32)
+    w = np.array([t.shape[1] for t in imgs], np.int32); h = np.array([t.shape[0] for t in imgs], np.int32)
+    out = (_lib.OverlapInfo * (n * (n + 1) // 2))()
+    cnt = C.c_int()
+    ctx.check(ctx.lib.spano_overlap_intensity(ctx.h, n, ptr, steps, _ip(tlx), _ip(tly), _ip(w), _ip(h),
+                                              a.ctypes.data_as(C.POINTER(C.c_double)), out, C.byref(cnt)))
+    return [(o.i, o.j, o.area, o.I_i, o.I_j) for o in out[: cnt.value]]
 
 
 def distance_transform(mask, ctx: Context | None = None) -> np.ndarray:

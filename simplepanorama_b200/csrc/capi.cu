@@ -1488,3 +1488,65 @@ extern "C" int spano_no_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles
     Guard g(ctx);
     return simple_or_no_blend(ctx, false, n, tiles, tile_steps, masks, mask_steps, tl_x, tl_y, w, h, out, out_step);
 }
+
+// ---------------------------------------------------------------------------------------------
+// gain::get_overlapp_intensity, host buffers
+// ---------------------------------------------------------------------------------------------
+extern "C" int spano_overlap_intensity(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps, const int *tl_x,
+                                       const int *tl_y, const int *w, const int *h, const double *adj, spano_overlap_info *out, int *n_out)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (n <= 0 || !tiles || !tile_steps || !tl_x || !tl_y || !w || !h || !adj || !out || !n_out)
+        return spano_fail(ctx, SPANO_E_INVALID, "spano_overlap_intensity: null/empty argument");
+    size_t total = 0;
+    std::vector<size_t> off_t(n), off_g(n), off_m(n), off_d(n), ts(n), gs(n);
+    for (int k = 0; k < n; ++k) {
+        if (int rc = check_image_args(ctx, tiles[k], w[k], h[k], tile_steps[k], 3, "tile")) return rc;
+        ts[k] = align_up((size_t)w[k] * 3, 16);
+        gs[k] = align_up((size_t)w[k], 16);
+        off_t[k] = total;  total += align_up(ts[k] * h[k], 256);
+        off_g[k] = total;  total += align_up(gs[k] * h[k], 256);
+        off_m[k] = total;  total += align_up(gs[k] * h[k], 256);
+        off_d[k] = total;  total += align_up(gs[k] * h[k], 256);
+    }
+    const int max_pairs = n * (n + 1) / 2;
+    const size_t off_acc = total;
+    total += (size_t)max_pairs * 3 * sizeof(unsigned long long);
+    uint8_t *arena = nullptr;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_DT_ARENA, total, (void **)&arena)) return rc;
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(arena + off_acc);
+    SPANO_CUDA(ctx, cudaMemsetAsync(acc, 0, (size_t)max_pairs * 3 * sizeof(unsigned long long), ctx->stream));
+    for (int k = 0; k < n; ++k) {
+        uint8_t *t = arena + off_t[k];
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(t, ts[k], tiles[k], tile_steps[k], (size_t)w[k] * 3, h[k], cudaMemcpyHostToDevice, ctx->stream));
+        if (int rc = launch_gray(ctx, t, ts[k], w[k], h[k], arena + off_g[k], gs[k]); rc < 0) return rc;
+        if (int rc = launch_dark_flags(ctx, t, w[k], h[k], ts[k], arena + off_d[k], gs[k]); rc < 0) return rc;
+        if (int rc = launch_valid_mask(ctx, arena + off_d[k], w[k], h[k], gs[k], 0, arena + off_m[k], gs[k]); rc < 0) return rc;
+    }
+    int count = 0;
+    std::vector<int> slot;
+    for (int i = 0; i < n; ++i)
+        for (int j = i; j < n; ++j) {
+            if (!(adj[(size_t)i * n + j] + (i == j ? 1.0 : 0.0) > 0)) continue;
+            out[count].i = i;  out[count].j = j;  out[count].area = out[count].I_i = out[count].I_j = 0.0;
+            const int x0 = std::max(tl_x[i], tl_x[j]), y0 = std::max(tl_y[i], tl_y[j]);
+            const int x1 = std::min(tl_x[i] + w[i], tl_x[j] + w[j]), y1 = std::min(tl_y[i] + h[i], tl_y[j] + h[j]);
+            if (x1 > x0 && y1 > y0)
+                if (int rc = launch_overlap_sums(ctx, arena + off_g[i], gs[i], arena + off_m[i], gs[i], arena + off_g[j], gs[j], arena + off_m[j],
+                                                 gs[j], x0 - tl_x[i], y0 - tl_y[i], x0 - tl_x[j], y0 - tl_y[j], x1 - x0, y1 - y0, acc + 3 * (size_t)count);
+                    rc < 0)
+                    return rc;
+            ++count;
+        }
+    std::vector<unsigned long long> host((size_t)std::max(1, count) * 3);
+    SPANO_CUDA(ctx, cudaMemcpyAsync(host.data(), acc, (size_t)count * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < count; ++k) {
+        out[k].area = (double)host[3 * (size_t)k];
+        out[k].I_i = (double)host[3 * (size_t)k + 1];
+        out[k].I_j = (double)host[3 * (size_t)k + 2];
+    }
+    *n_out = count;
+    return SPANO_OK;
+}

@@ -184,7 +184,63 @@ __global__ void no_blend_kernel(const uint8_t *tile, size_t tstep, const uint8_t
     o[0] = t[0]; o[1] = t[1]; o[2] = t[2];
 }
 
+// ---- gain::get_overlapp_intensity (reference src/math/_gain_compensation.cpp:7-75) ----------------------------
+// cv::cvtColor(BGR2GRAY) on 8 bit: (3735 B + 19235 G + 9798 R + 2^14) >> 15
+__global__ void gray_kernel(const uint8_t *bgr, size_t step, int w, int h, uint8_t *gray, size_t gstep)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w || y >= h) return;
+    const uint8_t *p = bgr + (size_t)y * step + (size_t)x * 3;
+    gray[(size_t)y * gstep + x] = (uint8_t)((3735u * p[0] + 19235u * p[1] + 9798u * p[2] + (1u << 14)) >> 15);
+}
+
+// one pair: over the overlap rectangle, count the pixels valid in both masks and sum both gray images there
+// acc[0] = area, acc[1] = sum gray_i, acc[2] = sum gray_j (exact integers)
+__global__ void overlap_sums_kernel(const uint8_t *gi, size_t gis, const uint8_t *mi, size_t mis, const uint8_t *gj, size_t gjs,
+                                    const uint8_t *mj, size_t mjs, int xi, int yi, int xj, int yj, int ow, int oh,
+                                    unsigned long long *acc)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    unsigned int a = 0, si = 0, sj = 0;
+    if (x < ow && y < oh && mi[(size_t)(yi + y) * mis + xi + x] && mj[(size_t)(yj + y) * mjs + xj + x]) {
+        a = 1;
+        si = gi[(size_t)(yi + y) * gis + xi + x];
+        sj = gj[(size_t)(yj + y) * gjs + xj + x];
+    }
+    for (int d = 16; d; d >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, d);
+        si += __shfl_xor_sync(0xffffffffu, si, d);
+        sj += __shfl_xor_sync(0xffffffffu, sj, d);
+    }
+    if ((threadIdx.x & 31) == 0 && a) {
+        atomicAdd(acc, (unsigned long long)a);
+        atomicAdd(acc + 1, (unsigned long long)si);
+        atomicAdd(acc + 2, (unsigned long long)sj);
+    }
+}
+
 } // namespace
+
+int launch_gray(spano_ctx *ctx, const uint8_t *bgr, size_t step, int w, int h, uint8_t *gray, size_t gstep)
+{
+    dim3 block(256), grid((w + 255) / 256, h);
+    gray_kernel<<<grid, block, 0, ctx->stream>>>(bgr, step, w, h, gray, gstep);
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return 1;
+}
+
+int launch_overlap_sums(spano_ctx *ctx, const uint8_t *gi, size_t gis, const uint8_t *mi, size_t mis, const uint8_t *gj, size_t gjs,
+                        const uint8_t *mj, size_t mjs, int xi, int yi, int xj, int yj, int ow, int oh, unsigned long long *acc)
+{
+    dim3 block(256), grid((ow + 255) / 256, oh);
+    overlap_sums_kernel<<<grid, block, 0, ctx->stream>>>(gi, gis, mi, mis, gj, gjs, mj, mjs, xi, yi, xj, yj, ow, oh, acc);
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return 1;
+}
 
 // blnd::simple_blend on device buffers: tiles/masks/dist per image (dist = distance transforms already computed),
 // acc = canvas_w x canvas_h float4 scratch, out = 8UC3 canvas.  Images are composited in order.

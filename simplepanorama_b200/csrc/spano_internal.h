@@ -149,6 +149,9 @@ int launch_simple_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles, cons
 int launch_no_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tsteps, const uint8_t *const *masks,
                     const size_t *msteps, const int *ax, const int *ay, const int *w, const int *h, int canvas_w, int canvas_h,
                     uint8_t *out, size_t ostep);
+int launch_gray(spano_ctx *ctx, const uint8_t *bgr, size_t step, int w, int h, uint8_t *gray, size_t gstep);
+int launch_overlap_sums(spano_ctx *ctx, const uint8_t *gi, size_t gis, const uint8_t *mi, size_t mis, const uint8_t *gj, size_t gjs,
+                        const uint8_t *mj, size_t mjs, int xi, int yi, int xj, int yj, int ow, int oh, unsigned long long *acc);
 // disk_kernels.cu: stereographic centre fix (util::RadialNormalizer state + normalised radius)
 struct SpanoDiskParams {
     float cx, cy, scale;

@@ -92,3 +92,25 @@ def test_simple_and_no_blend(ctx, oracle, golden):
     assert np.array_equal(api.no_blend(pd.imgs, cuts, pd.corners, ctx), oracle.no_blend(pd.imgs, cuts, pd.corners))
     with pytest.raises(api.SpanoError):
         api.simple_blend(tiles, masks[:-1], corners, ctx)       # "Input consistency!"
+
+
+def test_overlap_intensity(ctx, oracle, golden):
+    """gain::get_overlapp_intensity (the reduction feeding the gain solve): exact."""
+    from simplepanorama_b200 import api
+    g = golden("dist.npz")
+    corners = [tuple(int(v) for v in c) for c in g["cut_corners"]]
+    tiles = [g[f"ov_tile_{i}"] for i in range(len(corners))]
+    got = np.array(api.get_overlapp_intensity(tiles, corners, g["ov_adj"], ctx), np.float64)
+    assert np.array_equal(got, g["ov_ref"])
+    # real warped tiles (cfg1 at 1/4 scale), chain adjacency
+    from simplepanorama_b200 import synth
+    cfg = synth.config("cfg1", 0.25)
+    K, R, gains = synth.cameras(cfg)
+    images = synth.make_images(cfg, gains, 0)
+    pd = api.get_proj_parameters(images, R, K, [1.0] * cfg.n, cfg.kind, cfg.focal, False, ctx)
+    adj = np.zeros((cfg.n, cfg.n)); idx = np.arange(cfg.n - 1); adj[idx, idx + 1] = adj[idx + 1, idx] = 1
+    got = api.get_overlapp_intensity(pd.imgs, pd.corners, adj, ctx)
+    ref = oracle.overlap_intensity(pd.imgs, pd.corners, adj)
+    assert got == ref and len(got) == 2 * cfg.n - 1 and all(r[2] > 0 for r in got)
+    with pytest.raises(api.SpanoError):
+        api.get_overlapp_intensity(tiles, corners[:-1], g["ov_adj"], ctx)

@@ -45,3 +45,13 @@ def test_simple_and_no_blend_match_opencv(oracle, golden):
     s = oracle.simple_blend(tiles, masks, corners)
     assert np.abs(s.astype(int) - g["simple_ref"].astype(int)).max() <= 1      # <= 1 LSB on the 8-bit canvas
     assert np.array_equal(oracle.no_blend(tiles, masks, corners), g["noblend_ref"])
+
+
+def test_overlap_intensity_matches_opencv(oracle, golden):
+    """gain::get_overlapp_intensity: exact integer sums, same pair order as the reference's push_back."""
+    g = golden("dist.npz")
+    corners = [tuple(int(v) for v in c) for c in g["cut_corners"]]
+    tiles = [g[f"ov_tile_{i}"] for i in range(len(corners))]
+    got = np.array(oracle.overlap_intensity(tiles, corners, g["ov_adj"]), np.float64)
+    assert got.shape == g["ov_ref"].shape and np.array_equal(got, g["ov_ref"])
+    assert (got[:, 2] > 0).sum() >= 6 and (got[:, 2] == 0).sum() >= 1      # overlapping pairs and the disjoint one
