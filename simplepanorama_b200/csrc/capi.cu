@@ -807,8 +807,9 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
     struct ColRun { int c0, c1, idx; };
     std::vector<ColRun> runs;
     std::vector<cudaEvent_t> flush_events;
-    if (host && !use.empty()) {
-        if (!ctx->d2h_stream) SPANO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    // (device path too: the finished columns are normalised on the auxiliary stream while the next images blend)
+    if (!use.empty()) {
+        if (host && !ctx->d2h_stream) SPANO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
         std::vector<int> last(cw, 0);   // uncovered columns are final from the start: flushed after the first image
         for (int idx = 0; idx < (int)use.size(); ++idx) {
             const int j = use[idx];
@@ -902,27 +903,26 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         if (k < 0) return k;
         t2.stop(k);
         SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_blended[b], main_stream));
-        if (host) {
-            SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], main_stream));
-            // canvas columns that no later image touches are final: normalise and download them now, on the
-            // download stream, while the remaining images are still being blended
-            for (const ColRun &r : runs) {
-                if (r.idx != idx) continue;
-                StageTimer t3(ctx, 3);
-                int kn = launch_normalise(ctx, acc, cw, rows, bands, SPANO_OUT_U8, d_canvas, d_step, r.c0, r.c1);
-                if (kn < 0) return kn;
-                t3.stop(kn);
-                cudaEvent_t e;
-                SPANO_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                flush_events.push_back(e);
-                SPANO_CUDA(ctx, cudaEventRecord(e, main_stream));
-                SPANO_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, e, 0));
-                SPANO_CUDA(ctx, cudaMemcpy2DAsync(canvas + (size_t)r.c0 * 3, canvas_step, d_canvas + (size_t)r.c0 * 3, d_step,
-                                                  (size_t)(r.c1 - r.c0) * 3, rows, cudaMemcpyDeviceToHost, ctx->d2h_stream));
-            }
+        if (host) SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_free[b], main_stream));
+        // canvas columns that no later image touches are final: normalise them now (host path: and download them on
+        // the download stream) while the remaining images are still being blended
+        for (const ColRun &r : runs) {
+            if (r.idx != idx) continue;
+            StageTimer t3(ctx, 3);
+            int kn = launch_normalise(ctx, acc, cw, rows, bands, SPANO_OUT_U8, d_canvas, d_step, r.c0, r.c1);
+            if (kn < 0) return kn;
+            t3.stop(kn);
+            if (!host) continue;
+            cudaEvent_t e;
+            SPANO_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            flush_events.push_back(e);
+            SPANO_CUDA(ctx, cudaEventRecord(e, main_stream));
+            SPANO_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, e, 0));
+            SPANO_CUDA(ctx, cudaMemcpy2DAsync(canvas + (size_t)r.c0 * 3, canvas_step, d_canvas + (size_t)r.c0 * 3, d_step,
+                                              (size_t)(r.c1 - r.c0) * 3, rows, cudaMemcpyDeviceToHost, ctx->d2h_stream));
         }
     }
-    if (!host || use.empty()) {
+    if (use.empty()) {
         StageTimer t3(ctx, 3);
         int k = launch_normalise(ctx, acc, cw, rows, bands, SPANO_OUT_U8, d_canvas, d_step);
         if (k < 0) return k;
