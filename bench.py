@@ -307,6 +307,8 @@ def run_ours(args):
         if have:   # (host variant: queues the small mask uploads ahead of the large source uploads below)
             sdist.blend_begin(ctx, sp, rank, cfg.bands, cfg.sigma, host_descs=descs_host if host else None,
                               host_canvas=(h_canvas.data_ptr(), h_canvas.stride(0)))
+            # everything that does not depend on the owners' data (mask up-scaling, sparsity plans) starts now
+            sdist.blend_prepare(ctx, sp, rank, descs, arenas.own, host=host)
         tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)   # every rank has finished blending the previous step's arenas
         pe[1].record(stream)
         aux.wait_stream(stream)

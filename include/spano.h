@@ -311,6 +311,14 @@ int spano_warp_scatter(spano_ctx *ctx, int proj, float scale, const spano_image_
 int spano_dev_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma);
 int spano_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma,
                       int n, const spano_image_desc *images, uint8_t *canvas, size_t canvas_step);
+/* Optional, between begin and the first add: everything about the n images that does not depend on the owners' data
+ * -- the up-scaling of mask_cut for the slice rows and the blend's sparsity plan -- is done now, on an auxiliary
+ * stream, while the band waits for the tile rows to arrive; spano_*_blend_add then only launches the blend kernel
+ * of an image it recognises (by address: pass elements of the same `images` array).  slices[j].row1 <= row0 marks an
+ * image that does not touch the band.  spano_blend_prepare: mask_cut are HOST pointers (those announced at
+ * spano_blend_begin are already on the device).                                                              */
+int spano_dev_blend_prepare(spano_ctx *ctx, int n, const spano_image_desc *images, const spano_slice *slices);
+int spano_blend_prepare(spano_ctx *ctx, int n, const spano_image_desc *images, const spano_slice *slices);
 int spano_dev_blend_add(spano_ctx *ctx, const spano_image_desc *im, const spano_slice *slice);
 int spano_dev_blend_finish(spano_ctx *ctx, uint8_t *canvas, size_t canvas_step);
 int spano_blend_add(spano_ctx *ctx, const spano_image_desc *im, const spano_slice *slice);

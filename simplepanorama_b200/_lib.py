@@ -94,6 +94,8 @@ SYMBOLS = {
     "spano_dev_blend_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
     "spano_blend_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                     C.POINTER(ImageDesc), C.c_void_p, C.c_size_t]),
+    "spano_dev_blend_prepare": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ImageDesc), C.POINTER(Slice)]),
+    "spano_blend_prepare": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(ImageDesc), C.POINTER(Slice)]),
     "spano_dev_blend_add": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.POINTER(Slice)]),
     "spano_dev_blend_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "spano_blend_add": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.POINTER(Slice)]),

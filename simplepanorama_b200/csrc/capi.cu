@@ -220,6 +220,7 @@ extern "C" void spano_destroy(spano_ctx *ctx)
         for (int b = 0; b < 2; ++b) { cudaEventDestroy(ctx->ev_copied[b]); cudaEventDestroy(ctx->ev_free[b]); }
         cudaEventDestroy(ctx->ev_start);
     }
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1062,6 +1063,143 @@ int warp_scatter_impl(spano_ctx *ctx, int proj, float scale, const spano_image_d
     return SPANO_OK;
 }
 
+// mask_cut of image `im` at tile size for the tile rows [need0, need1): returns the VIRTUAL address of row 0 and the
+// step.  Preview-scale masks are up-scaled (host ones are first looked up among those staged at begin, else uploaded),
+// tile-sized host masks are uploaded, tile-sized device masks are used in place.  Work goes to ctx->stream; the
+// resized rows land in buffer `buf` at byte offset `buf_off`.
+int blend_resolve_cut(spano_ctx *ctx, const spano_image_desc *im, int need0, int need1, bool host, int buf, size_t buf_off,
+                      const uint8_t **cut_v, size_t *cut_step)
+{
+    spano_ctx::BlendSession &S = ctx->bs;
+    const bool small = im->mask_cut_w > 0 || im->mask_cut_h > 0;
+    if (int rc = check_image_args(ctx, im->mask_cut, small ? im->mask_cut_w : im->w, small ? im->mask_cut_h : im->h, im->mask_cut_step, 1, "mask_cut"))
+        return rc;
+    const size_t m_step = align_up((size_t)im->w, 16);
+    if (!small && !host) {
+        *cut_v = im->mask_cut;
+        *cut_step = im->mask_cut_step;
+        return 0;
+    }
+    uint8_t *cutbuf = (uint8_t *)ctx->buf[buf].ptr;
+    if (buf == spano_ctx::BUF_CUTMASK) {
+        if (int rc = spano_reserve(ctx, buf, m_step * (need1 - need0) + 256, (void **)&cutbuf)) return rc;
+    }
+    cutbuf += buf_off;
+    uint8_t *cut_base = cutbuf - (size_t)need0 * m_step;
+    if (small) {
+        const uint8_t *sm = im->mask_cut;
+        size_t sm_step = im->mask_cut_step;
+        const spano_ctx::BlendSession::Staged *hit = nullptr;
+        if (host)
+            for (const auto &st : S.staged)
+                if (st.host == im->mask_cut) { hit = &st; break; }
+        if (hit) {
+            sm = hit->dev;
+            sm_step = hit->step;
+        } else if (host) {
+            uint8_t *stage = nullptr;
+            sm_step = align_up((size_t)im->mask_cut_w, 16);
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTSMALL2, sm_step * im->mask_cut_h + 256, (void **)&stage)) return rc;
+            SPANO_CUDA(ctx, cudaMemcpy2DAsync(stage, sm_step, im->mask_cut, im->mask_cut_step, (size_t)im->mask_cut_w, im->mask_cut_h,
+                                              cudaMemcpyHostToDevice, ctx->stream));
+            sm = stage;
+        }
+        int k = launch_resize_mask(ctx, sm, im->mask_cut_w, im->mask_cut_h, sm_step, cut_base, im->w, im->h, m_step, need0, need1);
+        if (k < 0) return k;
+    } else {
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(cutbuf, m_step, im->mask_cut + (size_t)need0 * im->mask_cut_step, im->mask_cut_step, (size_t)im->w,
+                                          need1 - need0, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    *cut_v = cut_base;
+    *cut_step = m_step;
+    return 0;
+}
+
+// tile rows of `im` that band [S.row0, S.row1) produces and reads; false when the tile does not touch the band
+bool blend_rows(const spano_ctx::BlendSession &S, const spano_image_desc *im, int *first, int *last, int *need0, int *need1)
+{
+    const int cy = im->tl_y - S.my;
+    *first = std::max(0, S.row0 - cy);
+    *last = std::min(im->h, S.row1 - cy);
+    if (*last <= *first) return false;
+    const int R = S.radius;
+    *need0 = (im->h < 4 * R) ? 0 : std::max(0, *first - R);
+    *need1 = (im->h < 4 * R) ? im->h : std::min(im->h, *last + R);
+    return true;
+}
+
+int blend_prepare_impl(spano_ctx *ctx, int n, const spano_image_desc *images, const spano_slice *slices, bool host)
+{
+    spano_ctx::BlendSession &S = ctx->bs;
+    if (!S.open) return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_prepare without spano_dev_blend_begin");
+    if (n < 0 || (n > 0 && (!images || !slices))) return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_prepare: null argument");
+    S.prepared.clear();
+    // layout of the two arenas
+    std::vector<size_t> off_c(n, 0), off_p(n, 0);
+    std::vector<char> take(n, 0);
+    size_t cut_total = 0, plan_total = 0;
+    for (int j = 0; j < n; ++j) {
+        const spano_image_desc *im = images + j;
+        int first, last, need0, need1;
+        if (im->w <= 0 || im->h <= 0 || slices[j].row1 <= slices[j].row0 || !blend_rows(S, im, &first, &last, &need0, &need1)) continue;
+        const bool small = im->mask_cut_w > 0 || im->mask_cut_h > 0;
+        take[j] = 1;
+        if (small || host) {
+            off_c[j] = cut_total;
+            cut_total += align_up(align_up((size_t)im->w, 16) * (need1 - need0), 256);
+        }
+        off_p[j] = plan_total;
+        plan_total += align_up(blend_plan_bytes(ctx, im->w, S.bands, S.radius), 256);
+    }
+    uint8_t *cut_arena = nullptr, *plan_arena = nullptr;
+    if (cut_total)
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_PREP_CUT, cut_total, (void **)&cut_arena)) return rc;
+    if (plan_total)
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_PREP_PLAN, plan_total, (void **)&plan_arena)) return rc;
+    if (!ctx->aux_stream) {
+        SPANO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            SPANO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_warped[b], cudaEventDisableTiming));
+            SPANO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_blended[b], cudaEventDisableTiming));
+        }
+        SPANO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_start2, cudaEventDisableTiming));
+    }
+    // the auxiliary stream starts after everything queued so far (begin's uploads, the previous step's blends)
+    SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_start2, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_start2, 0));
+    struct StreamSwap {
+        spano_ctx *c; cudaStream_t keep;
+        StreamSwap(spano_ctx *ctx_, cudaStream_t s) : c(ctx_), keep(ctx_->stream) { c->stream = s; }
+        ~StreamSwap() { c->stream = keep; }
+    } sw(ctx, ctx->aux_stream);
+    size_t ev_used = 0;
+    for (int j = 0; j < n; ++j) {
+        if (!take[j]) continue;
+        const spano_image_desc *im = images + j;
+        int first, last, need0, need1;
+        blend_rows(S, im, &first, &last, &need0, &need1);
+        const uint8_t *cut_v = nullptr;
+        size_t c_step = 0;
+        if (int rc = blend_resolve_cut(ctx, im, need0, need1, host, spano_ctx::BUF_PREP_CUT, off_c[j], &cut_v, &c_step)) return rc;
+        int *plan = nullptr;
+        if (blend_plan_bytes(ctx, im->w, S.bands, S.radius)) {
+            plan = reinterpret_cast<int *>(plan_arena + off_p[j]);
+            const BlendTile pt{nullptr, 0, cut_v, c_step, nullptr, 0, im->w, im->h, im->tl_x - S.mx, im->tl_y - S.my};
+            int k = launch_blend_plan(ctx, pt, S.bands, S.radius, S.row0, S.row1, plan);
+            if (k < 0) return k;
+        }
+        if (ev_used == ctx->event_pool.size()) {
+            cudaEvent_t e;
+            SPANO_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->event_pool.push_back(e);
+        }
+        cudaEvent_t ready = ctx->event_pool[ev_used++];
+        SPANO_CUDA(ctx, cudaEventRecord(ready, ctx->stream));
+        S.prepared.push_back({im, cut_v, c_step, plan, ready});
+    }
+    return SPANO_OK;
+}
+
 // host variant: normalise + download the canvas column runs whose last image is `idx` (idx < 0: everything left)
 int blend_flush_runs(spano_ctx *ctx, int idx)
 {
@@ -1100,49 +1238,22 @@ int blend_add_impl(spano_ctx *ctx, const spano_image_desc *im, const spano_slice
         return spano_fail(ctx, SPANO_E_INVALID, "slice rows [%d,%d) do not cover the rows the band reads [%d,%d)", slice->row0, slice->row1, need0, need1);
     if (!slice->tile || !slice->valid || slice->tile_step < (size_t)im->w * 3 || slice->valid_step < (size_t)im->w)
         return spano_fail(ctx, SPANO_E_INVALID, "slice: null pointer or step too small");
-    const bool small = im->mask_cut_w > 0 || im->mask_cut_h > 0;
-    if (int rc = check_image_args(ctx, im->mask_cut, small ? im->mask_cut_w : im->w, small ? im->mask_cut_h : im->h, im->mask_cut_step, 1, "mask_cut"))
-        return rc;
-    const size_t m_step = align_up((size_t)im->w, 16);
     const uint8_t *cut_v = nullptr;   // virtual address of mask_cut row 0 at tile size
-    size_t c_step = m_step;
-    if (small || host) {
-        uint8_t *cutbuf = nullptr;
-        if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTMASK, m_step * (need1 - need0) + 256, (void **)&cutbuf)) return rc;
-        uint8_t *cut_base = cutbuf - (size_t)need0 * m_step;
-        if (small) {
-            const uint8_t *sm = im->mask_cut;
-            size_t sm_step = im->mask_cut_step;
-            const spano_ctx::BlendSession::Staged *hit = nullptr;
-            if (host)
-                for (const auto &st : S.staged)
-                    if (st.host == im->mask_cut) { hit = &st; break; }
-            if (hit) {
-                sm = hit->dev;
-                sm_step = hit->step;
-            } else if (host) {
-                uint8_t *stage = nullptr;
-                sm_step = align_up((size_t)im->mask_cut_w, 16);
-                if (int rc = spano_reserve(ctx, spano_ctx::BUF_CUTSMALL2, sm_step * im->mask_cut_h + 256, (void **)&stage)) return rc;
-                SPANO_CUDA(ctx, cudaMemcpy2DAsync(stage, sm_step, im->mask_cut, im->mask_cut_step, (size_t)im->mask_cut_w, im->mask_cut_h,
-                                                  cudaMemcpyHostToDevice, ctx->stream));
-                sm = stage;
-            }
-            int k = launch_resize_mask(ctx, sm, im->mask_cut_w, im->mask_cut_h, sm_step, cut_base, im->w, im->h, m_step, need0, need1);
-            if (k < 0) return k;
-        } else {
-            SPANO_CUDA(ctx, cudaMemcpy2DAsync(cutbuf, m_step, im->mask_cut + (size_t)need0 * im->mask_cut_step, im->mask_cut_step, (size_t)im->w,
-                                              need1 - need0, cudaMemcpyHostToDevice, ctx->stream));
+    size_t c_step = 0;
+    const int *plan = nullptr;
+    for (const auto &pr : S.prepared)
+        if (pr.im == im) {               // prepared ahead of time (spano_*_blend_prepare)
+            SPANO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pr.ready, 0));
+            cut_v = pr.cut_v;  c_step = pr.cut_step;  plan = pr.plan;
+            break;
         }
-        cut_v = cut_base;
-    } else {
-        cut_v = im->mask_cut;
-        c_step = im->mask_cut_step;
+    if (!cut_v) {
+        if (int rc = blend_resolve_cut(ctx, im, need0, need1, host, spano_ctx::BUF_CUTMASK, 0, &cut_v, &c_step)) return rc;
     }
     StageTimer t2(ctx, 2);
     const BlendTile bt{slice->tile - (size_t)slice->row0 * slice->tile_step, slice->tile_step, cut_v, c_step,
                        slice->valid - (size_t)slice->row0 * slice->valid_step, slice->valid_step, im->w, im->h, im->tl_x - S.mx, cy};
-    int k = launch_blend_tile(ctx, bt, S.bands, S.radius, S.acc, S.cw, S.row0, S.row1);
+    int k = launch_blend_tile(ctx, bt, S.bands, S.radius, S.acc, S.cw, S.row0, S.row1, plan);
     if (k < 0) return k;
     t2.stop(k);
     if (host && S.h_canvas && im >= S.images && im < S.images + S.n_images)
@@ -1283,12 +1394,27 @@ int blend_begin_impl(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row
     if (int rc = launch_blend_clear(ctx, S.acc, canvas_w, row1 - row0)) return rc;
     t.stop(0);
     S.staged.clear();
+    S.prepared.clear();
     S.runs.clear();
     S.images = nullptr;  S.n_images = 0;  S.h_canvas = nullptr;  S.d_canvas = nullptr;
     S.open = true;
     return SPANO_OK;
 }
 } // namespace
+
+extern "C" int spano_dev_blend_prepare(spano_ctx *ctx, int n, const spano_image_desc *images, const spano_slice *slices)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return blend_prepare_impl(ctx, n, images, slices, false);
+}
+
+extern "C" int spano_blend_prepare(spano_ctx *ctx, int n, const spano_image_desc *images, const spano_slice *slices)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    return blend_prepare_impl(ctx, n, images, slices, true);
+}
 
 extern "C" int spano_dev_blend_add(spano_ctx *ctx, const spano_image_desc *im, const spano_slice *slice)
 {

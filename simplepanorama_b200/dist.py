@@ -228,6 +228,20 @@ def scatter_tile(ctx, plan: ShardPlan, j: int, desc, arena_ptrs, kind: int, foca
     ctx.check(fn(ctx.h, int(kind), C.c_float(focal), C.byref(desc), n, sl))
 
 
+def blend_prepare(ctx, plan: ShardPlan, k: int, descs, arena_ptr: int, host: bool = False):
+    """Band side, once per step after blend_begin: mask_cut up-scaling and sparsity plan of every image that touches
+    band k, on the library's auxiliary stream (overlaps the wait for the owners' tile rows)."""
+    from ._lib import Slice
+    n = len(plan.sizes)
+    arr = (Slice * n)()
+    for j in range(n):
+        s = band_slice(plan, k, j, arena_ptr)
+        if s is not None:
+            arr[j] = s
+    fn = ctx.lib.spano_blend_prepare if host else ctx.lib.spano_dev_blend_prepare
+    ctx.check(fn(ctx.h, n, descs, arr))
+
+
 def blend_add(ctx, plan: ShardPlan, k: int, j: int, descs, arena_ptr: int, host: bool = False):
     """Band side of image j of the spano_image_desc array `descs` (no-op when tile j does not touch band k)."""
     import ctypes as C

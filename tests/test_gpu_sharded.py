@@ -50,6 +50,8 @@ def _run_sharded(ctx, cfg, gains, images, plan, cuts, world, host):
         announce = host and k % 2 == 0
         dist.blend_begin(ctx, sp, k, cfg.bands, cfg.sigma, host_descs=descs if announce else None,
                          host_canvas=(out.data_ptr(), out.stride(0)) if announce else (0, 0))
+        if k % 3 != 1:     # with and without the ahead-of-time preparation (mask up-scaling + plans on the aux stream)
+            dist.blend_prepare(ctx, sp, k, descs, ptrs[k], host=host)
         for j in range(cfg.n):
             dist.blend_add(ctx, sp, k, j, descs, ptrs[k], host=host)
         if host:
