@@ -20,7 +20,8 @@
  *     after a size query (spano_warp_roi / spano_pan_dimension).
  *   - images are row-major, interleaved BGR uint8 ("8UC3"), `step` = bytes per row.
  *   - one spano_ctx per panorama object / thread; calls on one ctx are serialised by an
- *     internal mutex, different contexts may be used concurrently.
+ *     internal mutex, different contexts may be used concurrently (contexts that blend with
+ *     different (bands, sigma) on one device take turns on the per-device Gaussian tap tables).
  *   - functions named spano_dev_* take DEVICE pointers and enqueue on the context's
  *     stream without synchronising (the caller owns the stream, see spano_set_stream);
  *     the others take HOST pointers and return when the result is in host memory.

@@ -28,6 +28,7 @@
 // constant-bank operands.
 #include "spano_internal.h"
 #include <cmath>
+#include <mutex>
 #include <cstdio>
 
 // debug / measurement switch: 1 = ignore the mask_cut sparsity (every tile pixel is processed)
@@ -465,13 +466,25 @@ int launch_generic(spano_ctx *ctx, const BlendParams &P, dim3 grid)
 } // namespace
 
 // Gaussian taps for every band into constant memory (cv::getGaussianKernel, see projector_host.cpp).
-int launch_blend_setup(spano_ctx *ctx, int bands, double sigma)
+// The tap tables live in __constant__ memory, i.e. once per device and process, while contexts are per thread: the
+// tables are keyed by (bands, sigma) and guarded by a per-device mutex.  A context that needs other tables than the
+// ones loaded waits for everything in flight on the device (cudaDeviceSynchronize, under the mutex, so no blend can
+// be launched meanwhile) before it rewrites them; blend launches take the mutex around "check key + launch".
+// Contexts that blend with the same parameters -- the normal case -- never wait.
+struct TapState {
+    std::mutex mu;
+    bool valid = false;
+    int bands = 0;
+    double sigma = 0.0;
+};
+static TapState g_tap_state[64];
+
+// caller holds g_tap_state[dev].mu
+static int ensure_taps_locked(spano_ctx *ctx, int bands, double sigma)
 {
-    if (bands < 1 || bands > MAXB) return spano_fail(ctx, SPANO_E_INVALID, "bands %d not in [1,%d]", bands, MAXB);
-    if (!(sigma > 0)) return spano_fail(ctx, SPANO_E_INVALID, "sigma must be > 0");
+    TapState &T = g_tap_state[ctx->device & 63];
+    if (T.valid && T.bands == bands && T.sigma == sigma) return 0;
     const int radius = (int)std::ceil(3 * sigma);
-    if (radius < 1 || radius > MAXR)
-        return spano_fail(ctx, SPANO_E_LIMIT, "blur radius ceil(3*sigma)=%d exceeds %d", radius, MAXR);
     float host[MAXB][MAXR + 1] = {};
     float full[2 * MAXR + 1];
     const int n = 2 * radius + 1;
@@ -480,7 +493,9 @@ int launch_blend_setup(spano_ctx *ctx, int bands, double sigma)
         spano_host_gaussian_taps(n, sb, full);
         for (int k = 0; k <= radius; ++k) host[i][k] = full[radius + k];
     }
-    SPANO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_taps, host, sizeof(host), 0, cudaMemcpyHostToDevice, ctx->stream));
+    T.valid = false;
+    SPANO_CUDA(ctx, cudaDeviceSynchronize());   // nothing that reads the old tables is in flight any more
+    SPANO_CUDA(ctx, cudaMemcpyToSymbol(c_taps, host, sizeof(host), 0, cudaMemcpyHostToDevice));
     if (radius == 21) {
         float2 pairs[MAXB][44] = {};
         for (int i = 0; i < bands; ++i)
@@ -489,8 +504,23 @@ int launch_blend_setup(spano_ctx *ctx, int bands, double sigma)
                 const float lo = d >= 1 ? host[i][(d - 1) < 21 ? 21 - (d - 1) : (d - 1) - 21] : 0.f;
                 pairs[i][d] = make_float2(hi, lo);
             }
-        SPANO_CUDA(ctx, cudaMemcpyToSymbolAsync(c_tap2, pairs, sizeof(pairs), 0, cudaMemcpyHostToDevice, ctx->stream));
+        SPANO_CUDA(ctx, cudaMemcpyToSymbol(c_tap2, pairs, sizeof(pairs), 0, cudaMemcpyHostToDevice));
     }
+    T.bands = bands;  T.sigma = sigma;  T.valid = true;
+    return 0;
+}
+
+int launch_blend_setup(spano_ctx *ctx, int bands, double sigma)
+{
+    if (bands < 1 || bands > MAXB) return spano_fail(ctx, SPANO_E_INVALID, "bands %d not in [1,%d]", bands, MAXB);
+    if (!(sigma > 0)) return spano_fail(ctx, SPANO_E_INVALID, "sigma must be > 0");
+    const int radius = (int)std::ceil(3 * sigma);
+    if (radius < 1 || radius > MAXR)
+        return spano_fail(ctx, SPANO_E_LIMIT, "blur radius ceil(3*sigma)=%d exceeds %d", radius, MAXR);
+    ctx->tap_bands = bands;
+    ctx->tap_sigma = sigma;
+    std::lock_guard<std::mutex> lk(g_tap_state[ctx->device & 63].mu);
+    if (int rc = ensure_taps_locked(ctx, bands, sigma)) return rc;
     return radius;
 }
 
@@ -550,6 +580,10 @@ int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius,
     P.radius = radius;
     P.plan = plan;
     int rc = 0;
+    // the tap tables must be this context's from here until the kernel is launched (see TapState)
+    std::lock_guard<std::mutex> tap_lock(g_tap_state[ctx->device & 63].mu);
+    if (ctx->tap_bands != bands || !(ctx->tap_sigma > 0)) return spano_fail(ctx, SPANO_E_INVALID, "blend launched without launch_blend_setup");
+    if (int trc = ensure_taps_locked(ctx, ctx->tap_bands, ctx->tap_sigma)) return trc;
     const bool fast = (radius == FR) && g_force_generic != 1;
     if (fast && g_force_generic == 0) {
         int sms = 148;

@@ -75,6 +75,8 @@ struct spano_ctx {
         std::vector<Prepared> prepared;
     } bs;
     std::vector<cudaEvent_t> event_pool;   // reusable events of the prepare step
+    int tap_bands = 0;                     // Gaussian tap tables this context blends with (launch_blend_setup)
+    double tap_sigma = 0.0;
     // timers
     bool timers_on = false;
     float stage_ms[4] = {0, 0, 0, 0};

@@ -79,3 +79,36 @@ def test_sparse_blend_skips_work(ctx):
     api.multi_blend([tile], [cut], [valid], [(0, 0)], 6, 7.0, ctx)
     done, offered = ctx.blend_stats(reset=True)
     assert done == 12 * 32 * h
+
+
+def test_two_contexts_with_different_bands_concurrently(ctx):
+    """One spano_ctx per thread (one pan::panorama per viewer window): the Gaussian tap tables are per device, so two
+    contexts blending with different (bands, sigma) at the same time must not see each other's tables."""
+    import threading
+    from simplepanorama_b200 import api
+    rng = np.random.default_rng(11)
+    w, h = 700, 300
+    tile = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    cut = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    valid = np.full((h, w), 255, np.uint8)
+    args = ([tile], [cut], [valid], [(0, 0)])
+    want = {b: api.multi_blend(*args, b, 7.0, ctx) for b in (3, 6)}
+    other = api.Context(0)
+    errors = []
+
+    def worker(c, bands):
+        try:
+            for _ in range(12):
+                got = api.multi_blend(*args, bands, 7.0, c)
+                if not np.array_equal(got.view(np.uint32), want[bands].view(np.uint32)):
+                    errors.append(bands)
+        except Exception as e:   # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(ctx, 3)), threading.Thread(target=worker, args=(other, 6))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    other.close()
+    assert not errors, errors
