@@ -88,3 +88,90 @@ def test_bands_are_work_balanced():
                 tot += max(0, y1 - y0) * w
             work.append(tot)
         assert max(work) / (sum(work) / world) < 1.05, (world, work)
+
+
+# ---------------------------------------------------------------------------------------------
+# tile-sharded path: owners warp + mask their images once, every band receives only the tile rows its
+# plan says it reads (here over gloo send/recv instead of NVLink peer stores), blends its band and the
+# bands are gathered.  The compositor is the oracle; rows a band did NOT receive are poisoned, so a wrong
+# slice range in dist.plan_tile_shards shows up as a wrong canvas.
+# ---------------------------------------------------------------------------------------------
+def _sharded_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from simplepanorama_b200 import dist as sdist, synth
+    cfg = synth.config("cfg1", 0.12)
+    K, R, gains = synth.cameras(cfg)
+    bands_n, sigma = 2, 7.0
+    # geometry is host arithmetic every rank can do; pixels only by the owner
+    geo = []
+    for j in range(cfg.n):
+        K32, R32 = orc.adjusted_camera(K[j], R[j], cfg.width, cfg.height)
+        geo.append((K32, R32) + tuple(orc.warp_roi(cfg.kind, cfg.focal, K32, R32, cfg.width, cfg.height)))
+    corners = [(g[2][0], g[2][1]) for g in geo]
+    sizes = [(g[3][0], g[3][1]) for g in geo]
+    sp = sdist.plan_tile_shards(corners, sizes, world, sigma)
+    cuts = synth.seam_masks(corners, sizes)
+    # owner side
+    mine = {}
+    for j in range(cfg.n):
+        if sp.owner[j] != rank:
+            continue
+        img = synth.make_image(cfg, j, gains[j])
+        _, tile = orc.warp(cfg.kind, cfg.focal, geo[j][0], geo[j][1], img)
+        mask = orc.surrounding_mask(tile, 3)
+        mine[j] = (orc.apply_gain(tile, gains[j]), mask)
+    # exchange: rows [r0, r1) of tile j go to every band k whose plan lists them
+    rng = np.random.default_rng(100 + rank)
+    tiles, valids = [], []
+    for j in range(cfg.n):
+        w, h = sizes[j]
+        for k in range(world):
+            sl = sp.slices[k][j]
+            if sl is None:
+                continue
+            r0, r1 = sl
+            if sp.owner[j] == rank and k != rank:
+                tdist.send(torch.from_numpy(np.ascontiguousarray(mine[j][0][r0:r1])), dst=k)
+                tdist.send(torch.from_numpy(np.ascontiguousarray(mine[j][1][r0:r1])), dst=k)
+        sl = sp.slices[rank][j]
+        t = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)      # poison: rows this band was never sent
+        v = rng.integers(0, 2, (h, w), dtype=np.uint8) * 255
+        if sl is not None:
+            r0, r1 = sl
+            if sp.owner[j] == rank:
+                t[r0:r1], v[r0:r1] = mine[j][0][r0:r1], mine[j][1][r0:r1]
+            else:
+                bt = torch.empty((r1 - r0, w, 3), dtype=torch.uint8); bv = torch.empty((r1 - r0, w), dtype=torch.uint8)
+                tdist.recv(bt, src=sp.owner[j]); tdist.recv(bv, src=sp.owner[j])
+                t[r0:r1], v[r0:r1] = bt.numpy(), bv.numpy()
+        tiles.append(t); valids.append(v)
+    # band side (the oracle has no band mode: it blends everything and the band keeps its rows)
+    row0, row1 = sp.bands[rank]
+    full = orc.blend_to_u8(orc.multi_blend(tiles, cuts, valids, corners, bands_n, sigma))
+    band = torch.from_numpy(np.ascontiguousarray(full[row0:row1]))
+    canvas = sdist.gather_bands(band, sp.bands, sp.canvas_w, rank, world)
+    if rank == 0:
+        np.save(out_path, canvas.numpy())
+    # the single-process answer, from the true tiles
+    if rank == 0:
+        true_t, true_v = [], []
+        for j in range(cfg.n):
+            img = synth.make_image(cfg, j, gains[j])
+            _, tile = orc.warp(cfg.kind, cfg.focal, geo[j][0], geo[j][1], img)
+            true_v.append(orc.surrounding_mask(tile, 3)); true_t.append(orc.apply_gain(tile, gains[j]))
+        np.save(out_path + ".ref.npy", orc.blend_to_u8(orc.multi_blend(true_t, cuts, true_v, corners, bands_n, sigma)))
+    tdist.barrier()
+    tdist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_tile_sharded_exchange_world2(tmp_path):
+    world = 2
+    out = str(tmp_path / "sharded.npy")
+    mp.spawn(_sharded_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got, ref = np.load(out), np.load(out + ".ref.npy")
+    assert got.shape == ref.shape and np.array_equal(got, ref)
