@@ -309,23 +309,28 @@ def run_ours(args):
                               host_canvas=(h_canvas.data_ptr(), h_canvas.stride(0)))
             # everything that does not depend on the owners' data (mask up-scaling, sparsity plans) starts now
             sdist.blend_prepare(ctx, sp, rank, descs, arenas.own, host=host)
-        tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)   # every rank has finished blending the previous step's arenas
-        pe[1].record(stream)
+        # All barriers live on the OWNER stream: "every rank has finished blending the previous step" (its arenas may be
+        # overwritten), then per group of rounds "every owner has written this group".  The band side only waits for
+        # the local event behind each of them, so a rank never waits for another rank's blends -- owners run ahead,
+        # bands blend as their rows arrive (on many-row panoramas the images of one round all land in the same bands).
         aux.wait_stream(stream)
-        pe[4].record(aux)
         evs = []
-        for g in groups:
-            for rnd in g:
-                for j in rnd:
-                    if sp.owner[j] == rank:
-                        sdist.scatter_tile(ctx_s, sp, j, descs[j], arenas.ptrs, cfg.kind, cfg.focal, host=host)
-            ev = torch.cuda.Event()
-            ev.record(aux)
-            evs.append(ev)
-        pe[5].record(aux)
+        with torch.cuda.stream(aux):
+            tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)
+            pe[1].record(aux)
+            pe[4].record(aux)
+            for g in groups:
+                for rnd in g:
+                    for j in rnd:
+                        if sp.owner[j] == rank:
+                            sdist.scatter_tile(ctx_s, sp, j, descs[j], arenas.ptrs, cfg.kind, cfg.focal, host=host)
+                tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)   # the rounds of this group are in every arena
+                ev = torch.cuda.Event()
+                ev.record(aux)
+                evs.append(ev)
+            pe[5].record(aux)
         for t, g in enumerate(groups):
             stream.wait_event(evs[t])
-            tdist.all_reduce(tok, op=tdist.ReduceOp.MAX)   # the rounds of group t are in every arena
             if have:
                 for rnd in g:
                     for j in rnd:
