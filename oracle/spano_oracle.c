@@ -20,6 +20,10 @@
  *   - util::get_pan_dimension                                src/system/_util.cpp:204-231
  *   - stitch_parameters::blend (MULTI_BLEND branch)          src/classes/_panorama.cpp:242-249
  *   - sten_proj::disk_reproj / get_bounding_box              src/math/_projection.cpp:132-294
+ *   - cv::resize of mask_cut, test::adjust_intensity         src/classes/_panorama.cpp:329-335, src/test/_test.cpp:110-122
+ *   - dcut::distance_transform / dcut::dist_cut              src/math/_distance_cut.cpp:7-73
+ *   - blnd::simple_blend / blnd::no_blend                    src/math/_blending.cpp:83-182
+ *   - gain::get_overlapp_intensity                           src/math/_gain_compensation.cpp:7-75
  *
  * PARITY PIN: the reference has no tests or golden vectors.  This
  * restatement is pinned against OpenCV 4.13.0 (python cv2, the only OpenCV in the build
