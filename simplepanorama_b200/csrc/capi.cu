@@ -769,8 +769,11 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         const int j = use[idx], b = idx & 1;
         cudaStream_t cs = ctx->copy_stream;
         if (idx >= 2) SPANO_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_free[b], 0));
-        SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_srcbuf[b], align_up((size_t)im[j].src_w * 3, 16), im[j].src_bgr, im[j].src_step,
-                                          (size_t)im[j].src_w * 3, im[j].src_h, cudaMemcpyHostToDevice, cs));
+        const size_t row_bytes = (size_t)im[j].src_w * 3, dpitch = align_up(row_bytes, 16);
+        if (im[j].src_step == row_bytes && dpitch == row_bytes)   // contiguous on both sides: one linear copy
+            SPANO_CUDA(ctx, cudaMemcpyAsync(d_srcbuf[b], im[j].src_bgr, row_bytes * im[j].src_h, cudaMemcpyHostToDevice, cs));
+        else
+            SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_srcbuf[b], dpitch, im[j].src_bgr, im[j].src_step, row_bytes, im[j].src_h, cudaMemcpyHostToDevice, cs));
         if (im[j].mask_cut_w > 0 || im[j].mask_cut_h > 0)   // preview-scale mask: resized on the device after the upload
             SPANO_CUDA(ctx, cudaMemcpy2DAsync(d_cutsmall[b], align_up((size_t)im[j].mask_cut_w, 16), im[j].mask_cut, im[j].mask_cut_step,
                                               (size_t)im[j].mask_cut_w, im[j].mask_cut_h, cudaMemcpyHostToDevice, cs));
