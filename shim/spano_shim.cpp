@@ -8,7 +8,10 @@
 //   proj::get_proj_parameters                                                     src/math/_projection.cpp:422-454
 //   sten_proj::disk_reproj                                                        src/math/_projection.cpp:193-294
 //   blnd::createSurroundingMask                                                   src/math/_blending.cpp:278-324
-//   blnd::multi_blend                                                             src/math/_blending.cpp:186-252
+//   blnd::multi_blend, simple_blend, no_blend                                     src/math/_blending.cpp:83-252
+//   dcut::distance_transform, dcut::dist_cut                                      src/math/_distance_cut.cpp:7-73
+//   gain::get_overlapp_intensity                                                  src/math/_gain_compensation.cpp:7-75
+//   test::adjust_intensity                                                        src/test/_test.cpp:110-122
 //
 // Each body only converts cv::Mat / Eigen arguments to pointers + sizes and forwards to the C ABI
 // (include/spano.h).  Errors come back as status codes and are re-thrown as std::runtime_error, the
@@ -23,6 +26,9 @@
 
 #include "_projection.h" // reference headers: proj::, blnd::, util::
 #include "_blending.h"
+#include "_distance_cut.h"      // dcut::
+#include "_gain_compensation.h" // gain::OverlapInfo
+#include "_test.h"              // test::adjust_intensity
 #include "spano.h"
 
 namespace {
