@@ -70,6 +70,31 @@ __global__ void __launch_bounds__(256) resize_linear_u8_kernel(const uint8_t *sr
     }
     const int y_first = row_begin + blockIdx.y * RESIZE_ROWS;
     const bool vec = dx0 + 4 <= dw && ((((uintptr_t)dst) | dstep) & 3) == 0;
+    {
+        // whole-thread early out: the source taps of all RESIZE_ROWS x 4 pixels lie in a small rectangle (both tables
+        // are monotonic); if every byte of it is 0 -- most of a seam mask -- the pixels are 0
+        const int y_last = min(y_first + RESIZE_ROWS, row_end) - 1;
+        if (y_last < y_first) return;
+        const int sy0 = min(max(yt[y_first].ofs, 0), sh - 1), sy1 = min(max(yt[y_last].ofs + 1, 0), sh - 1);
+        const int sx0 = ex[0].ofs, sx1 = x1[3];
+        uint32_t any = 1;
+        if ((sy1 - sy0 + 1) * (sx1 - sx0 + 1) <= 64) {   // (an up-scaling: a handful of bytes; skip the test when shrinking)
+            any = 0;
+            for (int y = sy0; y <= sy1; ++y) {
+                const uint8_t *rp = src + (size_t)y * sstep;
+                for (int x = sx0; x <= sx1; ++x) any |= __ldg(rp + x);
+            }
+        }
+        if (!any) {
+            for (int dy = y_first; dy <= y_last; ++dy) {
+                uint8_t *d = dst + (size_t)dy * dstep + dx0;
+                if (vec) *reinterpret_cast<uint32_t *>(d) = 0u;
+                else
+                    for (int i = 0; i < 4 && dx0 + i < dw; ++i) d[i] = 0;
+            }
+            return;
+        }
+    }
 #pragma unroll 4
     for (int r = 0; r < RESIZE_ROWS; ++r) {
         const int dy = y_first + r;
