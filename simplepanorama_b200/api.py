@@ -27,7 +27,7 @@ from ._lib import (CYLINDRICAL, OUT_F32, OUT_U8, SPHERICAL, STEREOGRAPHIC, Image
 __all__ = [
     "SPHERICAL", "CYLINDRICAL", "STEREOGRAPHIC", "Context", "ProjData", "SpanoError", "adjusted_camera", "warp_roi",
     "project", "get_proj_parameters", "create_surrounding_mask", "validity_mask", "apply_gain", "get_pan_dimension",
-    "multi_blend", "blend", "return_full", "default_context", "distance_transform", "dist_cut", "simple_blend", "no_blend", "get_overlapp_intensity",
+    "multi_blend", "blend", "return_full", "default_context", "distance_transform", "dist_cut", "simple_blend", "no_blend", "get_overlapp_intensity", "stitch_blend", "NO_BLEND", "SIMPLE_BLEND", "MULTI_BLEND",
 ]
 
 
@@ -306,6 +306,23 @@ def multi_blend(images, masks, masks_orig, top_lefts, bands: int, sigma: float, 
 def blend(images, masks, masks_orig, top_lefts, bands: int, sigma: float, ctx: Context | None = None):
     """stitch_parameters::blend with conf.blend == MULTI_BLEND -> CV_8UC3 canvas."""
     return _blend_call(images, masks, masks_orig, top_lefts, bands, sigma, OUT_U8, ctx)
+
+
+NO_BLEND, SIMPLE_BLEND, MULTI_BLEND = 0, 1, 2   # pan::Blending (src/classes/_panorama.h:34-36)
+
+
+def stitch_blend(imgs, msks_cut, msks, corners, blend_mode: int = MULTI_BLEND, bands: int = 3, sigma: float = 7.0,
+                 cut: bool = True, ctx: Context | None = None):
+    """stitch_parameters::blend(blend_data, config) (src/classes/_panorama.cpp:220-256): the dispatch on conf.blend.
+    NO_BLEND copies through msks_cut when conf.cut / conf.cut_seams is set, else through msks; SIMPLE_BLEND feathers
+    with msks; MULTI_BLEND is multi_blend(imgs, msks_cut, msks) * 255 -> CV_8UC3."""
+    if blend_mode == NO_BLEND:
+        return no_blend(imgs, msks_cut if cut else msks, corners, ctx)
+    if blend_mode == SIMPLE_BLEND:
+        return simple_blend(imgs, msks, corners, ctx)
+    if blend_mode == MULTI_BLEND:
+        return blend(imgs, msks_cut, msks, corners, bands, sigma, ctx)
+    raise SpanoError(_lib.E_INVALID, f"unknown blend mode {blend_mode}")   # the reference returns an empty cv::Mat here
 
 
 def disk_reproj_size(corners, sizes, ansatz, radius: float, quadratic: bool = True, ctx: Context | None = None):

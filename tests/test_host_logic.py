@@ -164,3 +164,12 @@ def test_tile_shard_plan_covers_every_band():
                 if sp.slices[k][j] is not None:
                     covered[sp.slices[k][j][0]:sp.slices[k][j][1]] = True
             assert covered.all()
+
+
+def test_stitch_blend_dispatch_rejects_unknown_mode(spano_lib):
+    """stitch_parameters::blend's switch (src/classes/_panorama.cpp:220-256): an unknown mode is an error here (the
+    reference hands back an empty cv::Mat); the argument check needs no device."""
+    from simplepanorama_b200 import api
+    assert (api.NO_BLEND, api.SIMPLE_BLEND, api.MULTI_BLEND) == (0, 1, 2)
+    with pytest.raises(api.SpanoError):
+        api.stitch_blend([], [], [], [], blend_mode=7)
