@@ -173,3 +173,29 @@ def test_stitch_blend_dispatch_rejects_unknown_mode(spano_lib):
     assert (api.NO_BLEND, api.SIMPLE_BLEND, api.MULTI_BLEND) == (0, 1, 2)
     with pytest.raises(api.SpanoError):
         api.stitch_blend([], [], [], [], blend_mode=7)
+
+
+def test_ctypes_structs_match_the_header(tmp_path):
+    """The ctypes mirrors of spano_image_desc / spano_slice / spano_overlap_info have the C layout of include/spano.h
+    (a C compiler is the judge)."""
+    import subprocess
+    fields = {"spano_image_desc": (L.ImageDesc, ["src_bgr", "src_w", "src_h", "src_step", "K", "R", "gain", "mask_cut", "mask_cut_step",
+                                                 "tl_x", "tl_y", "w", "h", "valid_mask", "valid_mask_step", "mask_cut_w", "mask_cut_h",
+                                                 "intensity", "intensity_w", "intensity_h", "intensity_step"]),
+              "spano_slice": (L.Slice, ["row0", "row1", "tile", "tile_step", "valid", "valid_step"]),
+              "spano_overlap_info": (L.OverlapInfo, ["i", "j", "area", "I_i", "I_j"])}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "spano.h"', 'int main(void) {']
+    for name, (_, fs) in fields.items():
+        src.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for f in fs:
+            src.append(f'  printf("{name}.{f} %zu\\n", offsetof({name}, {f}));')
+    src += ['  return 0;', '}']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(c)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for name, (cls, fs) in fields.items():
+        assert int(out[name]) == C.sizeof(cls), name
+        for f in fs:
+            assert int(out[f"{name}.{f}"]) == getattr(cls, f).offset, f"{name}.{f}"
