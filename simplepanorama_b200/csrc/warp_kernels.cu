@@ -9,8 +9,8 @@
 //
 // Arithmetic contract (what makes the result match OpenCV):
 //   * mapBackward in float32 with IEEE mul/add/div (no FMA contraction: __fmul_rn/__fadd_rn/__fdiv_rn)
-//     and CUDA's accurate sinf/cosf/atan2f/atanf/sqrtf (<= 2 ulp; glibc's differ in the last ulp
-//     for a small fraction of arguments, which can move a sample by one 1/32-px bin).
+//     and sinf/cosf/atan2f/atanf evaluated with the host libm's own arithmetic (glibc_trig.cuh: bit-identical
+//     to glibc for every float, checked exhaustively), so the maps equal cv2's buildMaps bit for bit.
 //   * sampling is OpenCV's 8-bit fixed point: sx = cvRound(32 x), weights (32-fy)(32-fx)*32,
 //     D = (sum + 2^14) >> 15.  Evaluated separably with exact integers:
 //     h = (32-fx) p0 + fx p1 (one dp4a per channel and row), D = ((32-fy) h_top + fy h_bot + 512) >> 10.
@@ -23,6 +23,7 @@
 // row): sin/cos are evaluated once per tile column / row into small tables, so the per-pixel work
 // is 9 mul/add + 2 div + the integer sampler.
 #include "spano_internal.h"
+#include "glibc_trig.cuh"
 
 namespace {
 
@@ -73,7 +74,7 @@ __global__ void warp_tables_kernel(float scale, int tl_x, int tl_y, int w, int h
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < w) {
         const float u = __fdiv_rn((float)(i + tl_x), scale);
-        const float su = sinf(u), cu = cosf(u);
+        const float su = gtrig::sinf_glibc(u), cu = gtrig::cosf_glibc(u);
         if (KIND == SPANO_CYLINDRICAL) {
             col[i] = __fmul_rn(m[0], su);           col[wp + i] = __fmul_rn(m[2], cu);
             col[2 * wp + i] = __fmul_rn(m[3], su);  col[3 * wp + i] = __fmul_rn(m[5], cu);
@@ -89,8 +90,8 @@ __global__ void warp_tables_kernel(float scale, int tl_x, int tl_y, int w, int h
             row[i] = __fmul_rn(m[1], v);  row[h + i] = __fmul_rn(m[4], v);  row[2 * h + i] = __fmul_rn(m[7], v);
         } else {
             const float t = __fsub_rn(kPiF, v);
-            const float y_ = cosf(t);
-            row[i] = sinf(t);
+            const float y_ = gtrig::cosf_glibc(t);
+            row[i] = gtrig::sinf_glibc(t);
             row[h + i] = __fmul_rn(m[1], y_);  row[2 * h + i] = __fmul_rn(m[4], y_);  row[3 * h + i] = __fmul_rn(m[7], y_);
         }
     }
@@ -221,14 +222,14 @@ __device__ __forceinline__ void project_ray(const WarpParams &P, int u_i, int v_
     } else {
         const float u = __fdiv_rn((float)(u_i + P.tl_x), P.scale);
         const float v = __fdiv_rn((float)(v_i + P.tl_y), P.scale);
-        const float az = atan2f(v, u);
+        const float az = gtrig::atan2f_glibc(v, u);
         const float r = sqrtf(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)));
-        const float pol = __fmul_rn(2.f, atanf(__fdiv_rn(1.f, r)));
+        const float pol = __fmul_rn(2.f, gtrig::atanf_glibc(__fdiv_rn(1.f, r)));
         const float t = __fsub_rn(kPiF, pol);
-        const float sinv = sinf(t);
-        x_ = __fmul_rn(sinv, sinf(az));
-        const float y_ = cosf(t);
-        z_ = __fmul_rn(sinv, cosf(az));
+        const float sinv = gtrig::sinf_glibc(t);
+        x_ = __fmul_rn(sinv, gtrig::sinf_glibc(az));
+        const float y_ = gtrig::cosf_glibc(t);
+        z_ = __fmul_rn(sinv, gtrig::cosf_glibc(az));
         my1 = __fmul_rn(m[1], y_);  my4 = __fmul_rn(m[4], y_);  my7 = __fmul_rn(m[7], y_);
     }
     X = __fadd_rn(__fadd_rn(__fmul_rn(m[0], x_), my1), __fmul_rn(m[2], z_));
