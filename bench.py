@@ -478,11 +478,11 @@ def run_ours(args):
     # seam masks are dense (e.g. all-soft masks); reported next to the headline, never instead of it
     dense = None
     if world == 1:
-        lib.spano_debug_blend_dense(1)
+        ctx.set_option(ctx.OPT_BLEND_DENSE, 1)
         ms_d, _, _ = timed(step_dev, 2, 1)
-        lib.spano_debug_blend_dense(0)
+        ctx.set_option(ctx.OPT_BLEND_DENSE, 0)
         dense = {"value": canvas_mpx / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d,
-                 "note": "blend sparsity disabled (spano_debug_blend_dense): all tile pixels filtered"}
+                 "note": "blend sparsity disabled (SPANO_OPT_BLEND_DENSE): all tile pixels filtered"}
 
     # checksum of the finished canvas (rank 0): identical at every N -- the multi-GPU canvas is bit-identical to the
     # single-GPU one

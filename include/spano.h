@@ -20,8 +20,8 @@
  *     after a size query (spano_warp_roi / spano_pan_dimension).
  *   - images are row-major, interleaved BGR uint8 ("8UC3"), `step` = bytes per row.
  *   - one spano_ctx per panorama object / thread; calls on one ctx are serialised by an
- *     internal mutex, different contexts may be used concurrently (contexts that blend with
- *     different (bands, sigma) on one device take turns on the per-device Gaussian tap tables).
+ *     internal mutex, different contexts may be used concurrently and share no mutable state
+ *     (the Gaussian taps of a blend travel in the parameters of its kernel launches).
  *   - functions named spano_dev_* take DEVICE pointers and enqueue on the context's
  *     stream without synchronising (the caller owns the stream, see spano_set_stream);
  *     the others take HOST pointers and return when the result is in host memory.
@@ -71,6 +71,14 @@ int spano_set_stream(spano_ctx *ctx, void *cuda_stream);
 int spano_sync(spano_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 long long spano_launch_count(spano_ctx *ctx);
+/* Per-context options (measurement and cross-check switches; they never change a result beyond the tolerances
+ * stated: BLEND_DENSE is bit-identical, BLEND_KERNEL selects a kernel with a different summation order).
+ *   SPANO_OPT_BLEND_DENSE  1: the multiband blend filters every tile pixel instead of skipping those whose whole
+ *                             window of mask_cut is zero (see spano_blend_stats); default 0
+ *   SPANO_OPT_BLEND_KERNEL 1: always the generic-radius blend kernel, also for sigma = 7; default 0            */
+#define SPANO_OPT_BLEND_DENSE 1
+#define SPANO_OPT_BLEND_KERNEL 2
+int spano_set_option(spano_ctx *ctx, int option, int value);
 
 /* ---- a3: projector geometry (host arithmetic, bit-exact with OpenCV's warpers) -----
  * Replaces cv::detail::RotationWarperBase::detectResultRoi[ByBorder] and

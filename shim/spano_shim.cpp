@@ -18,8 +18,8 @@
 // exception type the reference already uses on this path (_blending.cpp:86); the worker thread's
 // try/catch (src/ui/_image_viewer.cpp:535-550) keeps working.
 //
-// NOT compiled in the build container (no OpenCV C++ headers / Eigen there); it needs the
-// reference's own include set.
+// Not BUILT in the build container (no OpenCV C++ headers / Eigen there), but type-checked there against the reference's
+// real headers with stand-ins for <opencv2/...> and <Eigen/...> (tests/test_shim_compiles.py).
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -48,6 +48,10 @@ void check(int rc)
 {
     if (rc != SPANO_OK) throw std::runtime_error(std::string("spano: ") + spano_last_error(ctx()));
 }
+
+// get_proj_parameters -> projector->project(): when set, the project() bodies below also produce the validity mask
+// (createSurroundingMask + 3 erosions) in the same device pass instead of a second upload of the warped tile
+thread_local cv::Mat *g_mask_request = nullptr;
 
 struct Camera { float K[9], R[9]; };
 
@@ -81,11 +85,11 @@ namespace proj {
 
 // `focal` is the private member set by the constructor / change_focal (unchanged in _projection.h)
 warped spherical_proj::project(const Eigen::MatrixXd &R, const Eigen::MatrixXd &K, const cv::Mat &img) const
-{ return warp_with(SPANO_SPHERICAL, focal, R, K, img, nullptr); }
+{ return warp_with(SPANO_SPHERICAL, focal, R, K, img, g_mask_request); }
 warped cylindrical_proj::project(const Eigen::MatrixXd &R, const Eigen::MatrixXd &K, const cv::Mat &img) const
-{ return warp_with(SPANO_CYLINDRICAL, focal, R, K, img, nullptr); }
+{ return warp_with(SPANO_CYLINDRICAL, focal, R, K, img, g_mask_request); }
 warped sten_proj::project(const Eigen::MatrixXd &R, const Eigen::MatrixXd &K, const cv::Mat &img) const
-{ return warp_with(SPANO_STEREOGRAPHIC, focal, R, K, img, nullptr); }
+{ return warp_with(SPANO_STEREOGRAPHIC, focal, R, K, img, g_mask_request); }
 
 proj_data get_proj_parameters(const std::vector<cv::Mat> &images, std::vector<Eigen::MatrixXd> &R, std::vector<Eigen::MatrixXd> &K,
                               std::vector<double> &con, std::shared_ptr<projection> projector, bool get_masks)
@@ -93,12 +97,17 @@ proj_data get_proj_parameters(const std::vector<cv::Mat> &images, std::vector<Ei
     proj_data out;
     for (size_t i = 0; i < images.size(); ++i) {
         if (!(con[i] > 0)) continue;
-        warped w = projector->project(R[i], K[i], images[i]);
-        if (get_masks) {
-            cv::Mat m(w.imgs.rows, w.imgs.cols, CV_8UC1);
-            check(spano_surrounding_mask(ctx(), w.imgs.data, w.imgs.cols, w.imgs.rows, w.imgs.step, 3, m.data, m.step));
-            out.msks.push_back(m);
+        cv::Mat m;
+        struct Request {   // reset on every exit path, exceptions included
+            explicit Request(cv::Mat *p) { g_mask_request = p; }
+            ~Request() { g_mask_request = nullptr; }
+        };
+        warped w;
+        {
+            Request rq(get_masks ? &m : nullptr);
+            w = projector->project(R[i], K[i], images[i]);
         }
+        if (get_masks) out.msks.push_back(m);
         out.imgs.push_back(w.imgs);
         out.corners.push_back(w.corners);
     }

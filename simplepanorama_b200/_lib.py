@@ -100,6 +100,7 @@ SYMBOLS = {
     "spano_dev_blend_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "spano_blend_add": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.POINTER(Slice)]),
     "spano_blend_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "spano_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "spano_timers_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "spano_timers_reset": (C.c_int, [C.c_void_p]),
     "spano_timers_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
@@ -124,10 +125,6 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    lib.spano_debug_force_generic.restype = None
-    lib.spano_debug_force_generic.argtypes = [C.c_int]
-    lib.spano_debug_blend_dense.restype = None
-    lib.spano_debug_blend_dense.argtypes = [C.c_int]
     _lib = lib
     return lib
 

@@ -23,6 +23,9 @@ HEADERS = ["spano_internal.h", os.path.join("..", "..", "include", "spano.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+    # host code inside the .cu files (e.g. the disk_reproj geometry that decides integer tile corners) must round like the
+    # reference's scalar code: no FMA contraction on FMA-default hosts either
+    "-Xcompiler", "-ffp-contract=off",
 ]
 # host geometry must round like OpenCV's SSE3-baseline build: no FMA contraction
 CXX_FLAGS = ["-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-pthread"]

@@ -13,38 +13,32 @@
 //   out = color / clamp(alpha) / float(255/B)        [integer division]      (-> x255 -> u8)
 // BORDER_REFLECT applies at the borders of each warped TILE.
 //
-// Kernel structure: per tile, one CTA owns a 32 x BH block of tile pixels and runs four channel
-// phases (mask_cut, B, G, R).  Each phase stages the u8 channel (+ halo, reflect resolved) as
-// float in shared memory, runs the horizontal pass for ALL B sigmas at once (the symmetric
-// pair sums x[-k]+x[k] are shared by every sigma), keeps the B row-filtered planes in shared
-// memory, and runs the vertical pass from shared memory into registers (8 rows per thread, each
-// loaded value feeds up to 8 accumulators).  Band algebra, weights, validity zeroing and the
-// sum over bands happen in registers; the only HBM traffic is the u8 inputs (5 B/tile-px, halo
-// re-reads come from L2) and one float4 read-modify-write of the canvas accumulator per tile
-// pixel.  No level ever round-trips to HBM.
+// Kernels: the marching-strip kernel of blend_march.cuh (radius 21, i.e. sigma = 7: the reference default and every
+// BASELINE config) and a block-tiled kernel for any other radius <= 32 (also the on-device cross-check of the first).
+// Band algebra, weights, validity zeroing and the sum over bands happen in registers / shared memory; the only HBM
+// traffic is the u8 inputs (5 B/tile-px, halo re-reads come from L2) and one float4 read-modify-write of the canvas
+// accumulator per tile pixel.  No level ever round-trips to HBM.
 //
-// This stage is bound by the FP32 FMA pipe, not by HBM (4 ch x B x 2 x 43 MACs per tile pixel
-// against ~37 B): see DESIGN.md.  Taps live in constant memory so the FMAs take them as
-// constant-bank operands.
+// This stage is bound by the FP32 FMA pipe, not by HBM (4 ch x B x 2 x 43 MACs per tile pixel against ~37 B): see
+// DESIGN.md.  The Gaussian taps travel in the kernel parameters (constant bank), one set per launch: contexts share no
+// mutable device state.
 #include "spano_internal.h"
 #include <cmath>
-#include <mutex>
+#include <cstring>
 #include <cstdio>
-
-// debug / measurement switch: 1 = ignore the mask_cut sparsity (every tile pixel is processed)
-static int g_blend_dense = 0;
-extern "C" void spano_debug_blend_dense(int on) { g_blend_dense = on; }
+#include <mutex>
 
 namespace {
 
 constexpr int MAXB = SPANO_MAX_BANDS;
 constexpr int MAXR = SPANO_BLUR_RADIUS_MAX;
 
-// c_taps[b][k] = tap at distance k from the centre for band b's sigma (k = 0..radius)
-__constant__ float c_taps[MAXB][MAXR + 1];
-// radius-21 vertical pass, two output rows per packed FMA: c_tap2[b][d] = {T[d], T[d-1]} with T[d] = tap at
-// |d - 21| for d in 0..42 and T[-1] = T[43] = 0 (the tap pair that rows o, o+1 apply to input row o + d)
-__constant__ float2 c_tap2[MAXB][44];
+// Tap slots of the marching kernel (see blend_march.cuh): c_taps[s][b][k] = tap of band b at distance k from the
+// centre; c_tap2[s][b][d] = {T[d], T[d-1]} with T[d] = tap at |d - 21| for d in 0..42 and T[-1] = T[43] = 0 (the tap
+// pair that output rows o, o+1 of the vertical pass apply to input row o + d).
+constexpr int TAP_SLOTS = 8;
+__constant__ __align__(16) float c_taps[TAP_SLOTS][MAXB][24];
+__constant__ __align__(16) float2 c_tap2[TAP_SLOTS][MAXB][44];
 
 struct BlendParams {
     const uint8_t *tile;  size_t tile_step;
@@ -57,6 +51,7 @@ struct BlendParams {
     int ax, ay;        // tile corner relative to acc origin (canvas x, canvas y - row0)
     int radius;
     const int *plan = nullptr; // marching kernel: plan made beforehand (launch_blend_plan), else made at launch
+    float taps[MAXB][MAXR + 1]; // taps[b][k] = tap of band b at distance k from the centre (generic kernel)
 };
 
 // cv::borderInterpolate(p, len, BORDER_REFLECT)
@@ -78,146 +73,7 @@ __device__ __forceinline__ float load_channel(const BlendParams &P, int ch, int 
     return (float)__ldg(P.tile + (size_t)y * P.tile_step + (size_t)x * 3 + (ch - 1));
 }
 
-// ---------------------------------------------------------------------------------------------
-// Fast path: radius 21 (sigma = 7, the reference default and every BASELINE config).
-// ---------------------------------------------------------------------------------------------
-constexpr int FR = 21;           // radius
-constexpr int FBW = 32;          // block width (one warp = one row of the block)
-constexpr int FINP = FBW + 2 * FR + 2;   // 76: staged row pitch (floats), multiple of 4 for LDS.128
-constexpr int FCH = 8;           // output rows per thread in the vertical pass
-
-// block height: the B row-filtered planes + the B weight planes must fit in 227 KB
-template <int B> struct FastCfg {
-    static constexpr int BH = (B <= 7) ? 64 : 32;
-    static constexpr int ROWS = BH + 2 * FR;          // staged / row-filtered rows
-    static constexpr int THREADS = FBW * (BH / FCH);  // 256 or 128
-};
-
-template <int B>
-struct FastSmem {
-    float in[FastCfg<B>::ROWS][FINP];
-    float row[B][FastCfg<B>::ROWS][FBW];
-    float wgt[B][FastCfg<B>::BH][FBW];   // W_b of the block's pixels, kept across the colour phases
-};
-
-template <int B>
-__global__ void __launch_bounds__(FastCfg<B>::THREADS, 1) blend_fast_kernel(const BlendParams P)
-{
-    constexpr int FBH = FastCfg<B>::BH, FROWS = FastCfg<B>::ROWS, FTHREADS = FastCfg<B>::THREADS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FastSmem<B> &S = *reinterpret_cast<FastSmem<B> *>(smem_raw);
-
-    const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * FBW;                 // tile x of block column 0
-    const int ty0 = P.ty_begin + blockIdx.y * FBH;    // tile y of block row 0
-    const int cx = tid & 31;                          // my column in the vertical pass
-    const int cr0 = (tid >> 5) * FCH;                 // my first block row in the vertical pass
-
-    float contrib[3][FCH];
-    float wsum[FCH];
-
-    // validity of my output pixels
-    bool ok[FCH];
-#pragma unroll
-    for (int o = 0; o < FCH; ++o) {
-        const int x = tx0 + cx, y = ty0 + cr0 + o;
-        ok[o] = (x < P.w) && (y < P.ty_end);
-    }
-
-#pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
-        __syncthreads(); // previous phase's vertical pass is done with S
-        // ---- stage channel + halo as float, BORDER_REFLECT resolved against the tile ----
-        for (int i = tid; i < FROWS * (FBW + 2 * FR); i += FTHREADS) {
-            const int r = i / (FBW + 2 * FR), c = i - r * (FBW + 2 * FR);
-            const int y = reflect_idx(ty0 - FR + r, P.h);
-            const int x = reflect_idx(tx0 - FR + c, P.w);
-            S.in[r][c] = load_channel(P, ch, x, y);
-        }
-        __syncthreads();
-        // ---- horizontal pass, all sigmas at once: item = (row, group of 4 columns) ----
-#pragma unroll 1
-        for (int item = tid; item < FROWS * (FBW / 4); item += FTHREADS) {
-            const int r = item >> 3, g = item & 7;
-            float v[48];
-            const float4 *src = reinterpret_cast<const float4 *>(&S.in[r][4 * g]);
-#pragma unroll
-            for (int q = 0; q < 12; ++q) {
-                const float4 t = src[q];
-                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-            }
-            float out[B][4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float pair[FR + 1];
-                pair[0] = v[j + FR];
-#pragma unroll
-                for (int k = 1; k <= FR; ++k) pair[k] = v[j + FR - k] + v[j + FR + k];
-#pragma unroll
-                for (int b = 0; b < B; ++b) {
-                    float a = c_taps[b][0] * pair[0];
-#pragma unroll
-                    for (int k = 1; k <= FR; ++k) a = fmaf(c_taps[b][k], pair[k], a);
-                    out[b][j] = a;
-                }
-            }
-#pragma unroll
-            for (int b = 0; b < B; ++b)
-                *reinterpret_cast<float4 *>(&S.row[b][r][4 * g]) = make_float4(out[b][0], out[b][1], out[b][2], out[b][3]);
-        }
-        __syncthreads();
-        // ---- vertical pass from shared memory + band algebra in registers ----
-        float cur[FCH]; // G_b of the previous sigma (colour phases)
-#pragma unroll 1
-        for (int b = 0; b < B; ++b) {
-            float a[FCH];
-#pragma unroll
-            for (int o = 0; o < FCH; ++o) a[o] = 0.f;
-            const float *tp = c_taps[b];
-#pragma unroll
-            for (int i = 0; i < FCH + 2 * FR; ++i) {
-                const float val = S.row[b][cr0 + i][cx];
-#pragma unroll
-                for (int o = 0; o < FCH; ++o) {
-                    const int k = i - o; // tap index 0..42
-                    if (k >= 0 && k <= 2 * FR) a[o] = fmaf(tp[k < FR ? FR - k : k - FR], val, a[o]);
-                }
-            }
-            if (ch == 0) {
-#pragma unroll
-                for (int o = 0; o < FCH; ++o) {
-                    bool keep = false;
-                    if (ok[o]) keep = __ldg(P.valid + (size_t)(ty0 + cr0 + o) * P.valid_step + (tx0 + cx)) == 255;
-                    const float wv = keep ? a[o] * (float)(1.0 / 255.0) : 0.f;
-                    S.wgt[b][cr0 + o][cx] = wv;   // only this thread ever touches this element
-                    wsum[o] = (b == 0) ? wv : wsum[o] + wv;
-                }
-            } else {
-                float *cc = contrib[ch - 1];
-#pragma unroll
-                for (int o = 0; o < FCH; ++o) {
-                    if (b == 0) cc[o] = (B > 1) ? a[o] * S.wgt[0][cr0 + o][cx] : 0.f;
-                    else if (b >= 2) cc[o] = fmaf(cur[o] - a[o], S.wgt[b - 1][cr0 + o][cx], cc[o]); // band b-1 = G_{b-1} - G_b
-                    if (b == B - 1) {
-                        const float I = S.in[cr0 + o + FR][cx + FR];
-                        cc[o] = fmaf(I - a[o], S.wgt[B - 1][cr0 + o][cx], cc[o]);                 // band B-1 = I - G_{B-1}
-                    }
-                    cur[o] = a[o];
-                }
-            }
-        }
-    }
-    // ---- accumulate into the canvas (one float4 read-modify-write per tile pixel) ----
-#pragma unroll
-    for (int o = 0; o < FCH; ++o) {
-        if (!ok[o]) continue;
-        const int x = tx0 + cx, y = ty0 + cr0 + o;
-        float4 *q = P.acc + (size_t)(P.ay + y) * P.canvas_w + (P.ax + x);
-        float4 t = *q;
-        t.x += contrib[0][o]; t.y += contrib[1][o]; t.z += contrib[2][o]; t.w += wsum[o];
-        *q = t;
-    }
-}
+constexpr int FR = 21;           // radius of the marching kernel
 
 #include "blend_march.cuh"
 
@@ -229,7 +85,7 @@ constexpr int GB = 32;
 constexpr int GTHREADS = 256;
 
 template <int B>
-__global__ void __launch_bounds__(GTHREADS) blend_generic_kernel(const BlendParams P)
+__global__ void __launch_bounds__(GTHREADS) blend_generic_kernel(const __grid_constant__ BlendParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = P.radius;
@@ -265,8 +121,8 @@ __global__ void __launch_bounds__(GTHREADS) blend_generic_kernel(const BlendPara
             for (int i = tid; i < IW * GB; i += GTHREADS) {
                 const int r = i >> 5, c = i & 31;
                 const float *p = s_in + r * IP + c + R;
-                float a = c_taps[b][0] * p[0];
-                for (int k = 1; k <= R; ++k) a = fmaf(c_taps[b][k], p[-k] + p[k], a);
+                float a = P.taps[b][0] * p[0];
+                for (int k = 1; k <= R; ++k) a = fmaf(P.taps[b][k], p[-k] + p[k], a);
                 s_tmp[r * GB + c] = a;
             }
             __syncthreads();
@@ -275,7 +131,7 @@ __global__ void __launch_bounds__(GTHREADS) blend_generic_kernel(const BlendPara
                 const int ry = cy + 8 * j + R;
                 const float *p = s_tmp + ry * GB + cx;
                 float a = 0.f;
-                for (int k = -R; k <= R; ++k) a = fmaf(c_taps[b][k < 0 ? -k : k], p[k * GB], a);
+                for (int k = -R; k <= R; ++k) a = fmaf(P.taps[b][k < 0 ? -k : k], p[k * GB], a);
                 if (ch == 0) {
                     bool keep = false;
                     if (ok[j]) keep = __ldg(P.valid + (size_t)(ty0 + cy + 8 * j) * P.valid_step + (tx0 + cx)) == 255;
@@ -333,8 +189,9 @@ __global__ void normalise_kernel(const float4 *acc, int canvas_w, int rows, floa
 }
 
 // ---- FP32 pipe microbenchmark (roofline denominator of the blend kernels) ----
+struct PeakTaps { float t[8][16]; };
 template <int VARIANT>
-__global__ void __launch_bounds__(256) fp32_peak_kernel(float *sink, int iters, float seed)
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float *sink, int iters, float seed, const __grid_constant__ PeakTaps T)
 {
     float a[16];
 #pragma unroll
@@ -346,7 +203,7 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *sink, int iters, 
             for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
         } else if (VARIANT == 1) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], c_taps[i & 7][i], a[i]);
+            for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], T.t[i & 7][i], a[i]);
         } else {
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
@@ -370,21 +227,6 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *sink, int iters, 
     if (s == 123.456f) sink[0] = s;
 }
 
-template <int B>
-int launch_fast(spano_ctx *ctx, const BlendParams &P, dim3 grid)
-{
-    static bool configured[64] = {false};
-    const size_t smem = sizeof(FastSmem<B>);
-    int dev = ctx->device & 63;
-    if (!configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(blend_fast_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return spano_fail(ctx, SPANO_E_CUDA, "cudaFuncSetAttribute(blend_fast<%d>, %zu B): %s", B, smem, cudaGetErrorString(e));
-        configured[dev] = true;
-    }
-    blend_fast_kernel<B><<<grid, FastCfg<B>::THREADS, smem, ctx->stream>>>(P);
-    return 0;
-}
-
 // activity + plan kernels of one tile launch into `plan` (device, march::PlanView::ints(strips, sms) ints)
 template <int SW>
 int make_plan(spano_ctx *ctx, const BlendParams &Q, int sms, int *plan)
@@ -399,7 +241,7 @@ int make_plan(spano_ctx *ctx, const BlendParams &Q, int sms, int *plan)
     }
     int *ymin = plan + V.ymin(), *ymax = plan + V.ymax();
     march::plan_init_kernel<<<(strips + 255) / 256, 256, 0, ctx->stream>>>(ymin, ymax, strips);
-    const int dense = g_blend_dense;
+    const int dense = ctx->opt_blend_dense;
     if (!dense) {
         const int ra = std::max(0, Q.ty_begin - march::R), rb = std::min(Q.h, Q.ty_end + march::R);
         dim3 ag((Q.w + 511) / 512, (rb - ra + 63) / 64);
@@ -424,6 +266,7 @@ int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
         configured[dev] = true;
     }
     march::Params P;
+    P.slot = ctx->tap_slot;
     P.tile = Q.tile;  P.tile_step = Q.tile_step;
     P.cut = Q.cut;  P.cut_step = Q.cut_step;
     P.valid = Q.valid;  P.valid_step = Q.valid_step;
@@ -465,51 +308,49 @@ int launch_generic(spano_ctx *ctx, const BlendParams &P, dim3 grid)
 
 } // namespace
 
-// Gaussian taps for every band into constant memory (cv::getGaussianKernel, see projector_host.cpp).
-// The tap tables live in __constant__ memory, i.e. once per device and process, while contexts are per thread: the
-// tables are keyed by (bands, sigma) and guarded by a per-device mutex.  A context that needs other tables than the
-// ones loaded waits for everything in flight on the device (cudaDeviceSynchronize, under the mutex, so no blend can
-// be launched meanwhile) before it rewrites them; blend launches take the mutex around "check key + launch".
-// Contexts that blend with the same parameters -- the normal case -- never wait.
-struct TapState {
+// Tap slots of the marching kernel: write-once per (device, bands, sigma).  A slot is filled under the mutex with a
+// synchronous copy that is waited for before the slot is published, and is never rewritten afterwards, so kernels on any
+// stream of any context can read it without further ordering.  When all slots of a device are taken (more than
+// TAP_SLOTS distinct (bands, sigma) pairs in one process) the caller falls back to the generic kernel, whose taps
+// travel in its launch parameters.
+struct TapSlots {
     std::mutex mu;
-    bool valid = false;
-    int bands = 0;
-    double sigma = 0.0;
+    int n = 0;
+    int bands[TAP_SLOTS];
+    double sigma[TAP_SLOTS];
 };
-static TapState g_tap_state[64];
+static TapSlots g_tap_slots[64];
 
-// caller holds g_tap_state[dev].mu
-static int ensure_taps_locked(spano_ctx *ctx, int bands, double sigma)
+static int tap_slot(spano_ctx *ctx, int bands, double sigma, int *slot)
 {
-    TapState &T = g_tap_state[ctx->device & 63];
-    if (T.valid && T.bands == bands && T.sigma == sigma) return 0;
-    const int radius = (int)std::ceil(3 * sigma);
-    float host[MAXB][MAXR + 1] = {};
-    float full[2 * MAXR + 1];
-    const int n = 2 * radius + 1;
-    for (int i = 0; i < bands; ++i) {
-        const double sb = std::sqrt((double)(2 * (bands - i) + 1)) * sigma;
-        spano_host_gaussian_taps(n, sb, full);
-        for (int k = 0; k <= radius; ++k) host[i][k] = full[radius + k];
+    TapSlots &T = g_tap_slots[ctx->device & 63];
+    std::lock_guard<std::mutex> lk(T.mu);
+    *slot = -1;
+    for (int i = 0; i < T.n; ++i)
+        if (T.bands[i] == bands && T.sigma[i] == sigma) { *slot = i; return 0; }
+    if (T.n == TAP_SLOTS) return 0;
+    const int i = T.n;
+    float taps[MAXB][24] = {};
+    float2 pairs[MAXB][44] = {};
+    for (int b = 0; b < bands; ++b) {
+        for (int k = 0; k <= FR; ++k) taps[b][k] = ctx->taps[b][k];
+        for (int d = 0; d <= 2 * FR + 1; ++d) {
+            const float hi = d <= 2 * FR ? ctx->taps[b][d < FR ? FR - d : d - FR] : 0.f;
+            const float lo = d >= 1 ? ctx->taps[b][(d - 1) < FR ? FR - (d - 1) : (d - 1) - FR] : 0.f;
+            pairs[b][d] = make_float2(hi, lo);
+        }
     }
-    T.valid = false;
-    SPANO_CUDA(ctx, cudaDeviceSynchronize());   // nothing that reads the old tables is in flight any more
-    SPANO_CUDA(ctx, cudaMemcpyToSymbol(c_taps, host, sizeof(host), 0, cudaMemcpyHostToDevice));
-    if (radius == 21) {
-        float2 pairs[MAXB][44] = {};
-        for (int i = 0; i < bands; ++i)
-            for (int d = 0; d <= 43; ++d) {
-                const float hi = d <= 42 ? host[i][d < 21 ? 21 - d : d - 21] : 0.f;
-                const float lo = d >= 1 ? host[i][(d - 1) < 21 ? 21 - (d - 1) : (d - 1) - 21] : 0.f;
-                pairs[i][d] = make_float2(hi, lo);
-            }
-        SPANO_CUDA(ctx, cudaMemcpyToSymbol(c_tap2, pairs, sizeof(pairs), 0, cudaMemcpyHostToDevice));
-    }
-    T.bands = bands;  T.sigma = sigma;  T.valid = true;
+    SPANO_CUDA(ctx, cudaMemcpyToSymbol(c_taps, taps, sizeof(taps), (size_t)i * sizeof(taps), cudaMemcpyHostToDevice));
+    SPANO_CUDA(ctx, cudaMemcpyToSymbol(c_tap2, pairs, sizeof(pairs), (size_t)i * sizeof(pairs), cudaMemcpyHostToDevice));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(cudaStreamLegacy));   // the copies (pageable source, legacy stream) have landed
+    T.bands[i] = bands;  T.sigma[i] = sigma;
+    T.n = i + 1;
+    *slot = i;
     return 0;
 }
 
+// Gaussian taps of every band (cv::getGaussianKernel, see projector_host.cpp), kept on the host in the context and
+// copied into the parameters of every blend launch.
 int launch_blend_setup(spano_ctx *ctx, int bands, double sigma)
 {
     if (bands < 1 || bands > MAXB) return spano_fail(ctx, SPANO_E_INVALID, "bands %d not in [1,%d]", bands, MAXB);
@@ -517,10 +358,21 @@ int launch_blend_setup(spano_ctx *ctx, int bands, double sigma)
     const int radius = (int)std::ceil(3 * sigma);
     if (radius < 1 || radius > MAXR)
         return spano_fail(ctx, SPANO_E_LIMIT, "blur radius ceil(3*sigma)=%d exceeds %d", radius, MAXR);
+    if (ctx->tap_bands == bands && ctx->tap_sigma == sigma) return radius;
+    ctx->tap_bands = 0;
+    float full[2 * MAXR + 1];
+    const int n = 2 * radius + 1;
+    memset(ctx->taps, 0, sizeof(ctx->taps));
+    for (int i = 0; i < bands; ++i) {
+        const double sb = std::sqrt((double)(2 * (bands - i) + 1)) * sigma;
+        spano_host_gaussian_taps(n, sb, full);
+        for (int k = 0; k <= radius; ++k) ctx->taps[i][k] = full[radius + k];
+    }
+    ctx->tap_slot = -1;
+    if (radius == FR)
+        if (int rc = tap_slot(ctx, bands, sigma, &ctx->tap_slot)) return rc;
     ctx->tap_bands = bands;
     ctx->tap_sigma = sigma;
-    std::lock_guard<std::mutex> lk(g_tap_state[ctx->device & 63].mu);
-    if (int rc = ensure_taps_locked(ctx, bands, sigma)) return rc;
     return radius;
 }
 
@@ -530,15 +382,12 @@ int launch_blend_clear(spano_ctx *ctx, float4 *acc, int canvas_w, int rows)
     return 0;
 }
 
-// debug / cross-check switch: 0 = default (marching kernel), 1 = generic-radius kernel, 2 = block-tiled kernel
-static int g_force_generic = 0;
-extern "C" void spano_debug_force_generic(int on) { g_force_generic = on; }
-
-static bool march_path(int radius) { return radius == FR && g_force_generic == 0; }
+// ctx->opt_blend_kernel: 0 = default (marching kernel when the radius is 21), 1 = always the generic-radius kernel
+static bool march_path(const spano_ctx *ctx, int radius) { return radius == FR && ctx->opt_blend_kernel == 0 && ctx->tap_slot >= 0; }
 
 size_t blend_plan_bytes(spano_ctx *ctx, int w, int bands, int radius)
 {
-    if (!march_path(radius) || w <= 0) return 0;
+    if (!march_path(ctx, radius) || w <= 0) return 0;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     const int SW = bands <= 6 ? 32 : 16;
@@ -550,7 +399,7 @@ int launch_blend_plan(spano_ctx *ctx, const BlendTile &t, int bands, int radius,
     int ty_begin = row0 - t.cy, ty_end = row1 - t.cy;
     if (ty_begin < 0) ty_begin = 0;
     if (ty_end > t.h) ty_end = t.h;
-    if (ty_end <= ty_begin || t.w <= 0 || !march_path(radius)) return 0;
+    if (ty_end <= ty_begin || t.w <= 0 || !march_path(ctx, radius)) return 0;
     BlendParams P;
     P.cut = t.cut;  P.cut_step = t.cut_step;
     P.w = t.w;  P.h = t.h;
@@ -580,12 +429,8 @@ int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius,
     P.radius = radius;
     P.plan = plan;
     int rc = 0;
-    // the tap tables must be this context's from here until the kernel is launched (see TapState)
-    std::lock_guard<std::mutex> tap_lock(g_tap_state[ctx->device & 63].mu);
     if (ctx->tap_bands != bands || !(ctx->tap_sigma > 0)) return spano_fail(ctx, SPANO_E_INVALID, "blend launched without launch_blend_setup");
-    if (int trc = ensure_taps_locked(ctx, ctx->tap_bands, ctx->tap_sigma)) return trc;
-    const bool fast = (radius == FR) && g_force_generic != 1;
-    if (fast && g_force_generic == 0) {
+    if (march_path(ctx, radius)) {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
         switch (bands) {
@@ -594,16 +439,8 @@ int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius,
 #undef CASE
         default: return spano_fail(ctx, SPANO_E_INVALID, "bands %d unsupported", bands);
         }
-    } else if (fast) {
-        const int fbh = bands <= 7 ? 64 : 32; // FastCfg<B>::BH
-        dim3 grid((t.w + FBW - 1) / FBW, (ty_end - ty_begin + fbh - 1) / fbh);
-        switch (bands) {
-#define CASE(B) case B: rc = launch_fast<B>(ctx, P, grid); break;
-            CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
-#undef CASE
-        default: return spano_fail(ctx, SPANO_E_INVALID, "bands %d unsupported", bands);
-        }
     } else {
+        memcpy(P.taps, ctx->taps, sizeof(P.taps));
         dim3 grid((t.w + GB - 1) / GB, (ty_end - ty_begin + GB - 1) / GB);
         switch (bands) {
 #define CASE(B) case B: rc = launch_generic<B>(ctx, P, grid); break;
@@ -644,11 +481,14 @@ int launch_fp32_peak(spano_ctx *ctx, int variant, double *tflops)
     SPANO_CUDA(ctx, cudaEventCreate(&e0));
     SPANO_CUDA(ctx, cudaEventCreate(&e1));
     float best = 1e30f;
+    PeakTaps T;
+    for (int i = 0; i < 8; ++i)
+        for (int k = 0; k < 16; ++k) T.t[i][k] = 1.0f / (float)(17 + i + k);
     for (int rep = 0; rep < 4; ++rep) {
         SPANO_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-        if (variant == 0) fp32_peak_kernel<0><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 1.0f);
-        else if (variant == 1) fp32_peak_kernel<1><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 1.0f);
-        else fp32_peak_kernel<2><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 1.0f);
+        if (variant == 0) fp32_peak_kernel<0><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 1.0f, T);
+        else if (variant == 1) fp32_peak_kernel<1><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 1.0f, T);
+        else fp32_peak_kernel<2><<<blocks, threads, 0, ctx->stream>>>(sink, iters, 1.0f, T);
         SPANO_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
         SPANO_CUDA(ctx, cudaEventSynchronize(e1));
         float ms = 0;

@@ -47,7 +47,12 @@ struct Cfg {
                                    sizeof(int) * NC;
 };
 
+// The Gaussian taps live in __constant__ memory (the FMAs take them as constant-bank / uniform-register operands;
+// taps passed as kernel parameters end up in vector registers and cost the vertical pass its 2-source FFMA2 form).
+// They are stored in write-once SLOTS keyed by (bands, sigma) (blend_kernels.cu: tap_slot): a launch names its slot,
+// contexts with different parameters use different slots and nothing is ever rewritten while kernels may read it.
 struct Params {
+    int slot;               // tap slot of this launch's (bands, sigma)
     const uint8_t *tile;  size_t tile_step;
     const uint8_t *cut;   size_t cut_step;
     const uint8_t *valid; size_t valid_step;
@@ -250,7 +255,7 @@ __device__ __forceinline__ uint32_t fetch_raw(const Params &P, const int *xtab, 
 
 // horizontal pass of one item (row i of channel ch, 4 columns) of the staged chunk -> circular buffer slot
 template <int B, int SW>
-__device__ __forceinline__ void row_pass_item(const float *raw, float *rowbuf, int item, int slot_row0)
+__device__ __forceinline__ void row_pass_item(const Params &P, const float *raw, float *rowbuf, int item, int slot_row0)
 {
     using C = Cfg<B, SW>;
     const int g = item % C::GROUPS;
@@ -279,7 +284,7 @@ __device__ __forceinline__ void row_pass_item(const float *raw, float *rowbuf, i
         for (int b = 0; b < B; ++b) {
             unsigned long long a = 0ull;
 #pragma unroll
-            for (int k = 0; k <= R; ++k) ffma2_vs(a, plo[k], phi[k], c_taps[b][k]);
+            for (int k = 0; k <= R; ++k) ffma2_vs(a, plo[k], phi[k], c_taps[P.slot][b][k]);
             acc2[b][jp] = a;
         }
     }
@@ -464,7 +469,7 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
             for (int b = 0; b < B; ++b) {
                 if (b / C::HB == vg) {
                     float res[STEP];
-                    vertical_one<SW>(rowbuf + (size_t)(b * 4 + vch) * C::PLANE_STRIDE + vx, c_tap2[b], chunk0, res);
+                    vertical_one<SW>(rowbuf + (size_t)(b * 4 + vch) * C::PLANE_STRIDE + vx, c_tap2[P.slot][b], chunk0, res);
                     float *gp = G + (size_t)(b * 4 + vch) * STEP * SW + vx;
 #pragma unroll
                     for (int o = 0; o < STEP; ++o) gp[o * SW] = res[o];
@@ -484,7 +489,7 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
                 accv = *accp;
             }
         }
-        if (more_rows && tid < C::ROW_ITEMS) row_pass_item<B, SW>(raw, rowbuf, tid, chunk0 * STEP);   // chunk s+7 takes the slot chunk s vacates
+        if (more_rows && tid < C::ROW_ITEMS) row_pass_item<B, SW>(P, raw, rowbuf, tid, chunk0 * STEP);   // chunk s+7 takes the slot chunk s vacates
         chunk0 = (chunk0 + 1 == NCHUNK) ? 0 : chunk0 + 1;
     }
 }

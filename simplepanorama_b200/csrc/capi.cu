@@ -47,10 +47,22 @@ int spano_reserve(spano_ctx *ctx, int which, size_t bytes, void **out)
 
 namespace {
 
+// serialises the calls on one context and makes the context's device current for the duration of the call (the
+// caller's current device -- torch reads it with cudaGetDevice -- is restored on the way out)
 struct Guard {
     spano_ctx *c;
-    explicit Guard(spano_ctx *ctx) : c(ctx) { c->mu.lock(); cudaSetDevice(c->device); }
-    ~Guard() { c->mu.unlock(); }
+    int prev = -1;
+    explicit Guard(spano_ctx *ctx) : c(ctx)
+    {
+        c->mu.lock();
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != c->device) cudaSetDevice(c->device);
+    }
+    ~Guard()
+    {
+        if (prev >= 0 && prev != c->device) cudaSetDevice(prev);
+        c->mu.unlock();
+    }
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -186,7 +198,11 @@ extern "C" int spano_create(spano_ctx **out, int device)
     spano_ctx *ctx = new (std::nothrow) spano_ctx();
     if (!ctx) return SPANO_E_NOMEM;
     ctx->device = device;
-    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    const bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    if (!ok) {
         delete ctx;
         return SPANO_E_CUDA;
     }
@@ -198,6 +214,8 @@ extern "C" int spano_create(spano_ctx **out, int device)
 extern "C" void spano_destroy(spano_ctx *ctx)
 {
     if (!ctx) return;
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     drain_timers(ctx);
@@ -222,6 +240,7 @@ extern "C" void spano_destroy(spano_ctx *ctx)
     }
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
     delete ctx;
 }
 
@@ -245,6 +264,20 @@ extern "C" int spano_sync(spano_ctx *ctx)
 }
 
 extern "C" long long spano_launch_count(spano_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int spano_set_option(spano_ctx *ctx, int option, int value)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    switch (option) {
+    case SPANO_OPT_BLEND_DENSE: ctx->opt_blend_dense = value != 0; return SPANO_OK;
+    case SPANO_OPT_BLEND_KERNEL:
+        if (value < 0 || value > 1) return spano_fail(ctx, SPANO_E_INVALID, "SPANO_OPT_BLEND_KERNEL: value %d not in [0,1]", value);
+        ctx->opt_blend_kernel = value;
+        return SPANO_OK;
+    default: return spano_fail(ctx, SPANO_E_INVALID, "unknown option %d", option);
+    }
+}
 
 extern "C" int spano_timers_enable(spano_ctx *ctx, int on)
 {

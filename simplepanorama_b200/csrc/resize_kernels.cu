@@ -188,7 +188,7 @@ int launch_adjust_intensity(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t s
 {
     if (w <= 0 || h <= 0 || fw <= 0 || fh <= 0) return spano_fail(ctx, SPANO_E_INVALID, "adjust_intensity: empty image");
     AxisEntryF *tab = nullptr;
-    int rc = spano_reserve(ctx, spano_ctx::BUF_RESIZE, (size_t)(w + h) * sizeof(AxisEntryF), (void **)&tab);
+    int rc = spano_reserve(ctx, spano_table_buffer(ctx, spano_ctx::BUF_RESIZE, spano_ctx::BUF_RESIZE_AUX), (size_t)(w + h) * sizeof(AxisEntryF), (void **)&tab);
     if (rc) return rc;
     const int n = w > h ? w : h;
     intensity_tables_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(fw, fh, w, h, tab, tab + w);
@@ -207,7 +207,7 @@ int launch_resize_mask(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_
     if (row_begin < 0) row_begin = 0;
     if (row_end <= row_begin) return 0;
     AxisEntry *tab = nullptr;
-    int rc = spano_reserve(ctx, spano_ctx::BUF_RESIZE, (size_t)(dw + dh) * sizeof(AxisEntry), (void **)&tab);
+    int rc = spano_reserve(ctx, spano_table_buffer(ctx, spano_ctx::BUF_RESIZE, spano_ctx::BUF_RESIZE_AUX), (size_t)(dw + dh) * sizeof(AxisEntry), (void **)&tab);
     if (rc) return rc;
     const int n = dw > dh ? dw : dh;
     resize_tables_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sw, sh, dw, dh, tab, tab + dw);

@@ -46,7 +46,7 @@ struct spano_ctx {
     long long launches = 0;
     // grow-only scratch buffers, indexed by role
     enum { BUF_LABELS = 0, BUF_DARK, BUF_MASK0, BUF_TABLES, BUF_ACC, BUF_TILE, BUF_TILEMASK, BUF_CUTMASK, BUF_SRC,
-           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_BLENDPLAN, BUF_BLENDPLAN2, BUF_DT_TMP, BUF_DT_JOBS, BUF_DT_JOBS2, BUF_DT_ARENA, BUF_PREP_CUT, BUF_PREP_PLAN, BUF_COUNT };
+           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_BLENDPLAN, BUF_BLENDPLAN2, BUF_DT_TMP, BUF_DT_JOBS, BUF_DT_JOBS2, BUF_DT_ARENA, BUF_PREP_CUT, BUF_PREP_PLAN, BUF_RESIZE_AUX, BUF_TABLES_AUX, BUF_COUNT };
     DeviceBuffer buf[BUF_COUNT];
     std::vector<void *> owned; // extra allocations freed at destroy / end of call
     unsigned long long *blend_stats = nullptr; // device: [0] tile pixels the blend processed, [1] tile pixels offered
@@ -75,8 +75,13 @@ struct spano_ctx {
         std::vector<Prepared> prepared;
     } bs;
     std::vector<cudaEvent_t> event_pool;   // reusable events of the prepare step
-    int tap_bands = 0;                     // Gaussian tap tables this context blends with (launch_blend_setup)
-    double tap_sigma = 0.0;
+    int tap_bands = 0;                     // Gaussian taps this context blends with (launch_blend_setup), per band and
+    double tap_sigma = 0.0;                // distance from the centre; copied into the parameters of every blend launch
+    float taps[SPANO_MAX_BANDS][SPANO_BLUR_RADIUS_MAX + 1] = {};
+    int tap_slot = -1;                     // marching kernel: constant-memory slot holding these taps (-1: none)
+    // spano_set_option
+    int opt_blend_dense = 0;               // 1: ignore the mask_cut sparsity (every tile pixel is filtered)
+    int opt_blend_kernel = 0;              // 1: always the generic-radius blend kernel (cross-check of the marching one)
     // timers
     bool timers_on = false;
     float stage_ms[4] = {0, 0, 0, 0};
@@ -85,6 +90,10 @@ struct spano_ctx {
 };
 
 int spano_fail(spano_ctx *ctx, int code, const char *fmt, ...);
+// Small per-launch table buffers (resize axis tables, warp trig tables) are rewritten by every launch on whatever stream
+// the context currently enqueues on; work on the auxiliary stream (spano_*_blend_prepare, the warp-ahead of the fused
+// path) gets its own copy so that it cannot race with launches of the same kind on the main stream.
+inline int spano_table_buffer(const spano_ctx *ctx, int main_id, int aux_id) { return (ctx->aux_stream && ctx->stream == ctx->aux_stream) ? aux_id : main_id; }
 int spano_reserve(spano_ctx *ctx, int which, size_t bytes, void **out);
 
 #define SPANO_CUDA(ctx, call)                                                                      \

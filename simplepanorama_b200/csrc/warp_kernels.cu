@@ -432,7 +432,7 @@ int launch_warp(spano_ctx *ctx, const SpanoProjector &proj, const uint8_t *src, 
     float *tables = nullptr;
     const int wp = (dst_w + 3) & ~3;
     const size_t tab_floats = 6 * (size_t)wp + 4 * (size_t)dst_h;
-    int rc = spano_reserve(ctx, spano_ctx::BUF_TABLES, tab_floats * sizeof(float), (void **)&tables);
+    int rc = spano_reserve(ctx, spano_table_buffer(ctx, spano_ctx::BUF_TABLES, spano_ctx::BUF_TABLES_AUX), tab_floats * sizeof(float), (void **)&tables);
     if (rc) return rc;
     WarpParams P;
     for (int i = 0; i < 9; ++i) P.m[i] = proj.k_rinv[i];

@@ -1,7 +1,7 @@
 """GPU: the mask_cut sparsity of the blend is EXACT.  A tile pixel whose whole 43x43 window of mask_cut is zero
 has weight 0 in every band (blnd::multi_blend, src/math/_blending.cpp:205-222: the weight is GaussianBlur(mask)),
 so the marching kernel skips it; the canvas must be bit-identical to the dense evaluation of the same kernel
-(spano_debug_blend_dense) and within 1e-5 of the oracle, for adversarial sparsity patterns."""
+(SPANO_OPT_BLEND_DENSE) and within 1e-5 of the oracle, for adversarial sparsity patterns."""
 import numpy as np
 import pytest
 
@@ -48,9 +48,9 @@ def test_sparse_blend_is_bit_identical_to_dense(ctx, oracle, bands):
         for t, (w, h) in enumerate(sizes):
             pats = _patterns(rng, w, h)
             cuts.append(pats[names[(trial + t) % len(names)]])
-        ctx.lib.spano_debug_blend_dense(1)
+        ctx.set_option(ctx.OPT_BLEND_DENSE, 1)
         dense = api.multi_blend(tiles, cuts, valids, corners, bands, 7.0, ctx)
-        ctx.lib.spano_debug_blend_dense(0)
+        ctx.set_option(ctx.OPT_BLEND_DENSE, 0)
         ctx.blend_stats(reset=True)
         sparse = api.multi_blend(tiles, cuts, valids, corners, bands, 7.0, ctx)
         done, offered = ctx.blend_stats()
