@@ -33,12 +33,14 @@ namespace {
 constexpr int MAXB = SPANO_MAX_BANDS;
 constexpr int MAXR = SPANO_BLUR_RADIUS_MAX;
 
-// Tap slots of the marching kernel (see blend_march.cuh): c_taps[s][b][k] = tap of band b at distance k from the
-// centre; c_tap2[s][b][d] = {T[d], T[d-1]} with T[d] = tap at |d - 21| for d in 0..42 and T[-1] = T[43] = 0 (the tap
+// Tap slots of the marching kernel (see blend_march.cuh): c_taps[s + b][k] = tap of band b at distance k from the
+// centre; c_tap2[s + b][d] = {T[d], T[d-1]} with T[d] = tap at |d - 21| for d in 0..42 and T[-1] = T[43] = 0 (the tap
 // pair that output rows o, o+1 of the vertical pass apply to input row o + d).
-constexpr int TAP_SLOTS = 8;
-__constant__ __align__(16) float c_taps[TAP_SLOTS][MAXB][24];
-__constant__ __align__(16) float2 c_tap2[TAP_SLOTS][MAXB][44];
+// A slot is a run of `bands` consecutive rows of the two tables (slot = index of its first row).
+constexpr int TAP_ROWS = 120;   // 120 * (96 + 352) B = 53.8 KB of the 64 KB constant space
+constexpr int TAP_SLOTS = 32;
+__constant__ __align__(16) float c_taps[TAP_ROWS][24];
+__constant__ __align__(16) float2 c_tap2[TAP_ROWS][44];
 
 struct BlendParams {
     const uint8_t *tile;  size_t tile_step;
@@ -76,6 +78,7 @@ __device__ __forceinline__ float load_channel(const BlendParams &P, int ch, int 
 constexpr int FR = 21;           // radius of the marching kernel
 
 #include "blend_march.cuh"
+#include "blend_ws.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Generic path: any radius <= 32 (other sigma values).  Same arithmetic, runtime loops,
@@ -258,12 +261,15 @@ int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
 {
     constexpr int SW = (B <= 6) ? 32 : 16;
     using C = march::Cfg<B, SW>;
-    static bool configured[64] = {false};
+    using W = march::WsCfg<B, SW>;
+    const bool ws = ctx->opt_blend_kernel != 2;   // 2: the 8-warp marching kernel (cross-check of the warp-specialised one)
+    static bool configured[2][64] = {{false}, {false}};
     int dev = ctx->device & 63;
-    if (!configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(march::blend_march_kernel<B, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) return spano_fail(ctx, SPANO_E_CUDA, "cudaFuncSetAttribute(blend_march<%d>, %zu B): %s", B, C::SMEM, cudaGetErrorString(e));
-        configured[dev] = true;
+    if (!configured[ws][dev]) {
+        cudaError_t e = ws ? cudaFuncSetAttribute(march::blend_ws_kernel<B, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::SMEM)
+                           : cudaFuncSetAttribute(march::blend_march_kernel<B, SW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return spano_fail(ctx, SPANO_E_CUDA, "cudaFuncSetAttribute(blend_%s<%d>, %zu B): %s", ws ? "ws" : "march", B, ws ? W::SMEM : C::SMEM, cudaGetErrorString(e));
+        configured[ws][dev] = true;
     }
     march::Params P;
     P.slot = ctx->tap_slot;
@@ -284,7 +290,8 @@ int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
         if (int rc = make_plan<SW>(ctx, Q, sms, plan)) return rc;
         P.plan = plan;
     }
-    march::blend_march_kernel<B, SW><<<sms, march::THREADS, C::SMEM, ctx->stream>>>(P);
+    if (ws) march::blend_ws_kernel<B, SW><<<sms, march::WS_THREADS, W::SMEM, ctx->stream>>>(P);
+    else march::blend_march_kernel<B, SW><<<sms, march::THREADS, C::SMEM, ctx->stream>>>(P);
     return 0;
 }
 
@@ -310,13 +317,13 @@ int launch_generic(spano_ctx *ctx, const BlendParams &P, dim3 grid)
 
 // Tap slots of the marching kernel: write-once per (device, bands, sigma).  A slot is filled under the mutex with a
 // synchronous copy that is waited for before the slot is published, and is never rewritten afterwards, so kernels on any
-// stream of any context can read it without further ordering.  When all slots of a device are taken (more than
-// TAP_SLOTS distinct (bands, sigma) pairs in one process) the caller falls back to the generic kernel, whose taps
-// travel in its launch parameters.
+// stream of any context can read it without further ordering.  When the tables of a device are full (more than
+// TAP_ROWS bands in total over the distinct (bands, sigma) pairs of one process) the caller falls back to the generic
+// kernel, whose taps travel in its launch parameters.
 struct TapSlots {
     std::mutex mu;
-    int n = 0;
-    int bands[TAP_SLOTS];
+    int n = 0, rows = 0;
+    int bands[TAP_SLOTS], row0[TAP_SLOTS];
     double sigma[TAP_SLOTS];
 };
 static TapSlots g_tap_slots[64];
@@ -327,9 +334,9 @@ static int tap_slot(spano_ctx *ctx, int bands, double sigma, int *slot)
     std::lock_guard<std::mutex> lk(T.mu);
     *slot = -1;
     for (int i = 0; i < T.n; ++i)
-        if (T.bands[i] == bands && T.sigma[i] == sigma) { *slot = i; return 0; }
-    if (T.n == TAP_SLOTS) return 0;
-    const int i = T.n;
+        if (T.bands[i] == bands && T.sigma[i] == sigma) { *slot = T.row0[i]; return 0; }
+    if (T.n == TAP_SLOTS || T.rows + bands > TAP_ROWS) return 0;
+    const int i = T.n, r0 = T.rows;
     float taps[MAXB][24] = {};
     float2 pairs[MAXB][44] = {};
     for (int b = 0; b < bands; ++b) {
@@ -340,12 +347,13 @@ static int tap_slot(spano_ctx *ctx, int bands, double sigma, int *slot)
             pairs[b][d] = make_float2(hi, lo);
         }
     }
-    SPANO_CUDA(ctx, cudaMemcpyToSymbol(c_taps, taps, sizeof(taps), (size_t)i * sizeof(taps), cudaMemcpyHostToDevice));
-    SPANO_CUDA(ctx, cudaMemcpyToSymbol(c_tap2, pairs, sizeof(pairs), (size_t)i * sizeof(pairs), cudaMemcpyHostToDevice));
+    SPANO_CUDA(ctx, cudaMemcpyToSymbol(c_taps, taps, (size_t)bands * sizeof(taps[0]), (size_t)r0 * sizeof(taps[0]), cudaMemcpyHostToDevice));
+    SPANO_CUDA(ctx, cudaMemcpyToSymbol(c_tap2, pairs, (size_t)bands * sizeof(pairs[0]), (size_t)r0 * sizeof(pairs[0]), cudaMemcpyHostToDevice));
     SPANO_CUDA(ctx, cudaStreamSynchronize(cudaStreamLegacy));   // the copies (pageable source, legacy stream) have landed
-    T.bands[i] = bands;  T.sigma[i] = sigma;
+    T.bands[i] = bands;  T.sigma[i] = sigma;  T.row0[i] = r0;
     T.n = i + 1;
-    *slot = i;
+    T.rows = r0 + bands;
+    *slot = r0;
     return 0;
 }
 
@@ -382,8 +390,9 @@ int launch_blend_clear(spano_ctx *ctx, float4 *acc, int canvas_w, int rows)
     return 0;
 }
 
-// ctx->opt_blend_kernel: 0 = default (marching kernel when the radius is 21), 1 = always the generic-radius kernel
-static bool march_path(const spano_ctx *ctx, int radius) { return radius == FR && ctx->opt_blend_kernel == 0 && ctx->tap_slot >= 0; }
+// ctx->opt_blend_kernel: 0 = default (warp-specialised marching kernel when the radius is 21), 1 = always the
+// generic-radius kernel, 2 = the 8-warp marching kernel (same arithmetic and order as the default: bit-identical)
+static bool march_path(const spano_ctx *ctx, int radius) { return radius == FR && ctx->opt_blend_kernel != 1 && ctx->tap_slot >= 0; }
 
 size_t blend_plan_bytes(spano_ctx *ctx, int w, int bands, int radius)
 {

@@ -52,7 +52,7 @@ struct Cfg {
 // They are stored in write-once SLOTS keyed by (bands, sigma) (blend_kernels.cu: tap_slot): a launch names its slot,
 // contexts with different parameters use different slots and nothing is ever rewritten while kernels may read it.
 struct Params {
-    int slot;               // tap slot of this launch's (bands, sigma)
+    int slot;               // tap slot of this launch's (bands, sigma): first row of its taps in c_taps / c_tap2
     const uint8_t *tile;  size_t tile_step;
     const uint8_t *cut;   size_t cut_step;
     const uint8_t *valid; size_t valid_step;
@@ -284,7 +284,7 @@ __device__ __forceinline__ void row_pass_item(const Params &P, const float *raw,
         for (int b = 0; b < B; ++b) {
             unsigned long long a = 0ull;
 #pragma unroll
-            for (int k = 0; k <= R; ++k) ffma2_vs(a, plo[k], phi[k], c_taps[P.slot][b][k]);
+            for (int k = 0; k <= R; ++k) ffma2_vs(a, plo[k], phi[k], c_taps[P.slot + b][k]);
             acc2[b][jp] = a;
         }
     }
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
             for (int b = 0; b < B; ++b) {
                 if (b / C::HB == vg) {
                     float res[STEP];
-                    vertical_one<SW>(rowbuf + (size_t)(b * 4 + vch) * C::PLANE_STRIDE + vx, c_tap2[P.slot][b], chunk0, res);
+                    vertical_one<SW>(rowbuf + (size_t)(b * 4 + vch) * C::PLANE_STRIDE + vx, c_tap2[P.slot + b], chunk0, res);
                     float *gp = G + (size_t)(b * 4 + vch) * STEP * SW + vx;
 #pragma unroll
                     for (int o = 0; o < STEP; ++o) gp[o * SW] = res[o];

@@ -12,7 +12,9 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._lib import CYLINDRICAL, SPHERICAL, STEREOGRAPHIC
+# projection kinds (include/spano.h SPANO_SPHERICAL / _CYLINDRICAL / _STEREOGRAPHIC).  This module imports nothing
+# from the package: bench.py's reference arm loads it by path so that the CPU arm never touches the CUDA library.
+SPHERICAL, CYLINDRICAL, STEREOGRAPHIC = 0, 1, 2
 
 
 @dataclass
