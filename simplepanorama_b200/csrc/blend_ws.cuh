@@ -24,12 +24,15 @@
 namespace march {
 
 constexpr int WS_SLOTS = 8;                    // chunk slots of the circular row buffer
-constexpr int WS_VTHREADS = 256, WS_HTHREADS = 128, WS_THREADS = WS_VTHREADS + WS_HTHREADS;
-// registers per thread after the role split (the launch allocates 168 x 384 = 64512; 256 x 112 + 128 x 224 = 57344)
-constexpr int WS_VREGS = 112, WS_HREGS = 224;
+constexpr int WS_HTHREADS = 128;
+// V group size: 8 warps (2 per scheduler) or 12 warps (3 per scheduler; strips of 32 columns only).  Registers per thread
+// after the role split: the launch allocates 168 x 384 = 64512 (8 V warps; then 256 x 112 + 128 x 224 = 57344) or
+// 128 x 512 = 65536 (12 V warps; then 384 x 96 + 128 x 224 = 65536).
+template <int VT> struct WsRegs { static constexpr int V = (VT == 256) ? 112 : 96, H = 224; };
 
-template <int B, int SW>
+template <int B, int SW, int VT>
 struct WsCfg {
+    static constexpr int VTHREADS = VT, THREADS = VT + WS_HTHREADS;
     static constexpr int PLANES = 4 * B;
     static constexpr int PLANE_STRIDE = WS_SLOTS * STEP * SW + (SW == 16 ? 16 : 0);   // floats
     static constexpr int NC = SW + 2 * R;
@@ -37,7 +40,7 @@ struct WsCfg {
     static constexpr int GROUPS = SW / 4;
     static constexpr int ROW_ITEMS = STEP * 4 * GROUPS;                 // 256 (SW = 32) or 128 (SW = 16)
     static constexpr int ITEMS_PER_THREAD = ROW_ITEMS / WS_HTHREADS;    // 2 or 1
-    static constexpr int NG = WS_VTHREADS / (4 * SW);                   // sigma groups of the vertical pass
+    static constexpr int NG = VT / (4 * SW);                   // sigma groups of the vertical pass
     static constexpr int HB = (B + NG - 1) / NG;
     static constexpr int NPX = STEP * SW;
     static constexpr int NPASS = (NC + 31) / 32;                        // staging passes of 32 lanes over the NC columns
@@ -106,7 +109,7 @@ __device__ __forceinline__ void vertical_ring(const float *col /* plane + x */, 
 template <int B, int SW>
 __device__ __forceinline__ void ws_row_item(const Params &P, const float *raw, float *rowbuf, int item, int slot_row0)
 {
-    using C = WsCfg<B, SW>;
+    using C = WsCfg<B, SW, 256>;
     const int g = item % C::GROUPS;
     const int rc = item / C::GROUPS;
     const int i = rc & (STEP - 1), ch = rc >> 3;
@@ -144,10 +147,11 @@ __device__ __forceinline__ void ws_row_item(const Params &P, const float *raw, f
     }
 }
 
-template <int B, int SW>
-__global__ void __launch_bounds__(WS_THREADS, 1) blend_ws_kernel(const Params P)
+template <int B, int SW, int VT>
+__global__ void __launch_bounds__(VT + WS_HTHREADS, 1) blend_ws_kernel(const Params P)
 {
-    using C = WsCfg<B, SW>;
+    using C = WsCfg<B, SW, VT>;
+    constexpr int WS_VTHREADS = VT;
     static_assert(C::NPX <= WS_VTHREADS && C::HB <= 5 && STEP == 8 && (WS_SLOTS & (WS_SLOTS - 1)) == 0 && WS_SLOTS > NCHUNK, "mapping");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *rowbuf = reinterpret_cast<float *>(smem_raw);                  // [PLANES][PLANE_STRIDE]
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) blend_ws_kernel(const Params P)
         // =========================== H group: stage + horizontal pass, one chunk at a time ===========================
         // (the horizontal pass holds a 48-float window, 44 pair sums and 2B packed accumulators per item plus the
         // prefetched bytes of the next chunk: it takes the registers the V warps hand back)
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_HREGS));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WsRegs<VT>::H));
         const int ht = tid - WS_VTHREADS;
         const int lane = ht & 31, hw = ht >> 5;                 // warp hw stages channel hw (all 8 rows of a chunk)
         const uint8_t *sbase = (hw == 0) ? P.cut : P.tile + (hw - 1);
@@ -231,7 +235,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) blend_ws_kernel(const Params P)
     }
 
     // =============================== V group: vertical pass + combine, one step at a time ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_VREGS));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WsRegs<VT>::V));
     const int vx = tid % SW, vch = (tid / SW) & 3, vg = tid / (4 * SW);
     const int po = tid / SW, px = tid % SW;
 #pragma unroll 1
@@ -275,6 +279,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) blend_ws_kernel(const Params P)
                 if (s == nsteps - 1)                                     // the piece's remaining chunks were only ever read
                     for (int k = 1; k < NCHUNK; ++k) mbar_arrive(empty + ((chunk0 + k) & (WS_SLOTS - 1)));
             }
+            // (the loaded values must not be consumed before this point: without the pin the compiler hoists the first use
+            // above the vertical pass and every V warp sits out the DRAM latency at the top of the step)
+            asm volatile("" : "+r"(vraw), "+r"(i0), "+r"(i1), "+r"(i2), "+f"(accv.x), "+f"(accv.y), "+f"(accv.z), "+f"(accv.w));
             if (cdo) {
                 const bool keep = vraw == 255u;
                 const float I0 = (float)i0, I1 = (float)i1, I2 = (float)i2;
