@@ -81,6 +81,7 @@ long long spano_launch_count(spano_ctx *ctx);
  *                             same arithmetic in the same order as the default, bit-identical canvas)           */
 #define SPANO_OPT_BLEND_DENSE 1
 #define SPANO_OPT_BLEND_KERNEL 2
+#define SPANO_OPT_FLAG_WAIT 3 /* 0 (default): stream memory operations; 1: a one-thread polling kernel (spano_shard_step_*) */
 int spano_set_option(spano_ctx *ctx, int option, int value);
 
 /* ---- a3: projector geometry (host arithmetic, bit-exact with OpenCV's warpers) -----
@@ -335,6 +336,49 @@ int spano_dev_blend_add(spano_ctx *ctx, const spano_image_desc *im, const spano_
 int spano_dev_blend_finish(spano_ctx *ctx, uint8_t *canvas, size_t canvas_step);
 int spano_blend_add(spano_ctx *ctx, const spano_image_desc *im, const spano_slice *slice);
 int spano_blend_finish(spano_ctx *ctx, uint8_t *canvas, size_t canvas_step);
+
+/* ---- one step of the tile-sharded path, enqueued by the library -------------------------------------------
+ * The owner side and the band side of ONE rank for one pass over the image set (= the loop of
+ * proj::get_proj_parameters and the loop of blnd::multi_blend of stitch_parameters::return_full,
+ * src/classes/_panorama.cpp:259-354, as sharded above).  There is no collective and no host rendezvous inside a
+ * step: ranks order their work through READINESS FLAGS in device memory --
+ *   flags[k]        base of rank k's flag block as addressable from this process (own allocation or peer mapping,
+ *                   spano_peer_alloc / spano_peer_open): n + world 32-bit counters, zero-initialised once
+ *   ready[j]  = flags[k][j]          written by the owner of image j (a store from its stream, after the warp / mask
+ *                                    kernels whose peer stores put tile j's rows into rank k's arena): "the rows of
+ *                                    image j that band k reads have landed for step `step`"
+ *   done[r]   = flags[k][n + r]      written by band r after its last blend of the step: "band r no longer reads its
+ *                                    arena for step `step`" (owner k may overwrite it in step + 1)
+ * and each stream waits for the counters it depends on with a stream memory operation (cuStreamWaitValue32, >=),
+ * which occupies no SM; `step` must increase by one per step, starting at 1.
+ * spano_shard_step_owner (context / stream of the owner side): waits done[*] >= step - 1, then for every image j
+ * with owner[j] == rank, in `order`: upload (host variant) + warp + validity mask scattered to the slices
+ * slices[k * n + j] of every band k that reads it, then ready[j] = step at those bands.
+ * spano_shard_step_band (context / stream of the band side; a DIFFERENT context than the owner side's): blend_begin,
+ * prepare (mask up-scaling + sparsity plans on the auxiliary stream), then for j = 0..n-1 in array order (the
+ * accumulation order of the single-GPU path: bit-identical canvas): wait ready[j] >= step, blend; normalise into
+ * `canvas` (device pointer, local or peer; or, host variant, download to host_canvas); done[rank] = step at every owner.
+ * images: n descriptors, identical on every rank except the pointers (src_bgr is only dereferenced by the owner,
+ * mask_cut only by the bands that read the tile); host != 0: src_bgr / mask_cut are HOST pointers.              */
+typedef struct spano_shard_plan {
+    int world, rank, n;
+    int proj;
+    float scale;
+    int bands;
+    double sigma;
+    int canvas_w, min_x, min_y; /* spano_pan_dimension of the whole panorama */
+    int row0, row1;             /* this rank's canvas row band */
+    const spano_image_desc *images;
+    const int *owner;           /* [n] */
+    const int *order;           /* [n] permutation: the order in which owners process images */
+    const spano_slice *slices;  /* [world * n]; row1 <= row0: image j does not touch band k */
+    uint32_t *const *flags;     /* [world] */
+    uint8_t *canvas;            /* row 0 of this band in the destination canvas (device pointer; NULL with host != 0) */
+    size_t canvas_step;
+} spano_shard_plan;
+int spano_shard_step_owner(spano_ctx *ctx, const spano_shard_plan *plan, unsigned step, int host);
+int spano_shard_step_band(spano_ctx *ctx, const spano_shard_plan *plan, unsigned step, int host, uint8_t *host_canvas,
+                          size_t host_canvas_step);
 
 /* ---- measurement helpers ---------------------------------------------------------------
  * Time (ms, CUDA events on the context's stream) spent in the kernels of each stage since

@@ -39,6 +39,14 @@ class Slice(C.Structure):
                 ("valid", C.c_void_p), ("valid_step", C.c_size_t)]
 
 
+class ShardPlanC(C.Structure):
+    """struct spano_shard_plan"""
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("n", C.c_int), ("proj", C.c_int), ("scale", C.c_float), ("bands", C.c_int),
+                ("sigma", C.c_double), ("canvas_w", C.c_int), ("min_x", C.c_int), ("min_y", C.c_int), ("row0", C.c_int), ("row1", C.c_int),
+                ("images", C.POINTER(ImageDesc)), ("owner", C.POINTER(C.c_int)), ("order", C.POINTER(C.c_int)),
+                ("slices", C.POINTER(Slice)), ("flags", C.POINTER(C.c_void_p)), ("canvas", C.c_void_p), ("canvas_step", C.c_size_t)]
+
+
 class OverlapInfo(C.Structure):
     """struct spano_overlap_info == gain::OverlapInfo"""
     _fields_ = [("i", C.c_int), ("j", C.c_int), ("area", C.c_double), ("I_i", C.c_double), ("I_j", C.c_double)]
@@ -101,6 +109,8 @@ SYMBOLS = {
     "spano_blend_add": (C.c_int, [C.c_void_p, C.POINTER(ImageDesc), C.POINTER(Slice)]),
     "spano_blend_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "spano_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "spano_shard_step_owner": (C.c_int, [C.c_void_p, C.POINTER(ShardPlanC), C.c_uint, C.c_int]),
+    "spano_shard_step_band": (C.c_int, [C.c_void_p, C.POINTER(ShardPlanC), C.c_uint, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_timers_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "spano_timers_reset": (C.c_int, [C.c_void_p]),
     "spano_timers_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),

@@ -271,6 +271,7 @@ extern "C" int spano_set_option(spano_ctx *ctx, int option, int value)
     Guard g(ctx);
     switch (option) {
     case SPANO_OPT_BLEND_DENSE: ctx->opt_blend_dense = value != 0; return SPANO_OK;
+    case SPANO_OPT_FLAG_WAIT: ctx->opt_flag_wait = value != 0; return SPANO_OK;
     case SPANO_OPT_BLEND_KERNEL:
         if (value < 0 || value > 3) return spano_fail(ctx, SPANO_E_INVALID, "SPANO_OPT_BLEND_KERNEL: value %d not in [0,3]", value);
         ctx->opt_blend_kernel = value;
@@ -1359,13 +1360,11 @@ extern "C" int spano_dev_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, in
     return blend_begin_impl(ctx, canvas_w, min_x, min_y, row0, row1, bands, sigma);
 }
 
-extern "C" int spano_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma,
-                                 int n, const spano_image_desc *images, uint8_t *canvas, size_t canvas_step)
+namespace {
+// host variant of begin: uploads the preview-scale masks of the tiles that touch the band right away (ahead of the owners'
+// large source uploads) and, when the destination canvas is announced, prepares the early column download
+int blend_begin_host_extras(spano_ctx *ctx, int n, const spano_image_desc *images, uint8_t *canvas, size_t canvas_step)
 {
-    if (!ctx) return SPANO_E_INVALID;
-    Guard g(ctx);
-    if (n < 0 || (n > 0 && !images)) return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_begin: null images");
-    if (int rc = blend_begin_impl(ctx, canvas_w, min_x, min_y, row0, row1, bands, sigma)) return rc;
     spano_ctx::BlendSession &S = ctx->bs;
     // preview-scale masks of the tiles that touch this band: one staging arena, uploaded now
     size_t total = 0;
@@ -1415,6 +1414,17 @@ extern "C" int spano_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int mi
         }
     }
     return SPANO_OK;
+}
+} // namespace
+
+extern "C" int spano_blend_begin(spano_ctx *ctx, int canvas_w, int min_x, int min_y, int row0, int row1, int bands, double sigma,
+                                 int n, const spano_image_desc *images, uint8_t *canvas, size_t canvas_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (n < 0 || (n > 0 && !images)) return spano_fail(ctx, SPANO_E_INVALID, "spano_blend_begin: null images");
+    if (int rc = blend_begin_impl(ctx, canvas_w, min_x, min_y, row0, row1, bands, sigma)) return rc;
+    return blend_begin_host_extras(ctx, n, images, canvas, canvas_step);
 }
 
 namespace {
@@ -1478,6 +1488,122 @@ extern "C" int spano_blend_finish(spano_ctx *ctx, uint8_t *canvas, size_t canvas
     if (!ctx) return SPANO_E_INVALID;
     Guard g(ctx);
     return blend_finish_impl(ctx, canvas, canvas_step, true);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one step of the tile-sharded path: owner side and band side of a rank, ordered by readiness flags
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// cuStreamWaitValue32 through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef int (*stream_wait32_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+stream_wait32_fn driver_stream_wait32()
+{
+    static stream_wait32_fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<stream_wait32_fn>(p);
+    }();
+    return fn;
+}
+
+// the context's stream waits until *flag >= value (wrap-safe), without occupying an SM
+int stream_wait_flag(spano_ctx *ctx, const uint32_t *flag, uint32_t value)
+{
+    stream_wait32_fn fn = ctx->opt_flag_wait ? nullptr : driver_stream_wait32();
+    if (fn) {
+        const int rc = fn(ctx->stream, (unsigned long long)(uintptr_t)flag, value, 0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+        if (rc != 0) return spano_fail(ctx, SPANO_E_CUDA, "cuStreamWaitValue32 failed: CUresult %d", rc);
+        return 0;
+    }
+    if (!ctx->opt_flag_wait) return spano_fail(ctx, SPANO_E_CUDA, "cuStreamWaitValue32 is not available from this driver");
+    const int k = launch_flag_wait_kernel(ctx, flag, value);
+    return k < 0 ? k : 0;
+}
+
+int check_shard_plan(spano_ctx *ctx, const spano_shard_plan *P, unsigned step)
+{
+    if (!P || P->world <= 0 || P->rank < 0 || P->rank >= P->world || P->n <= 0 || !P->images || !P->owner || !P->order || !P->slices || !P->flags)
+        return spano_fail(ctx, SPANO_E_INVALID, "spano_shard_step: null / inconsistent plan");
+    if (step == 0) return spano_fail(ctx, SPANO_E_INVALID, "spano_shard_step: steps are numbered from 1");
+    for (int k = 0; k < P->world; ++k)
+        if (!P->flags[k]) return spano_fail(ctx, SPANO_E_INVALID, "spano_shard_step: flag block of rank %d is null", k);
+    return 0;
+}
+
+} // namespace
+
+extern "C" int spano_shard_step_owner(spano_ctx *ctx, const spano_shard_plan *P, unsigned step, int host)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (int rc = check_shard_plan(ctx, P, step)) return rc;
+    const int n = P->n, W = P->world;
+    bool any = false;
+    for (int j = 0; j < n && !any; ++j) any = P->owner[j] == P->rank;
+    if (!any) return SPANO_OK;
+    // every band has finished reading its arena for the previous step
+    if (step > 1)
+        for (int k = 0; k < W; ++k)
+            if (int rc = stream_wait_flag(ctx, P->flags[P->rank] + n + k, step - 1)) return rc;
+    std::vector<spano_slice> sl;
+    std::vector<uint32_t *> targets;
+    for (int t = 0; t < n; ++t) {
+        const int j = P->order[t];
+        if (j < 0 || j >= n) return spano_fail(ctx, SPANO_E_INVALID, "spano_shard_step_owner: order[%d] = %d", t, j);
+        if (P->owner[j] != P->rank) continue;
+        sl.clear();
+        targets.clear();
+        for (int k = 0; k < W; ++k) {
+            const spano_slice &s = P->slices[(size_t)k * n + j];
+            if (s.row1 <= s.row0) continue;
+            sl.push_back(s);
+            targets.push_back(P->flags[k] + j);
+        }
+        if (sl.empty()) continue;
+        if (int rc = warp_scatter_impl(ctx, P->proj, P->scale, P->images + j, (int)sl.size(), sl.data(), host != 0)) return rc;
+        const int k = launch_flag_signal(ctx, targets.data(), (int)targets.size(), step);
+        if (k < 0) return k;
+    }
+    return SPANO_OK;
+}
+
+extern "C" int spano_shard_step_band(spano_ctx *ctx, const spano_shard_plan *P, unsigned step, int host, uint8_t *host_canvas,
+                                     size_t host_canvas_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (int rc = check_shard_plan(ctx, P, step)) return rc;
+    const int n = P->n, W = P->world;
+    std::vector<uint32_t *> done_targets;
+    for (int r = 0; r < W; ++r) done_targets.push_back(P->flags[r] + n + P->rank);
+    if (P->row1 <= P->row0) {   // an empty band still tells the owners that it is "done"
+        const int k = launch_flag_signal(ctx, done_targets.data(), W, step);
+        return k < 0 ? k : SPANO_OK;
+    }
+    if (host) {
+        if (!host_canvas) return spano_fail(ctx, SPANO_E_INVALID, "spano_shard_step_band: host variant without a host canvas");
+    } else if (!P->canvas) {
+        return spano_fail(ctx, SPANO_E_INVALID, "spano_shard_step_band: null canvas");
+    }
+    const spano_slice *mine = P->slices + (size_t)P->rank * n;
+    if (int rc = blend_begin_impl(ctx, P->canvas_w, P->min_x, P->min_y, P->row0, P->row1, P->bands, P->sigma)) return rc;
+    if (host)
+        if (int rc = blend_begin_host_extras(ctx, n, P->images, host_canvas, host_canvas_step)) return rc;
+    if (int rc = blend_prepare_impl(ctx, n, P->images, mine, host != 0)) { ctx->bs.open = false; return rc; }
+    for (int j = 0; j < n; ++j) {
+        if (mine[j].row1 <= mine[j].row0) continue;
+        if (int rc = stream_wait_flag(ctx, P->flags[P->rank] + j, step)) { ctx->bs.open = false; return rc; }
+        if (int rc = blend_add_impl(ctx, P->images + j, mine + j, host != 0)) { ctx->bs.open = false; return rc; }
+    }
+    // the arena is not read after the last blend: tell the owners before the normalise / download tail
+    {
+        const int k = launch_flag_signal(ctx, done_targets.data(), W, step);
+        if (k < 0) { ctx->bs.open = false; return k; }
+    }
+    if (host) return blend_finish_impl(ctx, host_canvas, host_canvas_step, true);
+    return blend_finish_impl(ctx, P->canvas, P->canvas_step, false);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -250,3 +250,48 @@ int launch_valid_mask(spano_ctx *ctx, const uint8_t *dark, int w, int h, size_t 
     ctx->launches += 4;
     return 4;
 }
+
+// ---- readiness flags of the tile-sharded multi-GPU path ---------------------------------------------------------------
+namespace {
+struct FlagTargets { uint32_t *p[SPANO_MAX_FLAG_TARGETS]; };
+
+// Runs after the kernels whose (peer) stores it publishes, on the same stream: the kernel boundary orders those stores
+// before this one's; the system-scope fence keeps that order on the way to another GPU's memory.
+__global__ void flag_signal_kernel(FlagTargets T, int n, uint32_t value)
+{
+    if ((int)threadIdx.x < n) {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint32_t *>(T.p[threadIdx.x]) = value;
+    }
+}
+
+__global__ void flag_wait_kernel(const uint32_t *flag, uint32_t value)
+{
+    const volatile uint32_t *p = flag;
+    while ((int32_t)(*p - value) < 0) __nanosleep(256);
+    __threadfence_system();
+}
+} // namespace
+
+int launch_flag_signal(spano_ctx *ctx, uint32_t *const *targets, int n, uint32_t value)
+{
+    int launches = 0;
+    for (int i = 0; i < n; i += SPANO_MAX_FLAG_TARGETS) {
+        FlagTargets T;
+        const int m = n - i < SPANO_MAX_FLAG_TARGETS ? n - i : SPANO_MAX_FLAG_TARGETS;
+        for (int k = 0; k < m; ++k) T.p[k] = targets[i + k];
+        flag_signal_kernel<<<1, 32, 0, ctx->stream>>>(T, m, value);
+        ++launches;
+    }
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += launches;
+    return launches;
+}
+
+int launch_flag_wait_kernel(spano_ctx *ctx, const uint32_t *flag, uint32_t value)
+{
+    flag_wait_kernel<<<1, 1, 0, ctx->stream>>>(flag, value);
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return 1;
+}

@@ -81,6 +81,7 @@ struct spano_ctx {
     int tap_slot = -1;                     // marching kernel: constant-memory slot holding these taps (-1: none)
     // spano_set_option
     int opt_blend_dense = 0;               // 1: ignore the mask_cut sparsity (every tile pixel is filtered)
+    int opt_flag_wait = 0;                 // 1: wait for readiness flags with a polling kernel instead of cuStreamWaitValue32
     int opt_blend_kernel = 0;              // 1: always the generic-radius blend kernel (cross-check of the marching one)
     // timers
     bool timers_on = false;
@@ -168,6 +169,10 @@ int launch_no_blend(spano_ctx *ctx, int n, const uint8_t *const *tiles, const si
 int launch_gray(spano_ctx *ctx, const uint8_t *bgr, size_t step, int w, int h, uint8_t *gray, size_t gstep);
 int launch_overlap_sums(spano_ctx *ctx, const uint8_t *gi, size_t gis, const uint8_t *mi, size_t mis, const uint8_t *gj, size_t gjs,
                         const uint8_t *mj, size_t mjs, int xi, int yi, int xj, int yj, int ow, int oh, unsigned long long *acc);
+// mask_kernels.cu: readiness flags of the tile-sharded path (stores to possibly peer-GPU counters; polling wait)
+#define SPANO_MAX_FLAG_TARGETS 16
+int launch_flag_signal(spano_ctx *ctx, uint32_t *const *targets, int n, uint32_t value);
+int launch_flag_wait_kernel(spano_ctx *ctx, const uint32_t *flag, uint32_t value);
 // disk_kernels.cu: stereographic centre fix (util::RadialNormalizer state + normalised radius)
 struct SpanoDiskParams {
     float cx, cy, scale;

@@ -78,7 +78,8 @@ class ShardPlan:
     sizes: list
     bands: list                      # [(row0, row1)] per rank
     owner: list                      # owner rank of tile j
-    rounds: list                     # [[tile ids]]: round t holds at most one tile per owner
+    order: list                      # the order in which owners process tiles (a permutation of range(n))
+    rounds: list                     # [[tile ids]]: round t holds at most one tile per owner (array order; legacy callers)
     slices: list                     # slices[k][j] = (r0, r1) tile rows of j stored at rank k, or None
     offsets: list                    # offsets[k][j] = (tile_off, valid_off) into rank k's arena, or None
     arena_bytes: list                # per rank
@@ -96,9 +97,68 @@ def plan_area_bands(world: int, canvas_h: int):
     return [(edges[i], edges[i + 1]) for i in range(world)]
 
 
-def plan_tile_shards(corners, sizes, world: int, sigma: float = 7.0, balance: str = "area") -> ShardPlan:
+def assign_owners(corners, sizes, bands, min_y: int):
+    """Owner rank of every tile.  A tile's rows are stored into the arenas of the bands that read them, so the owner
+    with the most rows of the tile inside its own band turns most of the scatter into LOCAL stores (less NVLink
+    traffic); every owner takes at most ceil(n / world) tiles so that the warp + mask work stays balanced.  Tiles are
+    placed in order of how strongly they prefer one band; what is left falls to the least loaded rank.  On a one-row
+    panorama (every tile spans every band equally) this degenerates to the round robin j % world."""
+    n, world = len(sizes), len(bands)
+    cap = -(-n // world)
+    rows = []   # rows[j][k] = rows of tile j inside band k
+    for j in range(n):
+        cy, h = corners[j][1] - min_y, sizes[j][1]
+        rows.append([max(0, min(cy + h, b1) - max(cy, b0)) for (b0, b1) in bands])
+    load = [0] * world
+    owner = [-1] * n
+    pref = sorted(range(n), key=lambda j: (-(max(rows[j]) / max(1, sizes[j][1])), j))
+    for j in pref:
+        best = max(rows[j])
+        if best * world <= sum(rows[j]) + 1e-9 * best:   # no preference: spread evenly
+            continue
+        for k in sorted(range(world), key=lambda k: (-rows[j][k], load[k], k)):
+            if load[k] < cap and rows[j][k] > 0:
+                owner[j] = k
+                load[k] += 1
+                break
+    for j in range(n):
+        if owner[j] < 0:
+            k = min(range(world), key=lambda k: (load[k], (k - j) % world))
+            owner[j] = k
+            load[k] += 1
+    return owner
+
+
+def owner_order(n: int, slices):
+    """Order in which the owners process tiles.  Every band blends its tiles in array order (the accumulation order of
+    the single-GPU path) and can only start a tile once its rows have arrived: visiting the bands round robin and
+    taking each band's next outstanding tile keeps every band supplied (a set laid out row by row would otherwise
+    feed one band after the other)."""
+    world = len(slices)
+    need = [[j for j in range(n) if slices[k][j] is not None] for k in range(world)]
+    pos = [0] * world
+    done = [False] * n
+    order = []
+    while len(order) < n:
+        progressed = False
+        for k in range(world):
+            while pos[k] < len(need[k]) and done[need[k][pos[k]]]:
+                pos[k] += 1
+            if pos[k] < len(need[k]):
+                j = need[k][pos[k]]
+                done[j] = True
+                order.append(j)
+                progressed = True
+        if not progressed:
+            order.extend(j for j in range(n) if not done[j])   # tiles no band reads
+            break
+    return order
+
+
+def plan_tile_shards(corners, sizes, world: int, sigma: float = 7.0, balance: str = "area", owners: str = "locality") -> ShardPlan:
     """corners[j] = (tl_x, tl_y), sizes[j] = (w, h) of every warped tile (spano_warp_roi).
-    balance: "area" (equal band heights, see plan_area_bands) or "tile_pixels" (plan_row_bands)."""
+    balance: "area" (equal band heights, see plan_area_bands) or "tile_pixels" (plan_row_bands).
+    owners: "locality" (assign_owners) or "round_robin" (j % world)."""
     import math
     n = len(sizes)
     radius = int(math.ceil(3 * sigma))
@@ -106,7 +166,7 @@ def plan_tile_shards(corners, sizes, world: int, sigma: float = 7.0, balance: st
     xs1 = max(c[0] + s[0] for c, s in zip(corners, sizes)); ys1 = max(c[1] + s[1] for c, s in zip(corners, sizes))
     W, H = xs1 - xs0, ys1 - ys0           # == util::get_pan_dimension
     bands = plan_area_bands(world, H) if balance == "area" else plan_row_bands(list(zip(corners, sizes)), world, ys0, H)
-    owner = [j % world for j in range(n)]
+    owner = assign_owners(corners, sizes, bands, ys0) if owners == "locality" else [j % world for j in range(n)]
     rounds = [list(range(t, min(n, t + world))) for t in range(0, n, world)]
     tile_step = [_al(3 * w, 16) for (w, h) in sizes]
     valid_step = [_al(w, 16) for (w, h) in sizes]
@@ -128,8 +188,8 @@ def plan_tile_shards(corners, sizes, world: int, sigma: float = 7.0, balance: st
             fill = _al(fill + valid_step[j] * (r1 - r0), 256)
             of.append((t_off, v_off))
         slices.append(sl); offsets.append(of); arena.append(max(fill, 256))
-    return ShardPlan(world, radius, W, H, xs0, ys0, list(corners), list(sizes), bands, owner, rounds, slices, offsets, arena,
-                     tile_step, valid_step)
+    return ShardPlan(world, radius, W, H, xs0, ys0, list(corners), list(sizes), bands, owner, owner_order(n, slices), rounds, slices,
+                     offsets, arena, tile_step, valid_step)
 
 
 def scatter_slices(plan: ShardPlan, j: int, arena_ptrs):
@@ -229,6 +289,95 @@ class PeerCanvas:
         elif self.ptr:
             self.ctx.lib.spano_peer_close(self.ctx.h, C.c_void_p(self.ptr))
         self.ptr = self.own = None
+
+
+class PeerFlags:
+    """Readiness-flag block of every rank (include/spano.h, spano_shard_plan): n + world 32-bit counters per rank, zeroed
+    once, every block mapped into every process.  ptrs[k] = rank k's block as addressable from this process."""
+
+    def __init__(self, ctx, plan: ShardPlan, rank: int, group=None):
+        import ctypes as C
+        import torch.distributed as dist
+        self.ctx, self.rank, self.world = ctx, rank, plan.world
+        self.bytes = 4 * (len(plan.sizes) + plan.world)
+        own = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        ctx.check(ctx.lib.spano_peer_alloc(ctx.h, max(256, self.bytes), C.byref(own), handle))
+        self.own = own.value
+        C.CDLL("libcudart.so.12").cudaMemset(C.c_void_p(self.own), 0, C.c_size_t(max(256, self.bytes)))
+        handles = [None] * plan.world
+        dist.all_gather_object(handles, bytes(handle), group=group)   # (also orders the memset before any peer's first store)
+        self.ptrs = []
+        for k in range(plan.world):
+            if k == rank:
+                self.ptrs.append(self.own)
+                continue
+            p = C.c_void_p()
+            hb = (C.c_ubyte * 64).from_buffer_copy(handles[k])
+            ctx.check(ctx.lib.spano_peer_open(ctx.h, hb, C.byref(p)))
+            self.ptrs.append(p.value)
+
+    def close(self):
+        import ctypes as C
+        for k, p in enumerate(self.ptrs):
+            if k != self.rank and p:
+                self.ctx.lib.spano_peer_close(self.ctx.h, C.c_void_p(p))
+        if self.own:
+            self.ctx.lib.spano_peer_free(self.ctx.h, C.c_void_p(self.own))
+        self.ptrs, self.own = [], None
+
+
+class ShardSession:
+    """The spano_shard_plan of one rank plus the step counter: step_owner / step_band enqueue one pass over the image
+    set (include/spano.h: spano_shard_step_owner / spano_shard_step_band).  `arena_ptrs[k]` / `flag_ptrs[k]` = rank
+    k's slice arena / flag block as addressable from this process; `canvas_ptr` = row 0 of THIS band in the destination
+    canvas (device pointer, local or peer), `descs` the spano_image_desc array (device or host pointers)."""
+
+    def __init__(self, plan: ShardPlan, rank: int, kind: int, focal: float, bands: int, sigma: float, arena_ptrs, flag_ptrs,
+                 canvas_ptr: int = 0, canvas_step: int = 0):
+        import ctypes as C
+        from ._lib import ShardPlanC, Slice
+        n, world = len(plan.sizes), plan.world
+        self.plan, self.rank, self.step = plan, rank, 0
+        self._owner = (C.c_int * n)(*plan.owner)
+        self._order = (C.c_int * n)(*plan.order)
+        self._slices = (Slice * (world * n))()
+        for k in range(world):
+            for j in range(n):
+                s = band_slice(plan, k, j, arena_ptrs[k])
+                if s is not None:
+                    self._slices[k * n + j] = s
+        self._flags = (C.c_void_p * world)(*flag_ptrs)
+        self.c = ShardPlanC()
+        c = self.c
+        c.world, c.rank, c.n, c.proj, c.scale, c.bands, c.sigma = world, rank, n, int(kind), float(focal), int(bands), float(sigma)
+        c.canvas_w, c.min_x, c.min_y = plan.canvas_w, plan.min_x, plan.min_y
+        c.row0, c.row1 = plan.bands[rank]
+        c.owner, c.order, c.slices = self._owner, self._order, self._slices
+        c.flags = C.cast(self._flags, C.POINTER(C.c_void_p))
+        c.canvas, c.canvas_step = canvas_ptr or None, canvas_step
+        self._descs = None
+
+    def _bind(self, descs):
+        import ctypes as C
+        from ._lib import ImageDesc
+        self._descs = descs
+        self.c.images = C.cast(descs, C.POINTER(ImageDesc))
+
+    def next_step(self):
+        self.step += 1
+        return self.step
+
+    def step_owner(self, ctx, descs, host: bool = False):
+        import ctypes as C
+        self._bind(descs)
+        ctx.check(ctx.lib.spano_shard_step_owner(ctx.h, C.byref(self.c), self.step, 1 if host else 0))
+
+    def step_band(self, ctx, descs, host: bool = False, host_canvas=(0, 0)):
+        import ctypes as C
+        self._bind(descs)
+        ctx.check(ctx.lib.spano_shard_step_band(ctx.h, C.byref(self.c), self.step, 1 if host else 0,
+                                                C.c_void_p(host_canvas[0] or None), host_canvas[1]))
 
 
 def scatter_tile(ctx, plan: ShardPlan, j: int, desc, arena_ptrs, kind: int, focal: float, host: bool = False):

@@ -118,3 +118,162 @@ def test_sharded_errors(ctx):
     oob = (Slice * 1)(Slice(0, h + 1, arena.data_ptr(), sp.tile_step[0], arena.data_ptr(), sp.valid_step[0]))
     assert lib.spano_dev_warp_scatter(ctx.h, cfg.kind, C.c_float(cfg.focal), C.byref(descs[0]), 1, oob) == -1
     ctx.sync()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# spano_shard_step_owner / spano_shard_step_band: the library-driven step, ordered by readiness flags
+# ---------------------------------------------------------------------------------------------------------------
+def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=2, poll_kernel=False):
+    """`world` ranks emulated on one device: per rank one band context + one owner context (their own streams), arenas and
+    flag blocks are plain device buffers.  The band phases are enqueued BEFORE the owner phases, so the band streams really
+    sit in their flag waits until the owner streams get there (stream memory operations occupy no SM, so nothing can
+    dead-lock); with the polling-kernel fallback the owners go first (a kernel must never wait for a later launch)."""
+    import torch
+    from simplepanorama_b200 import api, dist
+    dev = torch.device("cuda", 0)
+    sp = dist.plan_tile_shards([p[2] for p in plan], [p[3] for p in plan], world, cfg.sigma)
+    n = cfg.n
+    arenas = [torch.full((sp.arena_bytes[k],), 0xAB, dtype=torch.uint8, device=dev) for k in range(world)]
+    flags = [torch.zeros(n + world, dtype=torch.int32, device=dev) for _ in range(world)]
+    canvas = torch.zeros((sp.canvas_h, sp.canvas_w, 3), dtype=torch.uint8, device=dev)
+    if host:
+        imgs = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in images]
+        cts = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in cuts]
+        hcv = [torch.zeros((max(1, b1 - b0), sp.canvas_w, 3), dtype=torch.uint8).pin_memory() for (b0, b1) in sp.bands]
+    else:
+        imgs = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in images]
+        cts = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in cuts]
+    torch.cuda.synchronize()
+    descs = api.make_descs(imgs, plan, gains, cts, lambda t: t.data_ptr(), lambda t: t.stride(0))
+    band_ctx = [api.Context(0) for _ in range(world)]
+    own_ctx = [api.Context(0) for _ in range(world)]
+    sessions = []
+    for k in range(world):
+        r0, _ = sp.bands[k]
+        sessions.append(dist.ShardSession(sp, k, cfg.kind, cfg.focal, cfg.bands, cfg.sigma, [a.data_ptr() for a in arenas],
+                                          [f.data_ptr() for f in flags], canvas.data_ptr() + r0 * canvas.stride(0), canvas.stride(0)))
+        if poll_kernel:
+            band_ctx[k].set_option(3, 1)   # SPANO_OPT_FLAG_WAIT
+            own_ctx[k].set_option(3, 1)
+    results = []
+    for s in range(steps):
+        if s == 1:   # poison the arenas between steps: every row a band reads must be rewritten by its owner in this step
+            for b in band_ctx:
+                b.sync()
+            for a in arenas:
+                a.fill_(0x5C)
+            canvas.zero_()
+            torch.cuda.synchronize()
+        for sess in sessions:
+            sess.next_step()
+        def bands():
+            for k in range(world):
+                if host:
+                    sessions[k].step_band(band_ctx[k], descs, host=True, host_canvas=(hcv[k].data_ptr(), hcv[k].stride(0)))
+                else:
+                    sessions[k].step_band(band_ctx[k], descs, host=False)
+        def owners():
+            for k in reversed(range(world)):
+                sessions[k].step_owner(own_ctx[k], descs, host=host)
+        if poll_kernel or host:   # (the host variant of the band phase blocks until its canvas is down: owners first)
+            owners(); bands()
+        else:
+            bands(); owners()
+        for c in band_ctx + own_ctx:
+            c.sync()
+        if host:
+            results.append(np.concatenate([hcv[k].numpy()[: b1 - b0] for k, (b0, b1) in enumerate(sp.bands) if b1 > b0], axis=0).copy())
+        else:
+            results.append(canvas.cpu().numpy())
+    for c in band_ctx + own_ctx:
+        c.close()
+    return results, sp
+
+
+@pytest.mark.parametrize("name,scale,coarse", [("cfg1", 0.2, False), ("cfg2", 0.04, True), ("cfg3", 0.06, True), ("cfg4", 0.03, True)])
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_shard_step_equals_single_gpu(ctx, name, scale, coarse, world):
+    from simplepanorama_b200 import api
+    cfg, K, R, gains, images, plan, cuts = _case(name, scale, coarse)
+    full = api.return_full(images, R, K, cfg.kind, cfg.focal, gains, cuts, cfg.bands, cfg.sigma, ctx=ctx)
+    res, sp = _run_shard_steps(cfg, gains, images, plan, cuts, world, host=False)
+    assert sorted(sp.order) == list(range(cfg.n)) and max(sp.owner.count(k) for k in range(world)) <= -(-cfg.n // world)
+    for got in res:
+        assert got.shape == full.shape and np.array_equal(got, full)
+
+
+def test_shard_step_host_and_poll_fallback(ctx):
+    from simplepanorama_b200 import api
+    cfg, K, R, gains, images, plan, cuts = _case("cfg2", 0.04, True)
+    full = api.return_full(images, R, K, cfg.kind, cfg.focal, gains, cuts, cfg.bands, cfg.sigma, ctx=ctx)
+    res, _ = _run_shard_steps(cfg, gains, images, plan, cuts, 3, host=True)
+    for got in res:
+        assert np.array_equal(got, full)
+    res, _ = _run_shard_steps(cfg, gains, images, plan, cuts, 2, host=False, poll_kernel=True)
+    for got in res:
+        assert np.array_equal(got, full)
+
+
+def test_shard_step_errors(ctx):
+    from simplepanorama_b200._lib import ShardPlanC
+    p = ShardPlanC()
+    assert ctx.lib.spano_shard_step_owner(ctx.h, C.byref(p), 1, 0) == -1
+    assert ctx.lib.spano_shard_step_band(ctx.h, C.byref(p), 1, 0, None, 0) == -1
+    assert ctx.lib.spano_shard_step_band(ctx.h, None, 1, 0, None, 0) == -1
+
+
+def _ipc_worker(rank, world, port, q):
+    """one process per GPU: the real thing (cudaIpc arenas / flags / canvas, NVLink peer stores)"""
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as tdist
+    from simplepanorama_b200 import api, dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg, K, R, gains, images, plan, cuts = _case("cfg2", 0.05, True)
+    sp = dist.plan_tile_shards([p[2] for p in plan], [p[3] for p in plan], world, cfg.sigma)
+    bctx, octx = api.Context(rank), api.Context(rank)
+    arenas, flags, pc = dist.PeerArenas(bctx, sp, rank), dist.PeerFlags(bctx, sp, rank), dist.PeerCanvas(bctx, sp, rank)
+    imgs = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) if sp.owner[j] == rank else None for j, a in enumerate(images)]
+    cts = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in cuts]
+
+    class _A:
+        shape = (1, 1, 3)
+    descs = api.make_descs([t if t is not None else _A() for t in imgs], plan, gains, cts,
+                           lambda t: t.data_ptr() if not isinstance(t, _A) else 0, lambda t: t.stride(0) if not isinstance(t, _A) else 0)
+    for j in range(cfg.n):
+        descs[j].src_h, descs[j].src_w = cfg.height, cfg.width
+    sess = dist.ShardSession(sp, rank, cfg.kind, cfg.focal, cfg.bands, cfg.sigma, arenas.ptrs, flags.ptrs, pc.band_ptr(sp.bands[rank][0]), pc.step)
+    for _ in range(3):
+        sess.next_step()
+        sess.step_band(bctx, descs)
+        sess.step_owner(octx, descs)
+    bctx.sync(); octx.sync()
+    tdist.barrier()
+    if rank == 0:
+        cv = torch.empty((sp.canvas_h, pc.step), dtype=torch.uint8, device=dev)
+        C.CDLL("libcudart.so.12").cudaMemcpy(C.c_void_p(cv.data_ptr()), C.c_void_p(pc.ptr), C.c_size_t(pc.bytes), 3)
+        full = api.return_full(images, R, K, cfg.kind, cfg.focal, gains, cuts, cfg.bands, cfg.sigma, ctx=bctx)
+        q.put(bool(np.array_equal(cv[:, : 3 * sp.canvas_w].reshape(sp.canvas_h, sp.canvas_w, 3).cpu().numpy(), full)))
+    tdist.barrier()
+    arenas.close(); flags.close(); pc.close()
+    tdist.destroy_process_group()
+
+
+def test_shard_step_two_processes_ipc():
+    """Two processes on two GPUs, cudaIpc-mapped arenas, flag blocks and canvas: needs >= 2 devices (gpurun --gpus 2)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    import torch.multiprocessing as mp
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    procs = [ctxm.Process(target=_ipc_worker, args=(r, 2, 29541, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert q.get(timeout=5) is True
