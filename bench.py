@@ -36,6 +36,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# every stream that may sit in a flag wait (cuStreamWaitValue32, tile-sharded path) needs its own hardware queue, otherwise it
+# holds up unrelated streams that share the queue; must be set before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "composited output Mpx/s (warp+gain+multiband)"
 UNIT = "Mpx/s"

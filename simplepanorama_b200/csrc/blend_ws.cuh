@@ -26,9 +26,12 @@ namespace march {
 constexpr int WS_SLOTS = 8;                    // chunk slots of the circular row buffer
 constexpr int WS_HTHREADS = 128;
 // V group size: 8 warps (2 per scheduler) or 12 warps (3 per scheduler; strips of 32 columns only).  Registers per thread
-// after the role split: the launch allocates 168 x 384 = 64512 (8 V warps; then 256 x 112 + 128 x 224 = 57344) or
+// after the role split: the launch allocates 128 x 384 = 49152 (8 V warps; then 256 x 96 + 128 x 192 = 49152) or
 // 128 x 512 = 65536 (12 V warps; then 384 x 96 + 128 x 224 = 65536).
-template <int VT> struct WsRegs { static constexpr int V = (VT == 256) ? 112 : 96, H = 224; };
+// With 8 V warps the launch is capped at 128 registers per thread (49152 per CTA) instead of the 168 it could take: the
+// remaining quarter of the register file lets the warp / mask kernels of the NEXT image (auxiliary stream of the fused
+// path) stay co-resident with the blend of the current one.
+template <int VT> struct WsRegs { static constexpr int LAUNCH = 128, V = 96, H = (VT == 256) ? 192 : 224; };
 
 template <int B, int SW, int VT>
 struct WsCfg {
@@ -148,7 +151,7 @@ __device__ __forceinline__ void ws_row_item(const Params &P, const float *raw, f
 }
 
 template <int B, int SW, int VT>
-__global__ void __launch_bounds__(VT + WS_HTHREADS, 1) blend_ws_kernel(const Params P)
+__global__ void __maxnreg__(WsRegs<VT>::LAUNCH) blend_ws_kernel(const Params P)
 {
     using C = WsCfg<B, SW, VT>;
     constexpr int WS_VTHREADS = VT;

@@ -1543,6 +1543,29 @@ extern "C" int spano_shard_step_owner(spano_ctx *ctx, const spano_shard_plan *P,
     bool any = false;
     for (int j = 0; j < n && !any; ++j) any = P->owner[j] == P->rank;
     if (!any) return SPANO_OK;
+    // Size the scratch buffers for the largest owned image up front: growing one later would cudaFree the old buffer,
+    // and cudaFree waits for the whole device -- including a band stream of this process that may already sit in a flag
+    // wait which only this call's kernels can satisfy.
+    {
+        size_t src = 0, dark = 0, labels = 0, bits = 0, tables = 0;
+        for (int j = 0; j < n; ++j) {
+            if (P->owner[j] != P->rank) continue;
+            const spano_image_desc &im = P->images[j];
+            if (im.w <= 0 || im.h <= 0 || im.src_w <= 0 || im.src_h <= 0) continue;
+            src = std::max(src, align_up((size_t)im.src_w * 3, 16) * im.src_h + 16);
+            dark = std::max(dark, align_up((size_t)im.w, 16) * im.h);
+            labels = std::max(labels, ((size_t)im.w * im.h + 1) * sizeof(uint32_t));
+            bits = std::max(bits, (size_t)((im.w + 31) / 32) * im.h * sizeof(uint32_t));
+            tables = std::max(tables, (6 * (size_t)((im.w + 3) & ~3) + 4 * (size_t)im.h) * sizeof(float));
+        }
+        void *dummy;
+        if (host)
+            if (int rc = spano_reserve(ctx, spano_ctx::BUF_SRC, src, &dummy)) return rc;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_DARK, dark, &dummy)) return rc;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_LABELS, labels, &dummy)) return rc;
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_MASK0, bits, &dummy)) return rc;
+        if (int rc = spano_reserve(ctx, spano_table_buffer(ctx, spano_ctx::BUF_TABLES, spano_ctx::BUF_TABLES_AUX), tables, &dummy)) return rc;
+    }
     // every band has finished reading its arena for the previous step
     if (step > 1)
         for (int k = 0; k < W; ++k)

@@ -49,6 +49,9 @@ def config(name: str, scale: float = 1.0) -> Config:
     elif name == "cfg2":  # 24 x 24MP, ~353 deg cylindrical ring, 6 bands (no tile crosses +-pi)
         c = Config(name, CYLINDRICAL, 24, 6000, 4000, 6000.0, 6, 7.0, _ring(24, -150.0, 13.04), [0.0] * 24, 2,
                    "24 synthetic 24MP images, 360deg cylindrical panorama, 6-band multiband")
+    elif name == "cfg2a":  # edge-case parity: true 360 deg ring, the tiles that straddle the +-pi seam come out full-width
+        c = Config(name, CYLINDRICAL, 24, 6000, 4000, 5000.0, 6, 7.0, _ring(24, -172.5, 15.0), [0.0] * 24, 21,
+                   "24 synthetic 24MP images, true 360deg cylindrical ring (f=5000): seam-straddling tiles are full-width")
     elif name == "cfg3":  # 36 x 12MP stereographic little planet, 7 bands (looking down)
         yaw = [30.0 * (k % 12) for k in range(36)]
         pitch = [(-10.0, -40.0, -65.0)[k // 12] for k in range(36)]

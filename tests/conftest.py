@@ -1,6 +1,11 @@
 import os
 import sys
 
+# The tile-sharded path parks streams in flag waits (cuStreamWaitValue32).  Streams beyond the number of hardware queues
+# share one, and a parked stream would then hold up whatever is queued behind it: give every stream its own queue
+# (must be set before the CUDA context exists; bench.py does the same).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 import pytest
 

@@ -123,11 +123,14 @@ def test_sharded_errors(ctx):
 # ---------------------------------------------------------------------------------------------------------------
 # spano_shard_step_owner / spano_shard_step_band: the library-driven step, ordered by readiness flags
 # ---------------------------------------------------------------------------------------------------------------
-def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=2, poll_kernel=False):
+def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=3, poll_kernel=False):
     """`world` ranks emulated on one device: per rank one band context + one owner context (their own streams), arenas and
-    flag blocks are plain device buffers.  The band phases are enqueued BEFORE the owner phases, so the band streams really
-    sit in their flag waits until the owner streams get there (stream memory operations occupy no SM, so nothing can
-    dead-lock); with the polling-kernel fallback the owners go first (a kernel must never wait for a later launch)."""
+    flag blocks are plain device buffers.  From the second step on (scratch buffers have their final size: nothing calls
+    cudaFree, which would wait for the blocked streams) the band phases are enqueued BEFORE the owner phases, so the band
+    streams really sit in their flag waits until the owner streams get there (stream memory operations occupy no SM);
+    with the polling-kernel fallback the owners always go first (a kernel must never wait for a later launch).
+    Every stream that may block needs its own hardware queue, or it would hold up an unrelated stream queued behind it:
+    tests/conftest.py raises CUDA_DEVICE_MAX_CONNECTIONS to 32 (world 4 = 12 streams here)."""
     import torch
     from simplepanorama_b200 import api, dist
     dev = torch.device("cuda", 0)
@@ -175,7 +178,7 @@ def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=2, poll_
         def owners():
             for k in reversed(range(world)):
                 sessions[k].step_owner(own_ctx[k], descs, host=host)
-        if poll_kernel or host:   # (the host variant of the band phase blocks until its canvas is down: owners first)
+        if poll_kernel or host or s == 0:   # (the host variant of the band phase blocks until its canvas is down: owners first)
             owners(); bands()
         else:
             bands(); owners()
@@ -190,8 +193,9 @@ def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=2, poll_
     return results, sp
 
 
+@pytest.mark.timeout(120)
 @pytest.mark.parametrize("name,scale,coarse", [("cfg1", 0.2, False), ("cfg2", 0.04, True), ("cfg3", 0.06, True), ("cfg4", 0.03, True)])
-@pytest.mark.parametrize("world", [1, 2, 8])
+@pytest.mark.parametrize("world", [1, 2, 4])
 def test_shard_step_equals_single_gpu(ctx, name, scale, coarse, world):
     from simplepanorama_b200 import api
     cfg, K, R, gains, images, plan, cuts = _case(name, scale, coarse)
@@ -202,6 +206,7 @@ def test_shard_step_equals_single_gpu(ctx, name, scale, coarse, world):
         assert got.shape == full.shape and np.array_equal(got, full)
 
 
+@pytest.mark.timeout(120)
 def test_shard_step_host_and_poll_fallback(ctx):
     from simplepanorama_b200 import api
     cfg, K, R, gains, images, plan, cuts = _case("cfg2", 0.04, True)
@@ -246,10 +251,14 @@ def _ipc_worker(rank, world, port, q):
     for j in range(cfg.n):
         descs[j].src_h, descs[j].src_w = cfg.height, cfg.width
     sess = dist.ShardSession(sp, rank, cfg.kind, cfg.focal, cfg.bands, cfg.sigma, arenas.ptrs, flags.ptrs, pc.band_ptr(sp.bands[rank][0]), pc.step)
-    for _ in range(3):
+    for s in range(3):
         sess.next_step()
-        sess.step_band(bctx, descs)
-        sess.step_owner(octx, descs)
+        if s == 0:   # first step: scratch buffers are still being sized (see _run_shard_steps)
+            sess.step_owner(octx, descs)
+            sess.step_band(bctx, descs)
+        else:
+            sess.step_band(bctx, descs)
+            sess.step_owner(octx, descs)
     bctx.sync(); octx.sync()
     tdist.barrier()
     if rank == 0:
@@ -262,6 +271,7 @@ def _ipc_worker(rank, world, port, q):
     tdist.destroy_process_group()
 
 
+@pytest.mark.timeout(400)
 def test_shard_step_two_processes_ipc():
     """Two processes on two GPUs, cudaIpc-mapped arenas, flag blocks and canvas: needs >= 2 devices (gpurun --gpus 2)."""
     import torch
