@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cfg1", action="store_true")
     ap.add_argument("--no-cfg4", action="store_true")
+    ap.add_argument("--no-center-fix", action="store_true", help="cfg3 without sten_proj::disk_reproj")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU time budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -242,6 +243,16 @@ class Runner:
         self.plan = api.plan_tiles(shapes, R, K, cfg.kind, cfg.focal)                      # host geometry only
         self.corners = [p[2] for p in self.plan]
         self.sizes = [p[3] for p in self.plan]
+        self.warp_sizes = list(self.sizes)
+        # cfg3 "with center-fix" (stitch_parameters::return_full with conf.fix_center, _panorama.cpp:292-311): the circle comes
+        # from sten_proj::estimate_circle, which stays in the reference (here: restated through cv2 on the validity masks of a
+        # 1/8-scale copy of the set, outside the timed region, and scaled up); sten_proj::disk_reproj runs inside the step
+        self.fix = None
+        if name == "cfg3" and world == 1 and not getattr(args, "no_center_fix", False):
+            self.fix, self.fix_note = self._estimate_circle(api, synth, name, scale)
+            if self.fix is not None:
+                self.corners, self.sizes = api.disk_reproj_size(self.corners, self.sizes, (self.fix.ansatz_x, self.fix.ansatz_y),
+                                                                self.fix.radius, bool(self.fix.quadratic))
         self.W, self.H, _, self.min_y = api.pan_dimension(self.corners, self.sizes)
         self.T = sum(w * h for w, h in self.sizes)
         self.sp = sdist.plan_tile_shards(self.corners, self.sizes, world, cfg.sigma)
@@ -300,6 +311,30 @@ class Runner:
                                               self.peer_canvas.band_ptr(self.row0), self.peer_canvas.step)
         self.enqueue_ms = []
 
+    def _estimate_circle(self, api, synth, name, scale):
+        from simplepanorama_b200 import _lib
+        try:
+            from oracle import cv2_ref
+            small = synth.config(name, scale / 8.0)
+            Ks, Rs, gs = synth.cameras(small)
+            c = api.Context(self.local)
+            pd = cv2_ref.ProjData()
+            for j in range(small.n):
+                corner, tile, mask = api.project(small.kind, small.focal, Rs[j], Ks[j], synth.make_image(small, j, gs[j]), 1.0, True, c)
+                pd.imgs.append(tile); pd.msks.append(mask); pd.corners.append(tuple(corner))
+            c.close()
+            ansatz, radius = cv2_ref.estimate_circle(pd)
+            if ansatz is None:
+                return None, "estimate_circle found no midsection: no centre fix"
+            Ws, Hs, _, _ = cv2_ref.get_pan_dimension(pd.corners, pd.imgs)
+            Wf, Hf, _, _ = api.pan_dimension(self.corners, self.sizes)
+            # canvas pixel coordinates scale with the canvas; the +3 px safety offset of estimate_circle does not
+            ax, ay = int(round(ansatz[0] * Wf / Ws)), int(round(ansatz[1] * Hf / Hs))
+            r = (radius - 3.0) * (Wf / Ws) + 3.0
+            return _lib.CenterFix(ax, ay, float(r), 1), f"circle ({ax}, {ay}) r = {r:.1f} px (estimate_circle at 1/8 scale, scaled up), QUADRATIC_SCALING"
+        except Exception as e:
+            return None, "no centre fix (%s)" % repr(e)[:160]
+
     # ---- one step -------------------------------------------------------------------------------------------
     def step_dev(self):
         import ctypes as C
@@ -311,6 +346,11 @@ class Runner:
             self.session.step_band(self.ctx, self.descs_dev, host=False)
             self.enqueue_ms.append((time.perf_counter() - t0) * 1e3)
             return
+        if self.fix is not None:
+            self.ctx.check(self.ctx.lib.spano_dev_composite_fixed(self.ctx.h, cfg.kind, C.c_float(cfg.focal), cfg.n, self.descs_dev, cfg.bands,
+                                                                  cfg.sigma, C.byref(self.fix), self.row0, self.row1, self.d_canvas.data_ptr(),
+                                                                  self.d_canvas.stride(0)))
+            return
         self.ctx.check(self.ctx.lib.spano_dev_composite(self.ctx.h, cfg.kind, C.c_float(cfg.focal), cfg.n, self.descs_dev, cfg.bands, cfg.sigma,
                                                         self.row0, self.row1, self.d_canvas.data_ptr(), self.d_canvas.stride(0)))
 
@@ -321,6 +361,11 @@ class Runner:
             self.session.next_step()
             self.session.step_owner(self.ctx_s, self.descs_host, host=True)
             self.session.step_band(self.ctx, self.descs_host, host=True, host_canvas=(self.h_canvas.data_ptr(), self.h_canvas.stride(0)))
+            return
+        if self.fix is not None:
+            self.ctx.check(self.ctx.lib.spano_composite_fixed(self.ctx.h, cfg.kind, C.c_float(cfg.focal), cfg.n, self.descs_host, cfg.bands,
+                                                              cfg.sigma, C.byref(self.fix), self.row0, self.row1, self.h_canvas.data_ptr(),
+                                                              self.h_canvas.stride(0)))
             return
         self.ctx.check(self.ctx.lib.spano_composite(self.ctx.h, cfg.kind, C.c_float(cfg.focal), cfg.n, self.descs_host, cfg.bands, cfg.sigma,
                                                     self.row0, self.row1, self.h_canvas.data_ptr(), self.h_canvas.stride(0)))
@@ -433,7 +478,7 @@ def run_ours(args):
     stage_ms, stage_n, (px_done, px_offered) = stage
     px_done /= args.steps        # tile pixels the blend kernels filtered per step (mask_cut sparsity)
     px_offered /= args.steps
-    warp_T = sum(rn.sizes[j][0] * rn.sizes[j][1] for j in sorted(rn.mine))   # tiles this rank warps (all at N = 1)
+    warp_T = sum(rn.warp_sizes[j][0] * rn.warp_sizes[j][1] for j in sorted(rn.mine))   # tiles this rank warps (all at N = 1)
     fp32_peak = max(ctx.fp32_peak(0), ctx.fp32_peak(1), ctx.fp32_peak(2))
     peaks = {}
     try:
@@ -447,8 +492,8 @@ def run_ours(args):
     # isolated pass over the same tiles right here (same buffers, CUDA events on the launching stream).
     iso_tiles = sorted(rn.mine)
     al16 = lambda v: (v + 15) // 16 * 16
-    iso_tile = torch.empty(max(al16(3 * w) * h for (w, h) in rn.sizes), dtype=torch.uint8, device=dev)
-    iso_mask = torch.empty(max(al16(w) * h for (w, h) in rn.sizes), dtype=torch.uint8, device=dev)
+    iso_tile = torch.empty(max(al16(3 * w) * h for (w, h) in rn.warp_sizes), dtype=torch.uint8, device=dev)
+    iso_mask = torch.empty(max(al16(w) * h for (w, h) in rn.warp_sizes), dtype=torch.uint8, device=dev)
     iso_reps = 3
     with torch.cuda.stream(rn.stream):
         for rep in range(iso_reps + 1):
@@ -554,7 +599,7 @@ def run_ours(args):
         parity = {"max_abs_diff_lsb": int(d.max()), "differing_bytes": int((d > 0).sum()), "bytes": int(d.size), "shape_equal": got.shape == r["canvas"].shape,
                   "sample": f"images {s['idx']}, {s['rows']}-row strips, canvas {got.shape[1]}x{got.shape[0]}: the cpu_baseline sample's own inputs "
                             f"through spano_composite vs the cv2 result", "bar": "<= 1 LSB per channel"}
-    prim = {"W": rn.W, "H": rn.H, "T": rn.T}
+    prim = {"W": rn.W, "H": rn.H, "T": rn.T, "note": ("centre fix: " + rn.fix_note) if name == "cfg3" and world == 1 and hasattr(rn, "fix_note") else None}
     enqueue = float(np.median(rn.enqueue_ms)) if rn.enqueue_ms else None
     rn.close()
     del rn
@@ -602,7 +647,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": config_json(cfg, prim["W"], prim["H"], prim["T"], args, world), "e2e": e2e, "gpu_launches": int(launches),
+                "data": "synthetic", "config": config_json(cfg, prim["W"], prim["H"], prim["T"], args, world, prim.get("note")), "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "numa": numa,
                 "canvas_checksum": checksum, "cpu_enqueue_ms_per_step": enqueue,
                 "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu, "parity_at_bench_scale": parity,

@@ -248,6 +248,25 @@ int spano_composite(spano_ctx *ctx, int proj, float scale, int n, const spano_im
 int spano_dev_composite(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *images, int bands,
                         double sigma, int row0, int row1, uint8_t *canvas, size_t canvas_step);
 
+/* The fused path with the little-planet centre fix (conf.proj == STEREOGRAPHIC && conf.fix_center,
+ * src/classes/_panorama.cpp:292-311): between the warp and the gain every tile goes through sten_proj::disk_reproj
+ * (src/math/_projection.cpp:193-294) for the circle (ansatz, radius) that sten_proj::estimate_circle found -- the
+ * radial re-projection, the new corners / sizes and the recomputed validity masks all stay on the device.
+ * images[j].tl_x / tl_y / w / h describe the tiles as spano_warp_roi gives them (the warp needs those); the tiles that
+ * are blended have the corners and sizes of spano_disk_reproj_size, so the canvas is spano_pan_dimension of THOSE, and a
+ * tile-sized mask_cut[j] must have the new size (preview-scale masks are up-scaled to it).  fix == NULL: no centre fix
+ * (identical to spano_composite / spano_dev_composite).  spano_composite_fixed: HOST buffers; spano_dev_composite_fixed:
+ * DEVICE buffers, asynchronous.                                                                               */
+typedef struct spano_center_fix {
+    int ansatz_x, ansatz_y; /* circle centre in canvas pixel coordinates (sten_proj::estimate_circle) */
+    float radius;
+    int quadratic;          /* conf.stretching == QUADRATIC_SCALING */
+} spano_center_fix;
+int spano_composite_fixed(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *images, int bands, double sigma,
+                          const spano_center_fix *fix, int row0, int row1, uint8_t *canvas, size_t canvas_step);
+int spano_dev_composite_fixed(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *images, int bands,
+                              double sigma, const spano_center_fix *fix, int row0, int row1, uint8_t *canvas, size_t canvas_step);
+
 /* ---- device-pointer stage entry points (asynchronous on the context's stream) -------- */
 /* Validity mask of one warped tile without keeping the tile (a3 sampling + a4), DEVICE pointers. */
 int spano_dev_tile_mask(spano_ctx *ctx, int proj, float scale, const float K[9], const float R[9], const uint8_t *src_bgr,

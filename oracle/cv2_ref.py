@@ -219,6 +219,54 @@ def return_full(images, R, K, kind, focal, gains, masks_cut_fullres, bands, sigm
     return out, pd
 
 
+def analyze_components_with_circles(image: np.ndarray, min_area: float):
+    """util::analyzeComponentsWithCircles for a CV_8UC1 image (src/system/_util.cpp:8-81): connected components of the
+    ZERO pixels, and for every component of at least min_area pixels the minimum enclosing circle of its first external
+    contour.  Returns [(center(x, y), radius, distance from the image centre)]."""
+    mask = (255 - image).astype(np.uint8)          # Mat::ones * 255 - image
+    if cv2.countNonZero(mask) == 0:
+        raise RuntimeError("No connected components found: mask is entirely zero")
+    cx, cy = np.float32(image.shape[1] / 2.0), np.float32(image.shape[0] / 2.0)
+    num, labels, stats, _ = cv2.connectedComponentsWithStats(mask)
+    if num <= 1:
+        raise RuntimeError("No connected components found")
+    out = []
+    for i in range(1, num):
+        if stats[i, cv2.CC_STAT_AREA] >= min_area:
+            comp = np.where(labels == i, 255, 0).astype(np.uint8)
+            contours, _ = cv2.findContours(comp, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+            if contours:
+                (x, y), r = cv2.minEnclosingCircle(contours[0])
+                dx, dy = np.float32(x) - cx, np.float32(y) - cy
+                out.append(((np.float32(x), np.float32(y)), np.float32(r), np.float32(math.sqrt(float(dx * dx + dy * dy)))))
+    if not out:
+        raise RuntimeError("No components found with area >= %g" % min_area)
+    return out
+
+
+def estimate_circle(pd: ProjData):
+    """sten_proj::estimate_circle (src/math/_projection.cpp:361-419): the hole of the union of the validity masks that
+    lies nearest the canvas centre.  Returns ((ansatz_x, ansatz_y), radius) with cv::Point's rounding of the centre and
+    the reference's +3 offset, or (None, -1.0) when there is no midsection."""
+    W, H, min_x, min_y = get_pan_dimension(pd.corners, pd.imgs)
+    test = np.zeros((H, W), np.uint8)
+    for c, m in zip(pd.corners, pd.msks):
+        x0, y0 = c[0] - min_x, c[1] - min_y
+        roi = test[y0:y0 + m.shape[0], x0:x0 + m.shape[1]]
+        roi[m != 0] = m[m != 0]                     # copyTo(dst, mask)
+    circles = analyze_components_with_circles(test, 100)
+    dist = np.float32(math.sqrt(float(W * W + H * H)))
+    cutoff, cutoff_dist = (dist / 2) * np.float32(.5), (dist / 2) * np.float32(.2)
+    best = None
+    for j, (_, _, d) in enumerate(circles):
+        if dist > d:
+            dist, best = d, j
+    if best is None or dist > cutoff_dist or circles[best][1] > cutoff:
+        return None, -1.0
+    (x, y), r, _ = circles[best]
+    return (int(np.rint(x)), int(np.rint(y))), float(np.float32(r) + np.float32(3))   # cv::Point(Point2f) rounds to nearest
+
+
 def simple_blend(images, masks, top_lefts) -> np.ndarray:
     """blnd::simple_blend (src/math/_blending.cpp:83-153) through the same OpenCV entry points
     (distanceTransform, normalize(NORM_MINMAX), convertTo, mul, subtract) -> CV_8UC3 canvas."""

@@ -47,6 +47,11 @@ class ShardPlanC(C.Structure):
                 ("slices", C.POINTER(Slice)), ("flags", C.POINTER(C.c_void_p)), ("canvas", C.c_void_p), ("canvas_step", C.c_size_t)]
 
 
+class CenterFix(C.Structure):
+    """struct spano_center_fix"""
+    _fields_ = [("ansatz_x", C.c_int), ("ansatz_y", C.c_int), ("radius", C.c_float), ("quadratic", C.c_int)]
+
+
 class OverlapInfo(C.Structure):
     """struct spano_overlap_info == gain::OverlapInfo"""
     _fields_ = [("i", C.c_int), ("j", C.c_int), ("area", C.c_double), ("I_i", C.c_double), ("I_j", C.c_double)]
@@ -87,6 +92,10 @@ SYMBOLS = {
                                   C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_dev_composite": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int, C.POINTER(ImageDesc), C.c_int, C.c_double,
                                       C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "spano_composite_fixed": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int, C.POINTER(ImageDesc), C.c_int, C.c_double,
+                                        C.POINTER(CenterFix), C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "spano_dev_composite_fixed": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_int, C.POINTER(ImageDesc), C.c_int, C.c_double,
+                                            C.POINTER(CenterFix), C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_dev_tile_mask": (C.c_int, [C.c_void_p, C.c_int, C.c_float, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_size_t,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_dev_warp": (C.c_int, [C.c_void_p, C.c_int, C.c_float, c_f32p, c_f32p, C.c_void_p, C.c_int, C.c_int, C.c_size_t,

@@ -507,11 +507,14 @@ def adjust_intensity(img, field, ctx: Context | None = None) -> np.ndarray:
 
 
 def return_full(images, R, K, kind: int, focal: float, gains, masks_cut, bands: int, sigma: float,
-                rows: tuple[int, int] | None = None, ctx: Context | None = None, intensities=None):
+                rows: tuple[int, int] | None = None, ctx: Context | None = None, intensities=None, center_fix=None):
     """stitch_parameters::return_full (MULTI_BLEND, gain optional): decoded sources + K/R + gains +
     mask_cut[] (tile-sized or preview-scale) [+ intensity-correction fields when conf.blend_intensity]
     -> final CV_8UC3 canvas, through the fused device path.
-    `rows=(row0,row1)` restricts the result to a band of canvas rows (row-band sharding)."""
+    `rows=(row0,row1)` restricts the result to a band of canvas rows (row-band sharding).
+    `center_fix=((ansatz_x, ansatz_y), radius, quadratic)`: the little-planet centre fix (conf.fix_center with the
+    stereographic projection, src/classes/_panorama.cpp:292-311) for the circle sten_proj::estimate_circle found; the
+    blended tiles then have the corners / sizes of disk_reproj_size, and tile-sized masks must have those sizes."""
     ctx = ctx or default_context()
     n = len(images)
     if n == 0 or n != len(R) or n != len(K) or n != len(masks_cut):
@@ -519,14 +522,22 @@ def return_full(images, R, K, kind: int, focal: float, gains, masks_cut, bands: 
     imgs = [_u8img(a, 3, f"images[{i}]") for i, a in enumerate(images)]
     plan = plan_tiles(imgs, R, K, kind, focal, ctx)
     cuts = [_u8img(a, 1, f"mask_cut[{i}]") for i, a in enumerate(masks_cut)]
+    corners, sizes = [p[2] for p in plan], [p[3] for p in plan]
+    fix = None
+    if center_fix is not None:
+        (ax, ay), radius, quadratic = center_fix
+        corners, sizes = disk_reproj_size(corners, sizes, (ax, ay), radius, quadratic, ctx)
+        fix = _lib.CenterFix(int(ax), int(ay), float(radius), int(bool(quadratic)))
     for j in range(n):
-        w, h = plan[j][3]
         if cuts[j].size == 0:
             raise SpanoError(_lib.E_INVALID, f"mask_cut[{j}] is empty")
-        # any other size is taken as the preview-scale mask and resized to (h, w) on the device
-    W, H, _, _ = pan_dimension([p[2] for p in plan], [p[3] for p in plan])
+        # any size other than the (blended) tile's is taken as the preview-scale mask and resized on the device
+    W, H, _, _ = pan_dimension(corners, sizes)
     row0, row1 = rows if rows is not None else (0, H)
     descs = make_descs(imgs, plan, gains, cuts)
+    for j in range(n):   # (make_descs compared the mask with the WARP tile; with the centre fix the blended tile decides)
+        mh, mw = int(cuts[j].shape[0]), int(cuts[j].shape[1])
+        descs[j].mask_cut_w, descs[j].mask_cut_h = (0, 0) if (mw, mh) == tuple(sizes[j]) else (mw, mh)
     fields = None
     if intensities is not None:
         if len(intensities) != n:
@@ -537,6 +548,10 @@ def return_full(images, R, K, kind: int, focal: float, gains, masks_cut, bands: 
             descs[j].intensity_h, descs[j].intensity_w = int(f.shape[0]), int(f.shape[1])
             descs[j].intensity_step = f.strides[0]
     canvas = np.empty((row1 - row0, W, 3), np.uint8)
-    ctx.check(ctx.lib.spano_composite(ctx.h, int(kind), C.c_float(focal), n, descs, int(bands), float(sigma),
-                                      int(row0), int(row1), canvas.ctypes.data, canvas.strides[0]))
+    if fix is not None:
+        ctx.check(ctx.lib.spano_composite_fixed(ctx.h, int(kind), C.c_float(focal), n, descs, int(bands), float(sigma), C.byref(fix),
+                                                int(row0), int(row1), canvas.ctypes.data, canvas.strides[0]))
+    else:
+        ctx.check(ctx.lib.spano_composite(ctx.h, int(kind), C.c_float(focal), n, descs, int(bands), float(sigma),
+                                          int(row0), int(row1), canvas.ctypes.data, canvas.strides[0]))
     return canvas

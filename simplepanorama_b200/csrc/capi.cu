@@ -704,13 +704,39 @@ extern "C" int spano_multiblend(spano_ctx *ctx, int n, const uint8_t *const *til
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *im, int bands, double sigma,
-                   int row0, int row1, uint8_t *canvas, size_t canvas_step, bool host)
+int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *im_in, int bands, double sigma,
+                   int row0, int row1, uint8_t *canvas, size_t canvas_step, bool host, const spano_center_fix *fix = nullptr)
 {
-    if (n <= 0 || !im || !canvas) return spano_fail(ctx, SPANO_E_INVALID, "spano_composite: null/empty argument");
+    if (n <= 0 || !im_in || !canvas) return spano_fail(ctx, SPANO_E_INVALID, "spano_composite: null/empty argument");
     if (int rc = valid_proj(ctx, proj, scale)) return rc;
     std::vector<int> tlx(n), tly(n), ww(n), hh(n);
-    for (int j = 0; j < n; ++j) { tlx[j] = im[j].tl_x; tly[j] = im[j].tl_y; ww[j] = im[j].w; hh[j] = im[j].h; }
+    for (int j = 0; j < n; ++j) { tlx[j] = im_in[j].tl_x; tly[j] = im_in[j].tl_y; ww[j] = im_in[j].w; hh[j] = im_in[j].h; }
+    // Little-planet centre fix (sten_proj::disk_reproj between the warp and the gain, _panorama.cpp:292-311): every tile is
+    // re-projected radially, which gives it a new corner (relative to the canvas centre) and a new size; from here on
+    // `im` describes the tiles as the BLEND sees them, `orig` as the WARP produces them.
+    const spano_image_desc *orig = im_in;
+    std::vector<spano_image_desc> fixed;
+    SpanoDiskParams DP = {};
+    std::vector<int> org_x, org_y;
+    size_t pre_max = 0;
+    if (fix) {
+        for (int j = 0; j < n; ++j)
+            if (ww[j] <= 0 || hh[j] <= 0) return spano_fail(ctx, SPANO_E_INVALID, "tile %d is empty", j);
+        org_x.resize(n); org_y.resize(n);
+        std::vector<int> nx(n), ny(n), nw(n), nh(n);
+        if (spano_disk_plan(n, tlx.data(), tly.data(), ww.data(), hh.data(), fix->ansatz_x, fix->ansatz_y, fix->radius, fix->quadratic, &DP,
+                            org_x.data(), org_y.data(), nx.data(), ny.data(), nw.data(), nh.data()))
+            return spano_fail(ctx, SPANO_E_LIMIT, "degenerate tile in disk_reproj (no border samples)");
+        fixed.assign(im_in, im_in + n);
+        for (int j = 0; j < n; ++j) {
+            if (int rc = check_remap_limits(ctx, ww[j], hh[j], nw[j], nh[j])) return rc;
+            pre_max = std::max(pre_max, align_up(align_up((size_t)ww[j] * 3, 16) * hh[j], 256));
+            fixed[j].tl_x = tlx[j] = nx[j];  fixed[j].tl_y = tly[j] = ny[j];
+            fixed[j].w = ww[j] = nw[j];      fixed[j].h = hh[j] = nh[j];
+            if (fixed[j].valid_mask) return spano_fail(ctx, SPANO_E_INVALID, "a precomputed validity mask cannot be combined with the centre fix");
+        }
+    }
+    const spano_image_desc *im = fix ? fixed.data() : im_in;
     int cw, chh, mx, my;
     spano_pan_dimension(n, tlx.data(), tly.data(), ww.data(), hh.data(), &cw, &chh, &mx, &my);
     if (row0 < 0) row0 = 0;
@@ -740,7 +766,7 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
             field_max = std::max(field_max, align_up(align_up((size_t)im[j].intensity_w * 4, 16) * im[j].intensity_h, 256));
         }
         if (!(im[j].gain > 0.0)) return spano_fail(ctx, SPANO_E_INVALID, "gain[%d] must be > 0", j);
-        if (int rc = check_remap_limits(ctx, im[j].src_w, im[j].src_h, im[j].w, im[j].h)) return rc;
+        if (int rc = check_remap_limits(ctx, im[j].src_w, im[j].src_h, orig[j].w, orig[j].h)) return rc;
         const int cy = im[j].tl_y - my;
         if (cy + im[j].h <= row0 || cy >= row1) continue;
         use.push_back(j);
@@ -758,6 +784,9 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
     }
     float4 *acc = nullptr;
     if (int rc = spano_reserve(ctx, spano_ctx::BUF_ACC, (size_t)cw * rows * sizeof(float4), (void **)&acc)) return rc;
+    uint8_t *d_pre = nullptr;   // centre fix: the un-gained warp of the current image, before its radial re-projection
+    if (fix && pre_max)
+        if (int rc = spano_reserve(ctx, spano_ctx::BUF_PRETILE, pre_max, (void **)&d_pre)) return rc;
     uint8_t *d_tile = nullptr, *d_valid = nullptr, *d_srcbuf[2] = {nullptr, nullptr}, *d_cutbuf[2] = {nullptr, nullptr};
     uint8_t *d_cutsmall[2] = {nullptr, nullptr};
     float *d_field[2] = {nullptr, nullptr};
@@ -907,6 +936,27 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
                                      r0, r1, tile_b, t_step, nullptr, 0);
                 if (kk < 0) return kk;
                 t0.stop(kk);
+            } else if (fix) {
+                // warp (no gain, no mask) -> radial gather into the new tile -> dark flags + validity mask -> gain
+                const size_t p_step = align_up((size_t)orig[j].w * 3, 16);
+                StageTimer t0(ctx, 0);
+                int kk = launch_warp(ctx, P, src, orig[j].src_w, orig[j].src_h, s_step, 1.0, orig[j].tl_x, orig[j].tl_y, orig[j].w, orig[j].h, 0,
+                                     orig[j].h, d_pre, p_step, nullptr, 0);
+                if (kk < 0) return kk;
+                int k2 = launch_disk_gather(ctx, DP, d_pre, orig[j].w, orig[j].h, p_step, org_x[j], org_y[j], tile_b, im[j].w, im[j].h, t_step,
+                                            im[j].tl_x, im[j].tl_y);
+                if (k2 < 0) return k2;
+                t0.stop(kk + k2);
+                uint8_t *dark = nullptr;
+                if (int rc = spano_reserve(ctx, spano_ctx::BUF_DARK, m_step * im[j].h, (void **)&dark)) return rc;
+                StageTimer t1(ctx, 1);
+                int k3 = launch_dark_flags(ctx, tile_b, im[j].w, im[j].h, t_step, dark, m_step);
+                if (k3 < 0) return k3;
+                int k4 = launch_valid_mask(ctx, dark, im[j].w, im[j].h, m_step, 3, valid_b, m_step);
+                if (k4 < 0) return k4;
+                t1.stop(k3 + k4);
+                int k5 = launch_gain(ctx, tile_b, im[j].w, im[j].h, t_step, im[j].gain);
+                if (k5 < 0) return k5;
             } else if (int rc = dev_warp_tile(ctx, P, src, im[j].src_w, im[j].src_h, s_step, im[j].gain, im[j].tl_x, im[j].tl_y, im[j].w,
                                               im[j].h, tile_b, t_step, valid_b, m_step))
                 return rc;
@@ -992,6 +1042,35 @@ extern "C" int spano_dev_composite(spano_ctx *ctx, int proj, float scale, int n,
     if (!ctx) return SPANO_E_INVALID;
     Guard g(ctx);
     return composite_impl(ctx, proj, scale, n, images, bands, sigma, row0, row1, canvas, canvas_step, false);
+}
+
+namespace {
+int check_fix(spano_ctx *ctx, int proj, const spano_center_fix *fix)
+{
+    if (!fix) return 0;
+    if (proj != SPANO_STEREOGRAPHIC) return spano_fail(ctx, SPANO_E_INVALID, "the centre fix belongs to the stereographic projection (conf.proj == STEREOGRAPHIC)");
+    if (!(fix->radius > 0.f)) return spano_fail(ctx, SPANO_E_INVALID, "centre fix: radius must be > 0 (estimate_circle found no circle: pass NULL)");
+    return 0;
+}
+} // namespace
+
+extern "C" int spano_composite_fixed(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *images, int bands,
+                                     double sigma, const spano_center_fix *fix, int row0, int row1, uint8_t *canvas, size_t canvas_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (int rc = check_fix(ctx, proj, fix)) return rc;
+    return composite_impl(ctx, proj, scale, n, images, bands, sigma, row0, row1, canvas, canvas_step, true, fix);
+}
+
+extern "C" int spano_dev_composite_fixed(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *images, int bands,
+                                         double sigma, const spano_center_fix *fix, int row0, int row1, uint8_t *canvas,
+                                         size_t canvas_step)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (int rc = check_fix(ctx, proj, fix)) return rc;
+    return composite_impl(ctx, proj, scale, n, images, bands, sigma, row0, row1, canvas, canvas_step, false, fix);
 }
 
 // ---------------------------------------------------------------------------------------------

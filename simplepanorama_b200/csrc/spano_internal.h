@@ -46,7 +46,7 @@ struct spano_ctx {
     long long launches = 0;
     // grow-only scratch buffers, indexed by role
     enum { BUF_LABELS = 0, BUF_DARK, BUF_MASK0, BUF_TABLES, BUF_ACC, BUF_TILE, BUF_TILEMASK, BUF_CUTMASK, BUF_SRC,
-           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_BLENDPLAN, BUF_BLENDPLAN2, BUF_DT_TMP, BUF_DT_JOBS, BUF_DT_JOBS2, BUF_DT_ARENA, BUF_PREP_CUT, BUF_PREP_PLAN, BUF_RESIZE_AUX, BUF_TABLES_AUX, BUF_COUNT };
+           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_BLENDPLAN, BUF_BLENDPLAN2, BUF_DT_TMP, BUF_DT_JOBS, BUF_DT_JOBS2, BUF_DT_ARENA, BUF_PREP_CUT, BUF_PREP_PLAN, BUF_RESIZE_AUX, BUF_TABLES_AUX, BUF_PRETILE, BUF_COUNT };
     DeviceBuffer buf[BUF_COUNT];
     std::vector<void *> owned; // extra allocations freed at destroy / end of call
     unsigned long long *blend_stats = nullptr; // device: [0] tile pixels the blend processed, [1] tile pixels offered

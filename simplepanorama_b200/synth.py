@@ -52,9 +52,11 @@ def config(name: str, scale: float = 1.0) -> Config:
     elif name == "cfg2a":  # edge-case parity: true 360 deg ring, the tiles that straddle the +-pi seam come out full-width
         c = Config(name, CYLINDRICAL, 24, 6000, 4000, 5000.0, 6, 7.0, _ring(24, -172.5, 15.0), [0.0] * 24, 21,
                    "24 synthetic 24MP images, true 360deg cylindrical ring (f=5000): seam-straddling tiles are full-width")
-    elif name == "cfg3":  # 36 x 12MP stereographic little planet, 7 bands (looking down)
+    elif name == "cfg3":  # 36 x 12MP stereographic little planet, 7 bands (looking down; the lowest ring stops 5 degrees
+        # short of the nadir, so the planet has the hole in its middle that sten_proj::estimate_circle looks for and the
+        # centre fix closes)
         yaw = [30.0 * (k % 12) for k in range(36)]
-        pitch = [(-10.0, -40.0, -65.0)[k // 12] for k in range(36)]
+        pitch = [(-10.0, -35.0, -48.0)[k // 12] for k in range(36)]
         c = Config(name, STEREOGRAPHIC, 36, 4000, 3000, 2000.0, 7, 7.0, yaw, pitch, 3,
                    "stereographic little-planet render of 36 synthetic 12MP images, 7 bands")
     elif name == "cfg4":  # ~1 Gpx canvas, 200 x 24MP, spherical, 8 bands

@@ -29,7 +29,7 @@ def test_full_size_warp_is_bit_identical_to_cv2(ctx, name, j):
     mask_ref = cv2_ref.validity_mask(tile_ref)
     corner, tile, mask = api.project(cfg.kind, cfg.focal, R[j], K[j], img, 1.0, True, ctx)
     assert tuple(corner) == tuple(int(v) for v in corner_ref) and tile.shape == tile_ref.shape
-    assert tile.shape[0] * tile.shape[1] > 10e6
+    assert tile.shape[0] * tile.shape[1] > (10e6 if name != "cfg3" else 2e6)   # (stereographic tiles looking down are small)
     assert np.array_equal(tile, tile_ref), int((tile != tile_ref).sum())
     assert np.array_equal(mask, mask_ref), int((mask != mask_ref).sum())
     _, gained, _ = api.project(cfg.kind, cfg.focal, R[j], K[j], img, gains[j], True, ctx)
