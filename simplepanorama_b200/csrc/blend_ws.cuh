@@ -138,7 +138,12 @@ __device__ __forceinline__ void ws_row_item(const Params &P, const float *raw, f
         for (int b = 0; b < B; ++b) {
             unsigned long long a = 0ull;
 #pragma unroll
-            for (int k = 0; k <= R; ++k) ffma2_vs(a, plo[k], phi[k], c_taps[P.slot + b][k]);
+            for (int k = 0; k <= R; ++k) {
+                // B >= 9: both passes read ONE table (T[R + k] is the .x of the vertical pass's pair R + k), so that the taps
+                // of all bands stay inside the 4 KB constant cache (9 x (96 + 352) B would not: measured 2x slower)
+                const float t = (B >= 9) ? c_tap2[P.slot + b][R + k].x : c_taps[P.slot + b][k];
+                ffma2_vs(a, plo[k], phi[k], t);
+            }
             acc2[b][jp] = a;
         }
     }
