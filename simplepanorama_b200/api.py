@@ -98,7 +98,7 @@ class Context:
     def launch_count(self) -> int:
         return int(self.lib.spano_launch_count(self.h))
 
-    OPT_BLEND_DENSE, OPT_BLEND_KERNEL = 1, 2   # include/spano.h: SPANO_OPT_*
+    OPT_BLEND_DENSE, OPT_BLEND_KERNEL, OPT_FLAG_WAIT, OPT_WARP_KERNEL = 1, 2, 3, 4   # include/spano.h: SPANO_OPT_*
 
     def set_option(self, option: int, value: int):
         self.check(self.lib.spano_set_option(self.h, int(option), int(value)))

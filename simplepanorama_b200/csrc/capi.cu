@@ -272,6 +272,7 @@ extern "C" int spano_set_option(spano_ctx *ctx, int option, int value)
     switch (option) {
     case SPANO_OPT_BLEND_DENSE: ctx->opt_blend_dense = value != 0; return SPANO_OK;
     case SPANO_OPT_FLAG_WAIT: ctx->opt_flag_wait = value != 0; return SPANO_OK;
+    case SPANO_OPT_WARP_KERNEL: ctx->opt_warp_kernel = value != 0; return SPANO_OK;
     case SPANO_OPT_BLEND_KERNEL:
         if (value < 0 || value > 3) return spano_fail(ctx, SPANO_E_INVALID, "SPANO_OPT_BLEND_KERNEL: value %d not in [0,3]", value);
         ctx->opt_blend_kernel = value;

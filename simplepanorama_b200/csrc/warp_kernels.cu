@@ -22,6 +22,7 @@
 // For spherical / cylindrical the trigonometry is separable (u depends on the column, v on the
 // row): sin/cos are evaluated once per tile column / row into small tables, so the per-pixel work
 // is 9 mul/add + 2 div + the integer sampler.
+#include <cuda.h>   // CUtensorMap and its enums only: the encode entry point is looked up through the runtime
 #include "spano_internal.h"
 #include "glibc_trig.cuh"
 
@@ -179,6 +180,57 @@ __device__ __forceinline__ uint32_t sample_bilinear(const WarpParams &P, float x
     return B | (G << 8) | (R << 16);
 }
 
+// ---- TMA-staged variant ---------------------------------------------------------------------------------------------
+// The source footprint of a block of BLK_W x BLK_H destination pixels is a small rectangle of the source image (the
+// projections are smooth and the panorama scale equals the focal length, so the footprint is about the size of the
+// block).  One thread asks the TMA unit for a fixed-size box around it (cp.async.bulk.tensor.2d, source viewed as a 2-D
+// tensor of 32-bit words, out-of-bounds words zero-filled) and the block samples from shared memory: 32-bit shared
+// addresses instead of 64-bit global ones, no L1 tag traffic, one bulk request per block instead of ~8 k loads.
+// Correctness never depends on the box: a tap outside it (or outside the image interior) takes the global path.
+constexpr int BLK_W = 64, BLK_H = 16;             // destination pixels per block (256 threads x 4 px)
+constexpr int BOX_W = 72, BOX_H = 32;             // staged box: 72 words (288 B = 96 px) x 32 rows = 9216 B
+constexpr int BOX_PITCH = BOX_W * 4;
+
+struct alignas(64) TmaDesc { unsigned long long opaque[16]; };
+static_assert(sizeof(TmaDesc) == sizeof(CUtensorMap), "tensor map size");
+
+struct StagedBox {
+    const uint8_t *smem;   // the box (nullptr: nothing staged for this block)
+    int byte0;             // source byte offset (within a row) of the box's first byte
+    int row0;              // source row of the box's first row
+};
+
+// interior sample (all four taps inside the image) from the staged box; false: the taps are not all inside the box
+__device__ __forceinline__ bool sample_from_box(const WarpParams &P, const StagedBox &S, float x, float y, uint32_t &out)
+{
+    if (!(fabsf(x) < 67108864.f) || !(fabsf(y) < 67108864.f)) { out = 0u; return true; }
+    const int fx = __float2int_rn(x * 32.f), fy = __float2int_rn(y * 32.f);
+    const int sx = fx >> 5, sy = fy >> 5;
+    if (!((unsigned)sx < (unsigned)(P.src_w - 1) && (unsigned)sy < (unsigned)(P.src_h - 1))) return false;
+    const int ob = 3 * sx - S.byte0, rb = sy - S.row0;
+    if (!((unsigned)ob <= (unsigned)(BOX_PITCH - 12) && (unsigned)rb < (unsigned)(BOX_H - 1))) return false;
+    const int ax = fx & 31, ay = fy & 31;
+    const uint32_t wx = (uint32_t)(32 - ax) | ((uint32_t)ax << 24);
+    const int t8 = (ob & 3) * 8;
+    const uint32_t *w0 = reinterpret_cast<const uint32_t *>(S.smem + rb * BOX_PITCH + (ob & ~3));
+    uint32_t hb[2], hg[2], hr[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const uint32_t *w = w0 + r * BOX_W;
+        const uint32_t a = w[0], b = w[1], c = w[2];
+        const uint32_t lo = __funnelshift_r(a, b, t8), hi = __funnelshift_r(b, c, t8);
+        hb[r] = __dp4a(lo, wx, 0u);
+        hg[r] = __dp4a(__funnelshift_r(lo, hi, 8), wx, 0u);
+        hr[r] = __dp4a(__funnelshift_r(lo, hi, 16), wx, 0u);
+    }
+    const uint32_t wy0 = 32 - ay, wy1 = ay;
+    const uint32_t B = (wy0 * hb[0] + wy1 * hb[1] + 512u) >> 10;
+    const uint32_t G = (wy0 * hg[0] + wy1 * hg[1] + 512u) >> 10;
+    const uint32_t R = (wy0 * hr[0] + wy1 * hr[1] + 512u) >> 10;
+    out = B | (G << 8) | (R << 16);
+    return true;
+}
+
 // gray = (3735 B + 19235 G + 9798 R + 2^14) >> 15 (cv::cvtColor BGR2GRAY, 8 bit); dark = gray <= 1, i.e.
 // 3735 B + 19235 G + 9798 R < 3 * 2^14.  The 16-bit weights are split into bytes so two dp4a do the sum.
 __device__ __forceinline__ uint32_t is_dark(uint32_t bgr)
@@ -301,20 +353,11 @@ __device__ __forceinline__ void map_backward4(const WarpParams &P, int x0, int v
 constexpr int WARP_PX_PER_THREAD = 4;
 constexpr int WARP_BLOCK_X = 32, WARP_BLOCK_Y = 8;
 
+// 4 consecutive destination pixels x0..x0+3 of tile row v: coordinates, sampling (from the staged box when there is one),
+// dark flags, gain, stores (local tile or the band slices of the tile-sharded path)
 template <int KIND>
-__global__ void __launch_bounds__(WARP_BLOCK_X *WARP_BLOCK_Y) warp_kernel(const WarpParams P)
+__device__ __forceinline__ void warp_four_pixels(const WarpParams &P, const uint8_t *s_gain, const StagedBox &S, int x0, int v)
 {
-    // 8-bit gain as a 256-entry table (one shared-memory load per channel instead of convert/multiply/round/clamp)
-    __shared__ uint8_t s_gain[256];
-    {
-        const uint32_t t = threadIdx.y * WARP_BLOCK_X + threadIdx.x;
-        s_gain[t] = (uint8_t)(P.apply_gain ? gain_u8(t, P.inv_gain) : t);
-    }
-    __syncthreads();
-    const int x0 = (blockIdx.x * WARP_BLOCK_X + threadIdx.x) * WARP_PX_PER_THREAD;
-    const int v = P.row_begin + blockIdx.y * WARP_BLOCK_Y + threadIdx.y;
-    if (x0 >= P.dst_w || v >= P.row_end) return;
-
     uint32_t px[WARP_PX_PER_THREAD];
     uint32_t dark = 0;
     float mx[WARP_PX_PER_THREAD], my[WARP_PX_PER_THREAD];
@@ -324,7 +367,7 @@ __global__ void __launch_bounds__(WARP_BLOCK_X *WARP_BLOCK_Y) warp_kernel(const 
         const int u = x0 + i;
         uint32_t s = 0, d = 1;
         if (u < P.dst_w) {
-            s = sample_bilinear(P, mx[i], my[i]);
+            if (!(S.smem && sample_from_box(P, S, mx[i], my[i], s))) s = sample_bilinear(P, mx[i], my[i]);
             d = is_dark(s);
             s = (uint32_t)s_gain[s & 255u] | ((uint32_t)s_gain[(s >> 8) & 255u] << 8) | ((uint32_t)s_gain[(s >> 16) & 255u] << 16);
         }
@@ -361,6 +404,93 @@ __global__ void __launch_bounds__(WARP_BLOCK_X *WARP_BLOCK_Y) warp_kernel(const 
         else
             for (int i = 0; i < WARP_PX_PER_THREAD && x0 + i < P.dst_w; ++i) krow[i] = (uint8_t)(dark >> (8 * i));
     }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(WARP_BLOCK_X *WARP_BLOCK_Y) warp_kernel(const WarpParams P)
+{
+    // 8-bit gain as a 256-entry table (one shared-memory load per channel instead of convert/multiply/round/clamp)
+    __shared__ uint8_t s_gain[256];
+    {
+        const uint32_t t = threadIdx.y * WARP_BLOCK_X + threadIdx.x;
+        s_gain[t] = (uint8_t)(P.apply_gain ? gain_u8(t, P.inv_gain) : t);
+    }
+    __syncthreads();
+    const int x0 = (blockIdx.x * WARP_BLOCK_X + threadIdx.x) * WARP_PX_PER_THREAD;
+    const int v = P.row_begin + blockIdx.y * WARP_BLOCK_Y + threadIdx.y;
+    if (x0 >= P.dst_w || v >= P.row_end) return;
+    const StagedBox none = {nullptr, 0, 0};
+    warp_four_pixels<KIND>(P, s_gain, none, x0, v);
+}
+
+// The TMA-staged kernel: block = BLK_W x BLK_H destination pixels, 256 threads (16 x 16, 4 px each).
+template <int KIND>
+__global__ void __launch_bounds__(256) warp_tma_kernel(const WarpParams P, const __grid_constant__ TmaDesc tmap)
+{
+    __shared__ __align__(128) uint8_t s_box[BOX_H * BOX_PITCH];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint8_t s_gain[256];
+    __shared__ int s_meta[3];          // staged?, byte0, row0
+    const int tid = threadIdx.x;
+    s_gain[tid] = (uint8_t)(P.apply_gain ? gain_u8(tid, P.inv_gain) : tid);
+    const int bx0 = blockIdx.x * BLK_W, by0 = P.row_begin + blockIdx.y * BLK_H;
+    if (tid < 32) {
+        // footprint of the block from 9 probes (corners, edge midpoints, centre) of mapBackward
+        float lox = 3.0e38f, loy = 3.0e38f, hix = -3.0e38f, hiy = -3.0e38f;
+        bool bad = false;
+        if (tid < 9) {
+            const int pu = min(P.dst_w - 1, bx0 + (tid % 3) * (BLK_W / 2) - ((tid % 3) == 2 ? 1 : 0));
+            const int pv = min(P.row_end - 1, by0 + (tid / 3) * (BLK_H / 2) - ((tid / 3) == 2 ? 1 : 0));
+            float x, y;
+            map_backward<KIND>(P, pu, pv, x, y);
+            bad = !(fabsf(x) < 1.0e6f) || !(fabsf(y) < 1.0e6f) || (x == -1.f && y == -1.f);
+            lox = hix = x;  loy = hiy = y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o));  loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o));
+            hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));  hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (tid == 0) {
+            int staged = 0, byte0 = 0, row0 = 0;
+            if (!bad) {
+                const int px0 = (int)floorf(lox) - 2, px1 = (int)ceilf(hix) + 3;      // pixels px0 .. px1 (taps included)
+                row0 = (int)floorf(loy) - 2;
+                const int rows = (int)ceilf(hiy) + 3 - row0 + 1;
+                const int w0 = (3 * px0) >> 2;                                          // first word (floor, also for negatives)
+                byte0 = 4 * w0;
+                if (rows <= BOX_H && 3 * (px1 + 1) - byte0 <= BOX_PITCH - 8) staged = 1;
+                if (staged) {
+                    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar), dst = (uint32_t)__cvta_generic_to_shared(s_box);
+                    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(BOX_H * BOX_PITCH) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(w0), "r"(row0), "r"(bar) : "memory");
+                }
+            }
+            s_meta[0] = staged;  s_meta[1] = byte0;  s_meta[2] = row0;
+        }
+    }
+    __syncthreads();
+    StagedBox S = {nullptr, s_meta[1], s_meta[2]};
+    if (s_meta[0]) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+        asm volatile("{\n"
+                     ".reg .pred p;\n"
+                     "WAITW_%=:\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+                     "@p bra DONEW_%=;\n"
+                     "bra WAITW_%=;\n"
+                     "DONEW_%=:\n"
+                     "}" ::"r"(bar) : "memory");
+        S.smem = s_box;
+    }
+    const int x0 = bx0 + (tid & 15) * WARP_PX_PER_THREAD;
+    const int v = by0 + (tid >> 4);
+    if (x0 >= P.dst_w || v >= P.row_end) return;
+    warp_four_pixels<KIND>(P, s_gain, S, x0, v);
 }
 
 // buildMaps alone (float maps, as cv::detail::RotationWarperBase::buildMaps returns them)
@@ -407,6 +537,28 @@ __global__ void dark_flags_kernel(const uint8_t *bgr, int w, int h, size_t step,
 }
 
 } // namespace
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda):
+// the source image as a 2-D tensor of 32-bit words, box BOX_W x BOX_H, no swizzle, out-of-bounds words read as zero
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool encode_source_tensor_map(TmaDesc *out, const uint8_t *src, int src_w, int src_h, size_t src_step)
+{
+    static encode_tiled_fn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<encode_tiled_fn>(p);
+    }();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)(((size_t)src_w * 3 + 3) / 4), (cuuint64_t)src_h};
+    const cuuint64_t strides[1] = {(cuuint64_t)src_step};
+    const cuuint32_t box[2] = {BOX_W, BOX_H}, estr[2] = {1, 1};
+    return fn(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t *>(src), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 int launch_remap(spano_ctx *ctx, const uint8_t *src, int src_w, int src_h, size_t src_step, const float *xmap,
                  const float *ymap, int dst_w, int dst_h, uint8_t *dst, size_t dst_step)
@@ -473,6 +625,22 @@ int launch_warp(spano_ctx *ctx, const SpanoProjector &proj, const uint8_t *src, 
         SPANO_CUDA(ctx, cudaGetLastError());
         ctx->launches += launches;
         return launches;
+    }
+    // TMA-staged kernel when the source can be described as a 2-D tensor of 32-bit words (16-byte aligned base and pitch)
+    if (ctx->opt_warp_kernel == 0 && src && ((((uintptr_t)src) | src_step) & 15) == 0 && src_step >= (((size_t)src_w * 3 + 3) & ~(size_t)3)) {
+        TmaDesc tm;
+        if (encode_source_tensor_map(&tm, src, src_w, src_h, src_step)) {
+            dim3 tb(256), tg((dst_w + BLK_W - 1) / BLK_W, (row_end - row_begin + BLK_H - 1) / BLK_H);
+            switch (proj.kind) {
+            case SPANO_SPHERICAL: warp_tma_kernel<SPANO_SPHERICAL><<<tg, tb, 0, ctx->stream>>>(P, tm); break;
+            case SPANO_CYLINDRICAL: warp_tma_kernel<SPANO_CYLINDRICAL><<<tg, tb, 0, ctx->stream>>>(P, tm); break;
+            default: warp_tma_kernel<SPANO_STEREOGRAPHIC><<<tg, tb, 0, ctx->stream>>>(P, tm); break;
+            }
+            ++launches;
+            SPANO_CUDA(ctx, cudaGetLastError());
+            ctx->launches += launches;
+            return launches;
+        }
     }
     dim3 block(WARP_BLOCK_X, WARP_BLOCK_Y);
     dim3 grid((dst_w + WARP_BLOCK_X * WARP_PX_PER_THREAD - 1) / (WARP_BLOCK_X * WARP_PX_PER_THREAD),

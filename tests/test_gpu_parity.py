@@ -366,3 +366,30 @@ def test_band_composite_with_supplied_masks(ctx):
             ctx.sync()
             parts.append(out.cpu().numpy())
         assert np.array_equal(np.concatenate(parts, axis=0), full), world
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("width", [640, 643])
+def test_tma_staged_warp_equals_plain_warp(ctx, oracle, kind, width):
+    """The TMA-staged warp kernel (default when the source pitch is a multiple of 16 bytes) and the un-staged kernel
+    (SPANO_OPT_WARP_KERNEL = 1; also what a source with another pitch gets) produce the same bytes, and both equal the oracle:
+    noise image, strong rotation (the footprint of a block is then much larger than the block: blocks fall back), a pose
+    that leaves part of the tile outside the source (border taps)."""
+    from simplepanorama_b200 import api
+    rng = np.random.default_rng(70 + kind)
+    W, H, f = width, 480, 520.0
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    for (yaw, pitch, roll) in ((0.3, -0.35, 0.02), (0.1, -0.9 if kind == 2 else 0.2, 0.8)):
+        K = np.array([[f * 1.03, 0, W / 2 + 3.5], [0, f * 1.03, H / 2 - 2.25], [0, 0, 1]])
+        R = _rot(yaw, pitch, roll)
+        K32, R32 = api.adjusted_camera(K, R, W, H)
+        _, ref = oracle.warp(kind, np.float32(f), K32, R32, img)
+        outs = []
+        for mode in (0, 1):
+            ctx.set_option(ctx.OPT_WARP_KERNEL, mode)
+            try:
+                outs.append(api.project(kind, f, R, K, img, 1.3, True, ctx))
+            finally:
+                ctx.set_option(ctx.OPT_WARP_KERNEL, 0)
+        assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+        assert np.array_equal(outs[0][1], oracle.apply_gain(ref, 1.3))
