@@ -137,6 +137,16 @@ int spano_resize_mask(spano_ctx *ctx, const uint8_t *src, int src_w, int src_h, 
 int spano_adjust_intensity(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, const float *field, int field_w,
                            int field_h, size_t field_step);
 
+/* test::equalizeIntensities(images, masks, top_lefts, ratio) (src/test/_test.cpp:9-106), the solve that produces the
+ * correction fields spano_adjust_intensity consumes: called by stitch_parameters::set_config on the preview-size warps
+ * when conf.blend_intensity is on (src/classes/_panorama.cpp:131-133).  tiles 8UC3, masks 8UC1 (validity masks), one
+ * CV_32FC1 field per image of the size spano_equalize_intensities_size gives (cv::resize(.., Size(), ratio, ratio)).
+ * field_steps in BYTES.  HOST buffers.  The integer stages are bit-exact with OpenCV, the fields within 1e-5 relative. */
+int spano_equalize_intensities_size(int w, int h, float ratio, int *field_w, int *field_h);
+int spano_equalize_intensities(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps,
+                               const uint8_t *const *masks, const size_t *mask_steps, const int *tl_x, const int *tl_y,
+                               const int *w, const int *h, float ratio, float *const *fields, const size_t *field_steps);
+
 /* ---- seam search by distance (preview scale) ---------------------------------
  * spano_distance_transform = cv::distanceTransform(mask, dist, cv::DIST_L2, cv::DIST_MASK_5, CV_32F) on CV_8UC1
  * (reference src/math/_distance_cut.cpp:63, src/math/_blending.cpp:110): distance of every pixel to the nearest

@@ -219,6 +219,55 @@ def return_full(images, R, K, kind, focal, gains, masks_cut_fullres, bands, sigm
     return out, pd
 
 
+def scale_rect(r, xs: float, ys: float):
+    """util::scaleRect (src/system/_util.cpp:157-166): (x, y, w, h) with std::round (half away from zero)."""
+    rnd = lambda v: int(math.floor(abs(v) + 0.5)) * (1 if v >= 0 else -1)
+    return rnd(r[0] * xs), rnd(r[1] * ys), rnd(r[2] * xs), rnd(r[3] * ys)
+
+
+def equalize_intensities(images, masks, top_lefts, ratio: float = 0.5):
+    """test::equalizeIntensities (src/test/_test.cpp:9-106): the per-image intensity-correction fields (CV_32FC1 at
+    `ratio` of the preview size) that test::adjust_intensity later divides the tiles by.  Same OpenCV calls in the same
+    order; MatExpr / scalar arithmetic on CV_32F is float arithmetic."""
+    n = len(images)
+    inv255 = np.float32(1.0 / 255.0)
+    eps = np.float32(0.00001)
+    D = [cv2.distanceTransform(m, cv2.DIST_L2, cv2.DIST_MASK_5) * inv255 for m in masks]     # dcut::distance_transform
+    _, _, min_x, min_y = get_pan_dimension(top_lefts, images)
+    msk_s, inten, idist, rois = [], [], [], []
+    for i in range(n):
+        ms = cv2.resize(masks[i], None, fx=ratio, fy=ratio, interpolation=cv2.INTER_LINEAR)
+        im = cv2.resize(images[i], None, fx=ratio, fy=ratio, interpolation=cv2.INTER_LINEAR)
+        D[i] = cv2.resize(D[i], None, fx=ratio, fy=ratio, interpolation=cv2.INTER_LINEAR)
+        gray = cv2.cvtColor(im, cv2.COLOR_BGR2GRAY).astype(np.float32) * inv255
+        gm = np.where(ms != 0, gray, np.float32(0)).astype(np.float32)
+        msk_s.append(ms); inten.append(gm); idist.append((gm * D[i]).astype(np.float32))
+        roi = (top_lefts[i][0] - min_x, top_lefts[i][1] - min_y, masks[i].shape[1], masks[i].shape[0])
+        rois.append(scale_rect(roi, im.shape[1] / images[i].shape[1], im.shape[0] / images[i].shape[0]))
+    out = []
+    for i in range(n):
+        alpha, it = D[i].copy(), idist[i].copy()
+        for j in range(n):
+            if i == j:
+                continue
+            x0, y0 = max(rois[i][0], rois[j][0]), max(rois[i][1], rois[j][1])
+            x1 = min(rois[i][0] + rois[i][2], rois[j][0] + rois[j][2]); y1 = min(rois[i][1] + rois[i][3], rois[j][1] + rois[j][3])
+            if x1 <= x0 or y1 <= y0:
+                continue
+            si = (slice(y0 - rois[i][1], y1 - rois[i][1]), slice(x0 - rois[i][0], x1 - rois[i][0]))
+            sj = (slice(y0 - rois[j][1], y1 - rois[j][1]), slice(x0 - rois[j][0], x1 - rois[j][0]))
+            on = msk_s[i][si] != 0
+            it[si] = np.where(on, it[si] + idist[j][sj], it[si])
+            alpha[si] = np.where(on, alpha[si] + D[j][sj], alpha[si])
+        alpha = alpha + eps
+        test = cv2.divide(it, alpha)
+        test = test + eps
+        test = cv2.divide(inten[i], test)
+        test = test + (255 - msk_s[i]).astype(np.float32) * inv255
+        out.append(cv2.GaussianBlur(test, (13, 13), sigmaX=7, sigmaY=7, borderType=cv2.BORDER_REFLECT))
+    return out
+
+
 def analyze_components_with_circles(image: np.ndarray, min_area: float):
     """util::analyzeComponentsWithCircles for a CV_8UC1 image (src/system/_util.cpp:8-81): connected components of the
     ZERO pixels, and for every component of at least min_area pixels the minimum enclosing circle of its first external

@@ -11,7 +11,7 @@
 //   blnd::multi_blend, simple_blend, no_blend                                     src/math/_blending.cpp:83-252
 //   dcut::distance_transform, dcut::dist_cut                                      src/math/_distance_cut.cpp:7-73
 //   gain::get_overlapp_intensity                                                  src/math/_gain_compensation.cpp:7-75
-//   test::adjust_intensity                                                        src/test/_test.cpp:110-122
+//   test::equalizeIntensities, test::adjust_intensity                             src/test/_test.cpp:9-122
 //
 // Each body only converts cv::Mat / Eigen arguments to pointers + sizes and forwards to the C ABI
 // (include/spano.h).  Errors come back as status codes and are re-thrown as std::runtime_error, the
@@ -207,6 +207,29 @@ cv::Mat no_blend(const std::vector<cv::Mat> &images, const std::vector<cv::Mat> 
 } // namespace blnd
 
 namespace test {
+
+// src/test/_test.cpp:9-106 (called from stitch_parameters::set_config when conf.blend_intensity is on)
+std::vector<cv::Mat> equalizeIntensities(const std::vector<cv::Mat> &images, const std::vector<cv::Mat> &masks,
+                                         const std::vector<cv::Point> &top_lefts, float ratio)
+{
+    const int n = (int)images.size();
+    std::vector<const uint8_t *> t(n), m(n);
+    std::vector<size_t> ts(n), ms(n), fs(n);
+    std::vector<int> x(n), y(n), w(n), h(n);
+    std::vector<cv::Mat> fields(n);
+    std::vector<float *> f(n);
+    for (int i = 0; i < n; ++i) {
+        t[i] = images[i].data; ts[i] = images[i].step; m[i] = masks[i].data; ms[i] = masks[i].step;
+        x[i] = top_lefts[i].x; y[i] = top_lefts[i].y; w[i] = images[i].cols; h[i] = images[i].rows;
+        int fw = 0, fh = 0;
+        check(spano_equalize_intensities_size(w[i], h[i], ratio, &fw, &fh));
+        fields[i].create(fh, fw, CV_32FC1);
+        f[i] = fields[i].ptr<float>(); fs[i] = fields[i].step;
+    }
+    check(spano_equalize_intensities(ctx(), n, t.data(), ts.data(), m.data(), ms.data(), x.data(), y.data(), w.data(), h.data(), ratio,
+                                     f.data(), fs.data()));
+    return fields;
+}
 
 // src/test/_test.cpp:110-122 (called from return_full / get_preview when conf.blend_intensity is on)
 void adjust_intensity(std::vector<cv::Mat> &images, const std::vector<cv::Mat> &intensities)

@@ -75,6 +75,9 @@ SYMBOLS = {
     "spano_surrounding_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]),
     "spano_resize_mask": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
     "spano_adjust_intensity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
+    "spano_equalize_intensities_size": (C.c_int, [C.c_int, C.c_int, C.c_float, c_intp, c_intp]),
+    "spano_equalize_intensities": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_u8pp, c_sizep, c_intp, c_intp, c_intp, c_intp, C.c_float,
+                                             c_u8pp, c_sizep]),
     "spano_distance_transform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_size_t]),
     "spano_dist_cut": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_intp, c_intp, c_intp, c_intp, c_u8pp, c_sizep]),
     "spano_simple_blend": (C.c_int, [C.c_void_p, C.c_int, c_u8pp, c_sizep, c_u8pp, c_sizep, c_intp, c_intp, c_intp, c_intp, C.c_void_p, C.c_size_t]),

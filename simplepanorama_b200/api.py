@@ -401,6 +401,29 @@ def make_descs(images, plan, gains, masks_cut, ptr_of=lambda a: a.ctypes.data, s
     return descs
 
 
+def equalize_intensities(images, masks, top_lefts, ratio: float = 0.5, ctx: Context | None = None):
+    """test::equalizeIntensities(images, masks, top_lefts, ratio) (src/test/_test.cpp:9-106): the CV_32FC1 intensity-
+    correction field of every preview-size warp (validity masks as `masks`), ready for adjust_intensity."""
+    ctx = ctx or default_context()
+    n = len(images)
+    if n == 0 or n != len(masks) or n != len(top_lefts):
+        raise SpanoError(_lib.E_INVALID, "Input consistency!")
+    imgs = [_u8img(a, 3, f"images[{i}]") for i, a in enumerate(images)]
+    msks = [_u8img(a, 1, f"masks[{i}]") for i, a in enumerate(masks)]
+    w = np.array([a.shape[1] for a in imgs], np.int32); h = np.array([a.shape[0] for a in imgs], np.int32)
+    tlx = np.array([c[0] for c in top_lefts], np.int32); tly = np.array([c[1] for c in top_lefts], np.int32)
+    outs = []
+    for i in range(n):
+        fw, fh = C.c_int(), C.c_int()
+        ctx.check(ctx.lib.spano_equalize_intensities_size(int(w[i]), int(h[i]), C.c_float(ratio), C.byref(fw), C.byref(fh)))
+        outs.append(np.empty((fh.value, fw.value), np.float32))
+    ptr = lambda arrs: (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    steps = lambda arrs: (C.c_size_t * n)(*[a.strides[0] for a in arrs])
+    ctx.check(ctx.lib.spano_equalize_intensities(ctx.h, n, ptr(imgs), steps(imgs), ptr(msks), steps(msks), _ip(tlx), _ip(tly), _ip(w), _ip(h),
+                                                 C.c_float(ratio), ptr(outs), steps(outs)))
+    return outs
+
+
 def resize_mask(mask, size_wh, ctx: Context | None = None) -> np.ndarray:
     """cv::resize(mask, dst, size) on CV_8UC1 with the default INTER_LINEAR -- return_full's mask_cut
     up-scaling (src/classes/_panorama.cpp:329-335)."""

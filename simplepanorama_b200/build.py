@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libspano.so")
 
-CU_SOURCES = ["warp_kernels.cu", "mask_kernels.cu", "blend_kernels.cu", "disk_kernels.cu", "resize_kernels.cu", "dist_kernels.cu", "capi.cu"]
+CU_SOURCES = ["warp_kernels.cu", "mask_kernels.cu", "blend_kernels.cu", "disk_kernels.cu", "resize_kernels.cu", "dist_kernels.cu", "equalize_kernels.cu", "capi.cu"]
 CPP_SOURCES = ["projector_host.cpp"]
 HEADERS = ["spano_internal.h", os.path.join("..", "..", "include", "spano.h")]
 

@@ -1788,6 +1788,59 @@ extern "C" int spano_dist_cut(spano_ctx *ctx, int n, const uint8_t *const *masks
 }
 
 // ---------------------------------------------------------------------------------------------
+// test::equalizeIntensities, host buffers
+// ---------------------------------------------------------------------------------------------
+extern "C" int spano_equalize_intensities_size(int w, int h, float ratio, int *field_w, int *field_h)
+{
+    if (w <= 0 || h <= 0 || !(ratio > 0.f) || !field_w || !field_h) return SPANO_E_INVALID;
+    spano_equalize_field_size(w, h, ratio, field_w, field_h);
+    return (*field_w > 0 && *field_h > 0) ? SPANO_OK : SPANO_E_INVALID;
+}
+
+extern "C" int spano_equalize_intensities(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tile_steps,
+                                          const uint8_t *const *masks, const size_t *mask_steps, const int *tl_x, const int *tl_y,
+                                          const int *w, const int *h, float ratio, float *const *fields, const size_t *field_steps)
+{
+    if (!ctx) return SPANO_E_INVALID;
+    Guard g(ctx);
+    if (n <= 0 || !tiles || !tile_steps || !masks || !mask_steps || !tl_x || !tl_y || !w || !h || !fields || !field_steps)
+        return spano_fail(ctx, SPANO_E_INVALID, "spano_equalize_intensities: null/empty argument");
+    if (!(ratio > 0.f) || ratio > 1.f) return spano_fail(ctx, SPANO_E_INVALID, "spano_equalize_intensities: ratio must be in (0, 1]");
+    size_t total = 0;
+    std::vector<size_t> off_t(n), off_m(n), off_f(n), ts(n), ms(n), fp(n);
+    std::vector<int> fw(n), fh(n);
+    for (int k = 0; k < n; ++k) {
+        if (int rc = check_image_args(ctx, tiles[k], w[k], h[k], tile_steps[k], 3, "tile")) return rc;
+        if (int rc = check_image_args(ctx, masks[k], w[k], h[k], mask_steps[k], 1, "mask")) return rc;
+        spano_equalize_field_size(w[k], h[k], ratio, &fw[k], &fh[k]);
+        if (fw[k] <= 0 || fh[k] <= 0) return spano_fail(ctx, SPANO_E_INVALID, "image %d is too small for ratio %g", k, (double)ratio);
+        if (!fields[k] || field_steps[k] < (size_t)fw[k] * sizeof(float)) return spano_fail(ctx, SPANO_E_INVALID, "field %d: null pointer or step too small", k);
+        ts[k] = align_up((size_t)w[k] * 3, 16);
+        ms[k] = align_up((size_t)w[k], 16);
+        fp[k] = align_up((size_t)fw[k], 4);
+        off_t[k] = total;  total += align_up(ts[k] * h[k], 256);
+        off_m[k] = total;  total += align_up(ms[k] * h[k], 256);
+        off_f[k] = total;  total += align_up(fp[k] * fh[k] * sizeof(float), 256);
+    }
+    uint8_t *arena = nullptr;
+    if (int rc = spano_reserve(ctx, spano_ctx::BUF_TILE, total, (void **)&arena)) return rc;
+    std::vector<const uint8_t *> dt(n), dm(n);
+    std::vector<float *> df(n);
+    for (int k = 0; k < n; ++k) {
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(arena + off_t[k], ts[k], tiles[k], tile_steps[k], (size_t)w[k] * 3, h[k], cudaMemcpyHostToDevice, ctx->stream));
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(arena + off_m[k], ms[k], masks[k], mask_steps[k], (size_t)w[k], h[k], cudaMemcpyHostToDevice, ctx->stream));
+        dt[k] = arena + off_t[k];  dm[k] = arena + off_m[k];  df[k] = reinterpret_cast<float *>(arena + off_f[k]);
+    }
+    int rc = launch_equalize_intensities(ctx, n, dt.data(), ts.data(), dm.data(), ms.data(), tl_x, tl_y, w, h, ratio, df.data(), fp.data());
+    if (rc < 0) return rc;
+    for (int k = 0; k < n; ++k)
+        SPANO_CUDA(ctx, cudaMemcpy2DAsync(fields[k], field_steps[k], df[k], fp[k] * sizeof(float), (size_t)fw[k] * sizeof(float), fh[k],
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+    SPANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SPANO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // blnd::simple_blend / blnd::no_blend, host buffers
 // ---------------------------------------------------------------------------------------------
 namespace {

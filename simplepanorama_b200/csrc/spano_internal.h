@@ -46,7 +46,7 @@ struct spano_ctx {
     long long launches = 0;
     // grow-only scratch buffers, indexed by role
     enum { BUF_LABELS = 0, BUF_DARK, BUF_MASK0, BUF_TABLES, BUF_ACC, BUF_TILE, BUF_TILEMASK, BUF_CUTMASK, BUF_SRC,
-           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_BLENDPLAN, BUF_BLENDPLAN2, BUF_DT_TMP, BUF_DT_JOBS, BUF_DT_JOBS2, BUF_DT_ARENA, BUF_PREP_CUT, BUF_PREP_PLAN, BUF_RESIZE_AUX, BUF_TABLES_AUX, BUF_PRETILE, BUF_COUNT };
+           BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_BLENDPLAN, BUF_BLENDPLAN2, BUF_DT_TMP, BUF_DT_JOBS, BUF_DT_JOBS2, BUF_DT_ARENA, BUF_PREP_CUT, BUF_PREP_PLAN, BUF_RESIZE_AUX, BUF_TABLES_AUX, BUF_PRETILE, BUF_EQUALIZE, BUF_COUNT };
     DeviceBuffer buf[BUF_COUNT];
     std::vector<void *> owned; // extra allocations freed at destroy / end of call
     unsigned long long *blend_stats = nullptr; // device: [0] tile pixels the blend processed, [1] tile pixels offered
@@ -174,6 +174,11 @@ int launch_overlap_sums(spano_ctx *ctx, const uint8_t *gi, size_t gis, const uin
 #define SPANO_MAX_FLAG_TARGETS 16
 int launch_flag_signal(spano_ctx *ctx, uint32_t *const *targets, int n, uint32_t value);
 int launch_flag_wait_kernel(spano_ctx *ctx, const uint32_t *flag, uint32_t value);
+// equalize_kernels.cu: test::equalizeIntensities (device buffers at preview scale)
+void spano_equalize_field_size(int w, int h, float ratio, int *fw, int *fh);
+int launch_equalize_intensities(spano_ctx *ctx, int n, const uint8_t *const *tiles, const size_t *tsteps, const uint8_t *const *masks,
+                                const size_t *msteps, const int *tl_x, const int *tl_y, const int *w, const int *h, float ratio,
+                                float *const *out, const size_t *opitch);
 // disk_kernels.cu: stereographic centre fix (util::RadialNormalizer state + normalised radius)
 struct SpanoDiskParams {
     float cx, cy, scale;
