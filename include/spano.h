@@ -81,8 +81,9 @@ long long spano_launch_count(spano_ctx *ctx);
  *                             same arithmetic in the same order as the default, bit-identical canvas)           */
 #define SPANO_OPT_BLEND_DENSE 1
 #define SPANO_OPT_BLEND_KERNEL 2
-#define SPANO_OPT_WARP_KERNEL 4 /* 0 (default): the warp kernel stages the source footprint of each block with TMA; 1: the
-                                   un-staged kernel (global loads only).  Same integer arithmetic: bit-identical tiles.       */
+#define SPANO_OPT_WARP_KERNEL 4 /* 1: the warp kernel stages the source footprint of each block of destination pixels with TMA
+                                   (cp.async.bulk.tensor.2d) and samples from shared memory; 0 (default): global loads only.
+                                   Same integer arithmetic: bit-identical tiles.                                           */
 #define SPANO_OPT_FLAG_WAIT 3 /* 0 (default): stream memory operations; 1: a one-thread polling kernel (spano_shard_step_*) */
 int spano_set_option(spano_ctx *ctx, int option, int value);
 

@@ -81,7 +81,7 @@ struct spano_ctx {
     int tap_slot = -1;                     // marching kernel: constant-memory slot holding these taps (-1: none)
     // spano_set_option
     int opt_blend_dense = 0;               // 1: ignore the mask_cut sparsity (every tile pixel is filtered)
-    int opt_warp_kernel = 0;               // 1: the plain (un-staged) warp kernel instead of the TMA-staged one
+    int opt_warp_kernel = 0;               // 1: the TMA-staged warp kernel instead of the plain (un-staged) one
     int opt_flag_wait = 0;                 // 1: wait for readiness flags with a polling kernel instead of cuStreamWaitValue32
     int opt_blend_kernel = 0;              // 1: always the generic-radius blend kernel (cross-check of the marching one)
     // timers

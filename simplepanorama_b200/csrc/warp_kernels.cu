@@ -627,7 +627,7 @@ int launch_warp(spano_ctx *ctx, const SpanoProjector &proj, const uint8_t *src, 
         return launches;
     }
     // TMA-staged kernel when the source can be described as a 2-D tensor of 32-bit words (16-byte aligned base and pitch)
-    if (ctx->opt_warp_kernel == 0 && src && ((((uintptr_t)src) | src_step) & 15) == 0 && src_step >= (((size_t)src_w * 3 + 3) & ~(size_t)3)) {
+    if (ctx->opt_warp_kernel == 1 && src && ((((uintptr_t)src) | src_step) & 15) == 0 && src_step >= (((size_t)src_w * 3 + 3) & ~(size_t)3)) {
         TmaDesc tm;
         if (encode_source_tensor_map(&tm, src, src_w, src_h, src_step)) {
             dim3 tb(256), tg((dst_w + BLK_W - 1) / BLK_W, (row_end - row_begin + BLK_H - 1) / BLK_H);

@@ -371,8 +371,8 @@ def test_band_composite_with_supplied_masks(ctx):
 @pytest.mark.parametrize("kind", [0, 1, 2])
 @pytest.mark.parametrize("width", [640, 643])
 def test_tma_staged_warp_equals_plain_warp(ctx, oracle, kind, width):
-    """The TMA-staged warp kernel (default when the source pitch is a multiple of 16 bytes) and the un-staged kernel
-    (SPANO_OPT_WARP_KERNEL = 1; also what a source with another pitch gets) produce the same bytes, and both equal the oracle:
+    """The TMA-staged warp kernel (SPANO_OPT_WARP_KERNEL = 1, taken when the source pitch is a multiple of 16 bytes) and the
+    un-staged kernel (also what a source with another pitch gets) produce the same bytes, and both equal the oracle:
     noise image, strong rotation (the footprint of a block is then much larger than the block: blocks fall back), a pose
     that leaves part of the tile outside the source (border taps)."""
     from simplepanorama_b200 import api

@@ -1,4 +1,4 @@
-"""One full-size tile through the warp kernel (for ncu): python tools/profile_warp.py [cfg] [image] [reps]"""
+"""One tile through the warp kernel (for ncu): python tools/profile_warp.py [cfg] [image] [reps] [scale] [SPANO_OPT_WARP_KERNEL]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,10 +8,13 @@ from simplepanorama_b200 import api, synth
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 j = int(sys.argv[2]) if len(sys.argv) > 2 else 11
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
-cfg = synth.config(name)
+scale = float(sys.argv[4]) if len(sys.argv) > 4 else 1.0
+mode = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+cfg = synth.config(name, scale)
 K, R, gains = synth.cameras(cfg)
 img = synth.make_image(cfg, j, gains[j])
 ctx = api.Context(0)
+ctx.set_option(ctx.OPT_WARP_KERNEL, mode)
 dev = torch.device("cuda", 0)
 plan = api.plan_tiles([img], [R[j]], [K[j]], cfg.kind, cfg.focal)
 K32, R32, (tlx, tly), (w, h) = plan[0]
@@ -31,4 +34,4 @@ for _ in range(reps):
 ctx.sync()
 ms, n = ctx.timers_read()
 t = ms["warp"] / reps
-print(f"{name} image {j}: tile {w}x{h} = {w*h/1e6:.2f} Mpx, warp {t:.4f} ms ({7*w*h/t/1e6:.0f} GB/s algorithmic = {7*w*h/t/1e6/6535.7:.3f} of 6535.7), mask {ms['mask']/reps:.4f} ms")
+print(f"{name} x{scale} kernel={mode} image {j}: tile {w}x{h} = {w*h/1e6:.2f} Mpx, warp {t:.4f} ms ({7*w*h/t/1e6:.0f} GB/s algorithmic = {7*w*h/t/1e6/6535.7:.3f} of 6535.7), mask {ms['mask']/reps:.4f} ms")
