@@ -116,7 +116,7 @@ def config_json(cfg, W, H, T, args, world, note=None):
          "projection": ["spherical", "cylindrical", "stereographic"][cfg.kind], "focal": cfg.focal, "bands": cfg.bands,
          "sigma": cfg.sigma, "canvas": [W, H], "tile_mpx": round(T / 1e6, 1),
          "sharding": (f"tile-sharded warp+mask (owner by band locality) -> NVLink peer stores -> row-band blend x{world}, ordered by "
-                      f"readiness flags (cuStreamWaitValue32)" if world > 1 else "single GPU"),
+                      f"readiness flags (cuStreamWaitValue32); two alternating sets of slice arenas, so the owners' warps of step s+1 overlap the blends of step s" if world > 1 else "single GPU"),
          "mask_cut": "preview scale (1/8), resized to tile size on the device inside the step",
          "l2": "inputs larger than L2 (sources 1.7 GB vs 126 MB)", "scale": args.scale}
     if note:
@@ -305,10 +305,11 @@ class Runner:
             self.aux = torch.cuda.Stream(device=dev)
             self.ctx_s.set_stream(self.aux.cuda_stream)
             self.arenas = sdist.PeerArenas(self.ctx, self.sp, rank)
+            self.arenas2 = sdist.PeerArenas(self.ctx, self.sp, rank)   # even / odd steps use different arenas (done_lag = 2)
             self.flags = sdist.PeerFlags(self.ctx, self.sp, rank)
             self.peer_canvas = sdist.PeerCanvas(self.ctx, self.sp, rank)   # the canvas lives on rank 0
             self.session = sdist.ShardSession(self.sp, rank, cfg.kind, cfg.focal, cfg.bands, cfg.sigma, self.arenas.ptrs, self.flags.ptrs,
-                                              self.peer_canvas.band_ptr(self.row0), self.peer_canvas.step)
+                                              self.peer_canvas.band_ptr(self.row0), self.peer_canvas.step, arena_ptrs2=self.arenas2.ptrs)
         self.enqueue_ms = []
 
     def _estimate_circle(self, api, synth, name, scale):
@@ -438,6 +439,7 @@ class Runner:
         if self.world > 1:
             self.tdist.barrier()
             self.arenas.close()
+            self.arenas2.close()
             self.flags.close()
             self.peer_canvas.close()
             self.ctx_s.close()

@@ -407,6 +407,10 @@ typedef struct spano_shard_plan {
     uint32_t *const *flags;     /* [world] */
     uint8_t *canvas;            /* row 0 of this band in the destination canvas (device pointer; NULL with host != 0) */
     size_t canvas_step;
+    /* 1 (or 0): the owners of step s wait until every band has finished step s - 1 (one set of slice arenas).
+     * 2: the caller alternates between TWO sets of arenas (`slices` of even / odd steps point into different memory), so the
+     * owners of step s only wait for step s - 2 and their warp + mask work overlaps the blends of step s - 1.     */
+    int done_lag;
 } spano_shard_plan;
 int spano_shard_step_owner(spano_ctx *ctx, const spano_shard_plan *plan, unsigned step, int host);
 int spano_shard_step_band(spano_ctx *ctx, const spano_shard_plan *plan, unsigned step, int host, uint8_t *host_canvas,

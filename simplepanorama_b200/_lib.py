@@ -44,7 +44,8 @@ class ShardPlanC(C.Structure):
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("n", C.c_int), ("proj", C.c_int), ("scale", C.c_float), ("bands", C.c_int),
                 ("sigma", C.c_double), ("canvas_w", C.c_int), ("min_x", C.c_int), ("min_y", C.c_int), ("row0", C.c_int), ("row1", C.c_int),
                 ("images", C.POINTER(ImageDesc)), ("owner", C.POINTER(C.c_int)), ("order", C.POINTER(C.c_int)),
-                ("slices", C.POINTER(Slice)), ("flags", C.POINTER(C.c_void_p)), ("canvas", C.c_void_p), ("canvas_step", C.c_size_t)]
+                ("slices", C.POINTER(Slice)), ("flags", C.POINTER(C.c_void_p)), ("canvas", C.c_void_p), ("canvas_step", C.c_size_t),
+                ("done_lag", C.c_int)]
 
 
 class CenterFix(C.Structure):

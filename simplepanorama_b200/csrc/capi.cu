@@ -1646,10 +1646,12 @@ extern "C" int spano_shard_step_owner(spano_ctx *ctx, const spano_shard_plan *P,
         if (int rc = spano_reserve(ctx, spano_ctx::BUF_MASK0, bits, &dummy)) return rc;
         if (int rc = spano_reserve(ctx, spano_table_buffer(ctx, spano_ctx::BUF_TABLES, spano_ctx::BUF_TABLES_AUX), tables, &dummy)) return rc;
     }
-    // every band has finished reading its arena for the previous step
-    if (step > 1)
+    // every band has finished reading the arena this step overwrites (the previous step's, or with two alternating sets of
+    // arenas the one before)
+    const unsigned lag = P->done_lag >= 2 ? 2u : 1u;
+    if (step > lag)
         for (int k = 0; k < W; ++k)
-            if (int rc = stream_wait_flag(ctx, P->flags[P->rank] + n + k, step - 1)) return rc;
+            if (int rc = stream_wait_flag(ctx, P->flags[P->rank] + n + k, step - lag)) return rc;
     std::vector<spano_slice> sl;
     std::vector<uint32_t *> targets;
     for (int t = 0; t < n; ++t) {

@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(256) warp_tma_kernel(const WarpParams P, const
                 const int px0 = (int)floorf(lox) - 2, px1 = (int)ceilf(hix) + 3;      // pixels px0 .. px1 (taps included)
                 row0 = (int)floorf(loy) - 2;
                 const int rows = (int)ceilf(hiy) + 3 - row0 + 1;
-                const int w0 = (3 * px0) >> 2;                                          // first word (floor, also for negatives)
+                const int w0 = ((3 * px0) >> 4) << 2;   // first word: the box must start on a 16-byte boundary of the row (floor, also for negatives)
                 byte0 = 4 * w0;
                 if (rows <= BOX_H && 3 * (px1 + 1) - byte0 <= BOX_PITCH - 8) staged = 1;
                 if (staged) {

@@ -331,31 +331,37 @@ class ShardSession:
     """The spano_shard_plan of one rank plus the step counter: step_owner / step_band enqueue one pass over the image
     set (include/spano.h: spano_shard_step_owner / spano_shard_step_band).  `arena_ptrs[k]` / `flag_ptrs[k]` = rank
     k's slice arena / flag block as addressable from this process; `canvas_ptr` = row 0 of THIS band in the destination
-    canvas (device pointer, local or peer), `descs` the spano_image_desc array (device or host pointers)."""
+    canvas (device pointer, local or peer), `descs` the spano_image_desc array (device or host pointers).
+    `arena_ptrs2`: a second set of arenas; even and odd steps then use different memory, and the owners of a step need
+    not wait for the bands of the previous one (done_lag = 2)."""
 
     def __init__(self, plan: ShardPlan, rank: int, kind: int, focal: float, bands: int, sigma: float, arena_ptrs, flag_ptrs,
-                 canvas_ptr: int = 0, canvas_step: int = 0):
+                 canvas_ptr: int = 0, canvas_step: int = 0, arena_ptrs2=None):
         import ctypes as C
         from ._lib import ShardPlanC, Slice
         n, world = len(plan.sizes), plan.world
         self.plan, self.rank, self.step = plan, rank, 0
         self._owner = (C.c_int * n)(*plan.owner)
         self._order = (C.c_int * n)(*plan.order)
-        self._slices = (Slice * (world * n))()
-        for k in range(world):
-            for j in range(n):
-                s = band_slice(plan, k, j, arena_ptrs[k])
-                if s is not None:
-                    self._slices[k * n + j] = s
+        self._slices = []
+        for ptrs in ([arena_ptrs] if arena_ptrs2 is None else [arena_ptrs, arena_ptrs2]):
+            arr = (Slice * (world * n))()
+            for k in range(world):
+                for j in range(n):
+                    s = band_slice(plan, k, j, ptrs[k])
+                    if s is not None:
+                        arr[k * n + j] = s
+            self._slices.append(arr)
         self._flags = (C.c_void_p * world)(*flag_ptrs)
         self.c = ShardPlanC()
         c = self.c
         c.world, c.rank, c.n, c.proj, c.scale, c.bands, c.sigma = world, rank, n, int(kind), float(focal), int(bands), float(sigma)
         c.canvas_w, c.min_x, c.min_y = plan.canvas_w, plan.min_x, plan.min_y
         c.row0, c.row1 = plan.bands[rank]
-        c.owner, c.order, c.slices = self._owner, self._order, self._slices
+        c.owner, c.order, c.slices = self._owner, self._order, self._slices[0]
         c.flags = C.cast(self._flags, C.POINTER(C.c_void_p))
         c.canvas, c.canvas_step = canvas_ptr or None, canvas_step
+        c.done_lag = len(self._slices)
         self._descs = None
 
     def _bind(self, descs):
@@ -363,6 +369,7 @@ class ShardSession:
         from ._lib import ImageDesc
         self._descs = descs
         self.c.images = C.cast(descs, C.POINTER(ImageDesc))
+        self.c.slices = self._slices[self.step % len(self._slices)]
 
     def next_step(self):
         self.step += 1

@@ -123,7 +123,7 @@ def test_sharded_errors(ctx):
 # ---------------------------------------------------------------------------------------------------------------
 # spano_shard_step_owner / spano_shard_step_band: the library-driven step, ordered by readiness flags
 # ---------------------------------------------------------------------------------------------------------------
-def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=3, poll_kernel=False):
+def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=3, poll_kernel=False, two_arenas=False):
     """`world` ranks emulated on one device: per rank one band context + one owner context (their own streams), arenas and
     flag blocks are plain device buffers.  From the second step on (scratch buffers have their final size: nothing calls
     cudaFree, which would wait for the blocked streams) the band phases are enqueued BEFORE the owner phases, so the band
@@ -137,6 +137,7 @@ def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=3, poll_
     sp = dist.plan_tile_shards([p[2] for p in plan], [p[3] for p in plan], world, cfg.sigma)
     n = cfg.n
     arenas = [torch.full((sp.arena_bytes[k],), 0xAB, dtype=torch.uint8, device=dev) for k in range(world)]
+    arenas_b = [torch.full((sp.arena_bytes[k],), 0xCD, dtype=torch.uint8, device=dev) for k in range(world)] if two_arenas else None
     flags = [torch.zeros(n + world, dtype=torch.int32, device=dev) for _ in range(world)]
     canvas = torch.zeros((sp.canvas_h, sp.canvas_w, 3), dtype=torch.uint8, device=dev)
     if host:
@@ -154,7 +155,8 @@ def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=3, poll_
     for k in range(world):
         r0, _ = sp.bands[k]
         sessions.append(dist.ShardSession(sp, k, cfg.kind, cfg.focal, cfg.bands, cfg.sigma, [a.data_ptr() for a in arenas],
-                                          [f.data_ptr() for f in flags], canvas.data_ptr() + r0 * canvas.stride(0), canvas.stride(0)))
+                                          [f.data_ptr() for f in flags], canvas.data_ptr() + r0 * canvas.stride(0), canvas.stride(0),
+                                          arena_ptrs2=[a.data_ptr() for a in arenas_b] if two_arenas else None))
         if poll_kernel:
             band_ctx[k].set_option(3, 1)   # SPANO_OPT_FLAG_WAIT
             own_ctx[k].set_option(3, 1)
@@ -163,7 +165,7 @@ def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=3, poll_
         if s == 1:   # poison the arenas between steps: every row a band reads must be rewritten by its owner in this step
             for b in band_ctx:
                 b.sync()
-            for a in arenas:
+            for a in arenas + (arenas_b or []):
                 a.fill_(0x5C)
             canvas.zero_()
             torch.cuda.synchronize()
@@ -215,6 +217,17 @@ def test_shard_step_host_and_poll_fallback(ctx):
     for got in res:
         assert np.array_equal(got, full)
     res, _ = _run_shard_steps(cfg, gains, images, plan, cuts, 2, host=False, poll_kernel=True)
+    for got in res:
+        assert np.array_equal(got, full)
+
+
+@pytest.mark.timeout(120)
+def test_shard_step_two_arena_sets(ctx):
+    """done_lag = 2: even and odd steps use different arenas, the owners of a step do not wait for the previous step's bands"""
+    from simplepanorama_b200 import api
+    cfg, K, R, gains, images, plan, cuts = _case("cfg2", 0.04, True)
+    full = api.return_full(images, R, K, cfg.kind, cfg.focal, gains, cuts, cfg.bands, cfg.sigma, ctx=ctx)
+    res, _ = _run_shard_steps(cfg, gains, images, plan, cuts, 2, host=False, steps=5, two_arenas=True)
     for got in res:
         assert np.array_equal(got, full)
 

@@ -1,5 +1,7 @@
 // tma_probe.cu -- minimal cp.async.bulk.tensor.2d load of a (72 words x 32 rows) box from a 2-D uint32 tensor, the exact
-// sequence warp_tma_kernel uses; prints whether the staged bytes equal the source.
+// sequence warp_tma_kernel uses; prints whether the staged bytes equal the source.  Finding (B200, driver 580): the box must
+// start on a 16-byte boundary of the innermost dimension (coordinate 0 * 4 bytes a multiple of 16): an unaligned start -- e.g. word -3
+// -- raises "illegal instruction"; negative and past-the-end coordinates are fine and read as zeros.
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
@@ -21,7 +23,7 @@ __global__ void k(const __grid_constant__ TmaDesc tmap, int w0, int row0, uint32
         if (variant == 1) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(BOX_H * BOX_PITCH) : "memory");
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                     ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(w0 + (int)blockIdx.x), "r"(row0), "r"(bar) : "memory");
+                     ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(w0 + 4 * (int)blockIdx.x), "r"(row0), "r"(bar) : "memory");
     }
     __syncthreads();
     asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}" ::"r"(bar) : "memory");
@@ -53,7 +55,7 @@ int main(int argc, char **argv)
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     printf("encode W=%d H=%d step=%zu -> %d\n", W, H, step, (int)r);
     for (int test = 0; test < 4; ++test) {
-        const int w0 = test == 0 ? 100 : test == 1 ? -3 : test == 2 ? (int)dims[0] - 20 : 1000, row0 = test == 0 ? 50 : test == 1 ? -2 : test == 2 ? H - 10 : 2000;
+        const int w0 = test == 0 ? 100 : test == 1 ? -4 : test == 2 ? (int)dims[0] - 20 - ((int)dims[0] & 3) : 1000, row0 = test == 0 ? 50 : test == 1 ? -2 : test == 2 ? H - 10 : 2000;
         cudaMemset(out, 0xff, BOX_H * BOX_PITCH);
         k<<<test == 3 ? 2000 : 1, 256>>>(tm, w0, row0, out, variant);
         cudaError_t e = cudaDeviceSynchronize();
