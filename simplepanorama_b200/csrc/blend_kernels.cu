@@ -167,49 +167,27 @@ __global__ void __launch_bounds__(GTHREADS) blend_generic_kernel(const __grid_co
 }
 
 // out = color / clamp(alpha) / float(255/B)  [ -> *255 -> u8 ]
-// One thread = 4 consecutive canvas pixels: four 16-byte accumulator loads in flight, and (8-bit output, aligned rows)
-// the 12 result bytes leave as three 32-bit stores -- a warp writes 384 contiguous bytes instead of 96 scattered ones.
-__device__ __forceinline__ void normalise_px(const float4 t, float inv_div, float &c0, float &c1, float &c2)
+__global__ void normalise_kernel(const float4 *acc, int canvas_w, int rows, float inv_div, int out_kind, void *out,
+                                 size_t out_step, int col0, int col1)
 {
+    const int x = col0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= col1 || y >= rows) return;
+    const float4 t = acc[(size_t)y * canvas_w + x];
     float d = t.w;
     d = copysignf(fmaxf(fabsf(d), 1e-6f), d);
     const float s = __fdiv_rn(1.f, d);
-    c0 = __fmul_rn(__fmul_rn(t.x, s), inv_div);
-    c1 = __fmul_rn(__fmul_rn(t.y, s), inv_div);
-    c2 = __fmul_rn(__fmul_rn(t.z, s), inv_div);
-}
-
-__device__ __forceinline__ uint32_t to_u8(float c) { return (uint32_t)min(255, max(0, __float2int_rn(__fmul_rn(c, 255.f)))); }
-
-__global__ void __launch_bounds__(256) normalise_kernel(const float4 *acc, int canvas_w, int rows, float inv_div, int out_kind, void *out,
-                                                        size_t out_step, int col0, int col1)
-{
-    const int x0 = col0 + (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
-    if (x0 >= col1 || y >= rows) return;
-    const int n = min(4, col1 - x0);
-    float4 t[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) t[i] = (i < n) ? acc[(size_t)y * canvas_w + x0 + i] : make_float4(0.f, 0.f, 0.f, 1.f);
-    float c[4][3];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) normalise_px(t[i], inv_div, c[i][0], c[i][1], c[i][2]);
+    const float c0 = __fmul_rn(__fmul_rn(t.x, s), inv_div);
+    const float c1 = __fmul_rn(__fmul_rn(t.y, s), inv_div);
+    const float c2 = __fmul_rn(__fmul_rn(t.z, s), inv_div);
     if (out_kind == SPANO_OUT_F32) {
-        float *o = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(out) + (size_t)y * out_step) + 3 * (size_t)x0;
-        for (int i = 0; i < n; ++i) { o[3 * i] = c[i][0]; o[3 * i + 1] = c[i][1]; o[3 * i + 2] = c[i][2]; }
-        return;
-    }
-    unsigned char *o = reinterpret_cast<unsigned char *>(out) + (size_t)y * out_step + 3 * (size_t)x0;
-    uint32_t p[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) p[i] = to_u8(c[i][0]) | (to_u8(c[i][1]) << 8) | (to_u8(c[i][2]) << 16);
-    if (n == 4 && (((uintptr_t)o) & 3) == 0) {
-        uint32_t *q = reinterpret_cast<uint32_t *>(o);
-        q[0] = p[0] | (p[1] << 24);
-        q[1] = (p[1] >> 8) | (p[2] << 16);
-        q[2] = (p[2] >> 16) | (p[3] << 8);
+        float *o = reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(out) + (size_t)y * out_step) + 3 * (size_t)x;
+        o[0] = c0; o[1] = c1; o[2] = c2;
     } else {
-        for (int i = 0; i < n; ++i) { o[3 * i] = (unsigned char)p[i]; o[3 * i + 1] = (unsigned char)(p[i] >> 8); o[3 * i + 2] = (unsigned char)(p[i] >> 16); }
+        unsigned char *o = reinterpret_cast<unsigned char *>(out) + (size_t)y * out_step + 3 * (size_t)x;
+        o[0] = (unsigned char)min(255, max(0, __float2int_rn(__fmul_rn(c0, 255.f))));
+        o[1] = (unsigned char)min(255, max(0, __float2int_rn(__fmul_rn(c1, 255.f))));
+        o[2] = (unsigned char)min(255, max(0, __float2int_rn(__fmul_rn(c2, 255.f))));
     }
 }
 
@@ -512,7 +490,7 @@ int launch_normalise(spano_ctx *ctx, const float4 *acc, int canvas_w, int rows, 
     if (rows <= 0 || col1 <= col0) return 0;
     const float divisor = (float)(255 / bands); // integer division, as in the reference
     const float inv_div = (float)(1.0 / (double)divisor);
-    dim3 block(256), grid((col1 - col0 + 1023) / 1024, rows);
+    dim3 block(256), grid((col1 - col0 + 255) / 256, rows);
     normalise_kernel<<<grid, block, 0, ctx->stream>>>(acc, canvas_w, rows, inv_div, out_kind, out, out_step, col0, col1);
     SPANO_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;

@@ -8,9 +8,11 @@
 //   g_i   = float(gray(t_i)) / 255 where m_i != 0, else 0;   q_i = g_i * d_i
 //   over the overlaps with every other image j (ascending j), where m_i != 0:  Q_i = q_i + sum q_j,  A_i = d_i + sum d_j
 //   F_i   = GaussianBlur_13x13,sigma=7,REFLECT( g_i / (Q_i / (A_i + 1e-5) + 1e-5) + (255 - m_i) / 255 )
-// cv::resize's INTER_LINEAR is OpenCV's fixed-point scheme for 8-bit data and plain float arithmetic for CV_32F; when the
-// size is halved EXACTLY in both directions OpenCV switches to the 2x2 area average (cv::resize: "INTER_LINEAR && is_area_fast
-// && iscale == 2 -> INTER_AREA"), which is reproduced here.  cv::divide gives 0 where the divisor is 0.
+// cv::resize(src, dst, Size(), ratio, ratio, INTER_LINEAR): the scale is 1 / ratio exactly (not src / dst), and for ratio = 0.5
+// -- the reference's only value -- OpenCV replaces INTER_LINEAR by the 2x2 AREA average ("INTER_LINEAR && is_area_fast &&
+// iscale == 2 -> INTER_AREA"), for odd sizes too: a cell that sticks out of the source averages the pixels it has
+// ((float)sum / count, rounded half to even for 8-bit).  Other ratios take OpenCV's fixed-point (8-bit) / float linear scheme.
+// cv::divide gives 0 where the divisor is 0.
 // Preview-scale data (a few hundred kB per image): nothing here is performance critical; exactness is (integer stages
 // bit-exact, the float field within 1e-5 relative of OpenCV's).
 #include <cmath>
@@ -27,11 +29,10 @@ struct Axis {
 };
 
 // one entry per destination index: source offset + coefficients, as cv::resize computes them for INTER_LINEAR
-__global__ void axis_kernel(int slen, int dlen, Axis *t)
+__global__ void axis_kernel(int slen, int dlen, double scale, Axis *t)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dlen) return;
-    const double scale = (double)slen / dlen;
     float f = (float)((i + 0.5) * scale - 0.5);
     int s = (int)floorf(f);
     f -= (float)s;
@@ -53,9 +54,20 @@ __global__ void resize_u8_kernel(const uint8_t *src, int sw, int sh, size_t sste
     if (x >= dw || y >= dh) return;
     uint8_t *d = dst + (size_t)y * dstep + (size_t)x * CN;
     if (area2) {
-        const uint8_t *r0 = src + (size_t)(2 * y) * sstep + (size_t)(2 * x) * CN, *r1 = r0 + sstep;
+        const int nx = min(2, sw - 2 * x), ny = min(2, sh - 2 * y);      // pixels of the 2x2 cell inside the source
+        if (nx <= 0 || ny <= 0) {
 #pragma unroll
-        for (int c = 0; c < CN; ++c) d[c] = (uint8_t)((r0[c] + r0[c + CN] + r1[c] + r1[c + CN] + 2) >> 2);
+            for (int c = 0; c < CN; ++c) d[c] = 0;
+            return;
+        }
+        const uint8_t *r0 = src + (size_t)(2 * y) * sstep + (size_t)(2 * x) * CN;
+#pragma unroll
+        for (int c = 0; c < CN; ++c) {
+            int sum = 0;
+            for (int yy = 0; yy < ny; ++yy)
+                for (int xx = 0; xx < nx; ++xx) sum += r0[(size_t)yy * sstep + xx * CN + c];
+            d[c] = (nx * ny == 4) ? (uint8_t)((sum + 2) >> 2) : (uint8_t)min(255, max(0, __float2int_rn(__fdiv_rn((float)sum, (float)(nx * ny)))));
+        }
         return;
     }
     const Axis ex = xt[x], ey = yt[y];
@@ -77,10 +89,15 @@ __global__ void resize_f32_kernel(const float *src, int sw, int sh, size_t spitc
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= dw || y >= dh) return;
     if (area2) {
-        const float *r0 = src + (size_t)(2 * y) * spitch + 2 * x, *r1 = r0 + spitch;
-        const float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0[0], pre_scale), __fmul_rn(r0[1], pre_scale)), __fmul_rn(r1[0], pre_scale)),
-                                  __fmul_rn(r1[1], pre_scale));
-        dst[(size_t)y * dpitch + x] = __fmul_rn(s, 0.25f);
+        const int nx = min(2, sw - 2 * x), ny = min(2, sh - 2 * y);
+        float s = 0.f;
+        if (nx > 0 && ny > 0) {
+            const float *r0 = src + (size_t)(2 * y) * spitch + 2 * x;
+            for (int yy = 0; yy < ny; ++yy)
+                for (int xx = 0; xx < nx; ++xx) s = __fadd_rn(s, __fmul_rn(r0[(size_t)yy * spitch + xx], pre_scale));
+            s = (nx * ny == 4) ? __fmul_rn(s, 0.25f) : __fdiv_rn(s, (float)(nx * ny));
+        }
+        dst[(size_t)y * dpitch + x] = s;
         return;
     }
     const Axis ex = xt[x], ey = yt[y];
@@ -227,10 +244,11 @@ int launch_equalize_intensities(spano_ctx *ctx, int n, const uint8_t *const *til
     std::vector<EqImage> desc(n);
     for (int i = 0; i < n; ++i) {
         Axis *xt = reinterpret_cast<Axis *>(arena + offX[i]), *yt = reinterpret_cast<Axis *>(arena + offY[i]);
-        axis_kernel<<<(fw[i] + 255) / 256, 256, 0, ctx->stream>>>(w[i], fw[i], xt);
-        axis_kernel<<<(fh[i] + 255) / 256, 256, 0, ctx->stream>>>(h[i], fh[i], yt);
-        // cv::resize switches INTER_LINEAR to the 2x2 area average when both axes shrink by exactly 2
-        const int area2 = (w[i] == 2 * fw[i]) && (h[i] == 2 * fh[i]);
+        const double inv_scale = 1.0 / (double)ratio;    // cv::resize with fx, fy given: scale = 1 / fx, whatever the rounded size is
+        axis_kernel<<<(fw[i] + 255) / 256, 256, 0, ctx->stream>>>(w[i], fw[i], inv_scale, xt);
+        axis_kernel<<<(fh[i] + 255) / 256, 256, 0, ctx->stream>>>(h[i], fh[i], inv_scale, yt);
+        // cv::resize switches INTER_LINEAR to the 2x2 area average when the scale is exactly 2 in both directions
+        const int area2 = (ratio == 0.5f);
         dim3 b(128), g((fw[i] + 127) / 128, fh[i]);
         uint8_t *m = arena + offM[i], *t = arena + offT[i];
         float *d = reinterpret_cast<float *>(arena + offd[i]), *gg = reinterpret_cast<float *>(arena + offg[i]),
