@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-cfg1", action="store_true")
     ap.add_argument("--no-cfg4", action="store_true")
     ap.add_argument("--no-center-fix", action="store_true", help="cfg3 without sten_proj::disk_reproj")
+    ap.add_argument("--blend-kernel", type=int, default=0, help="SPANO_OPT_BLEND_KERNEL (0 default; 2 = the 8-warp marching kernel of round 1)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU time budget of the cpu_baseline sample")
     return ap.parse_args()
 
@@ -270,9 +271,15 @@ class Runner:
         self.ctx = api.Context(local)
         # a dedicated (non-default) stream shared by torch and the library, so that torch.cuda.Event brackets exactly the
         # kernels the library launches (the legacy default stream has handle 0 = "use the context's own stream")
-        self.stream = torch.cuda.Stream(device=dev)
+        # HIGH priority: when the blend of image i and the warp of image i+1 (the library's auxiliary stream, default priority)
+        # become runnable at the same moment, the blend's 148 large CTAs must be placed first -- otherwise the warp kernel's
+        # thousands of small CTAs fill every SM and the blend waits for them to drain (measured: the two then run one after
+        # the other instead of side by side)
+        self.stream = torch.cuda.Stream(device=dev, priority=-1)
         assert self.stream.cuda_stream != 0
         self.ctx.set_stream(self.stream.cuda_stream)
+        if getattr(args, "blend_kernel", 0):
+            self.ctx.set_option(self.ctx.OPT_BLEND_KERNEL, args.blend_kernel)
         self.h_img = None
         if device_synth:
             self.d_img = [make_image_torch(torch, cfg, j, gains[j], dev) if j in self.mine else None for j in range(cfg.n)]

@@ -77,8 +77,9 @@ long long spano_launch_count(spano_ctx *ctx);
  *                             window of mask_cut is zero (see spano_blend_stats); default 0
  *   SPANO_OPT_BLEND_KERNEL 0 (default): the warp-specialised marching-strip kernel for sigma = 7, the generic-radius
  *                             kernel otherwise; 1: always the generic-radius kernel; 2: the 8-warp marching-strip kernel
- *                             of round 1; 3: the warp-specialised kernel with 12 instead of 8 consumer warps (2 and 3:
- *                             same arithmetic in the same order as the default, bit-identical canvas)           */
+ *                             of round 1; 3: the warp-specialised kernel with 12 instead of 8 consumer warps; 4: the
+ *                             warp-specialised kernel without the register re-split (2, 3 and 4 are measurement
+ *                             variants: same arithmetic in the same order as the default, bit-identical canvas) */
 #define SPANO_OPT_BLEND_DENSE 1
 #define SPANO_OPT_BLEND_KERNEL 2
 #define SPANO_OPT_WARP_KERNEL 4 /* 1: the warp kernel stages the source footprint of each block of destination pixels with TMA

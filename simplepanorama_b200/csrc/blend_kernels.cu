@@ -256,18 +256,18 @@ int make_plan(spano_ctx *ctx, const BlendParams &Q, int sms, int *plan)
     return 0;
 }
 
-template <int B, int SW, int VT>
+template <int B, int SW, int VT, bool UNIFORM>
 int launch_ws(spano_ctx *ctx, const march::Params &P, int sms)
 {
     using W = march::WsCfg<B, SW, VT>;
     static bool configured[64] = {false};
     const int dev = ctx->device & 63;
     if (!configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(march::blend_ws_kernel<B, SW, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(march::blend_ws_kernel<B, SW, VT, UNIFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W::SMEM);
         if (e != cudaSuccess) return spano_fail(ctx, SPANO_E_CUDA, "cudaFuncSetAttribute(blend_ws<%d,%d>, %zu B): %s", B, VT, W::SMEM, cudaGetErrorString(e));
         configured[dev] = true;
     }
-    march::blend_ws_kernel<B, SW, VT><<<sms, W::THREADS, W::SMEM, ctx->stream>>>(P);
+    march::blend_ws_kernel<B, SW, VT, UNIFORM><<<sms, W::THREADS, W::SMEM, ctx->stream>>>(P);
     return 0;
 }
 
@@ -276,7 +276,8 @@ int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
 {
     constexpr int SW = (B <= 6) ? 32 : 16;
     using C = march::Cfg<B, SW>;
-    const int mode = ctx->opt_blend_kernel;   // 0 default (warp-specialised, 8 V warps), 2 the 8-warp marching kernel, 3 warp-specialised with 12 V warps
+    const int mode = ctx->opt_blend_kernel;   // 0 default (warp-specialised, 8 V warps, uniform registers), 2 the 8-warp marching kernel, 3 warp-specialised with 12 V warps,
+    // 4 warp-specialised with the setmaxnreg register split
     static bool configured[64] = {false};
     int dev = ctx->device & 63;
     if (mode == 2 && !configured[dev]) {
@@ -303,14 +304,22 @@ int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
         if (int rc = make_plan<SW>(ctx, Q, sms, plan)) return rc;
         P.plan = plan;
     }
+    P.start_count = P.start_flag = nullptr;
+    P.start_value = 0;
     if (mode == 2) {
         march::blend_march_kernel<B, SW><<<sms, march::THREADS, C::SMEM, ctx->stream>>>(P);
         return 0;
     }
-    if constexpr (SW == 32) {
-        if (mode == 3) return launch_ws<B, SW, 384>(ctx, P, sms);
+    if (ctx->blend_sync) {   // (allocated by the fused path when it wants the signal)
+        P.start_count = ctx->blend_sync;
+        P.start_flag = ctx->blend_sync + 1;
+        P.start_value = ++ctx->blend_seq;
     }
-    return launch_ws<B, SW, 256>(ctx, P, sms);
+    if constexpr (SW == 32) {
+        if (mode == 3) return launch_ws<B, SW, 384, false>(ctx, P, sms);
+    }
+    if (mode == 4) return launch_ws<B, SW, 256, true>(ctx, P, sms);   // no setmaxnreg: measured 2x slower, kept for A/B
+    return launch_ws<B, SW, 256, false>(ctx, P, sms);
 }
 
 template <int B>

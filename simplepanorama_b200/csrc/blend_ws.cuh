@@ -155,7 +155,11 @@ __device__ __forceinline__ void ws_row_item(const Params &P, const float *raw, f
     }
 }
 
-template <int B, int SW, int VT>
+// UNIFORM = true: every thread keeps the 128 registers of the launch (no setmaxnreg) and the H group loads the bytes of a
+// chunk right before it stages them instead of one chunk ahead (no prefetch registers; the H group has the slack to sit out
+// the load latency).  A CTA that re-partitions its registers with setmaxnreg does not share its SM with CTAs of other
+// kernels (measured: the warp / mask kernels of the next image then only run between blend launches), a uniform one does.
+template <int B, int SW, int VT, bool UNIFORM>
 __global__ void __maxnreg__(WsRegs<VT>::LAUNCH) blend_ws_kernel(const Params P)
 {
     using C = WsCfg<B, SW, VT>;
@@ -173,6 +177,13 @@ __global__ void __maxnreg__(WsRegs<VT>::LAUNCH) blend_ws_kernel(const Params P)
 #pragma unroll
         for (int i = 0; i < WS_SLOTS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (P.start_flag) {   // the grid is one CTA per SM, all resident at once: the last one to arrive publishes it
+            if (atomicAdd(P.start_count, 1u) == gridDim.x - 1) {
+                *P.start_count = 0u;
+                __threadfence();
+                *reinterpret_cast<volatile unsigned int *>(P.start_flag) = P.start_value;
+            }
+        }
     }
     __syncthreads();
 
@@ -187,7 +198,7 @@ __global__ void __maxnreg__(WsRegs<VT>::LAUNCH) blend_ws_kernel(const Params P)
         // =========================== H group: stage + horizontal pass, one chunk at a time ===========================
         // (the horizontal pass holds a 48-float window, 44 pair sums and 2B packed accumulators per item plus the
         // prefetched bytes of the next chunk: it takes the registers the V warps hand back)
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WsRegs<VT>::H));
+        if (!UNIFORM) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WsRegs<VT>::H));
         const int ht = tid - WS_VTHREADS;
         const int lane = ht & 31, hw = ht >> 5;                 // warp hw stages channel hw (all 8 rows of a chunk)
         const uint8_t *sbase = (hw == 0) ? P.cut : P.tile + (hw - 1);
@@ -218,11 +229,12 @@ __global__ void __maxnreg__(WsRegs<VT>::LAUNCH) blend_ws_kernel(const Params P)
             }
 #pragma unroll
             for (int k = 0; k < STEP * C::NPASS; ++k) pre[k] = 0u;
-            prefetch(ybase);
+            if (!UNIFORM) prefetch(ybase);
 #pragma unroll 1
             for (int c = 0; c < nchunks; ++c, ++gc) {
                 const int slot = gc & (WS_SLOTS - 1);
-                // raw <- prefetched bytes of chunk c (raw is free: the barrier at the end of the previous chunk)
+                if (UNIFORM) prefetch(ybase + c * STEP);
+                // raw <- the bytes of chunk c (raw is free: the barrier at the end of the previous chunk)
 #pragma unroll
                 for (int q = 0; q < STEP; ++q) {
                     float *rrow = raw + (hw * STEP + q) * C::RAW_PITCH + lane;
@@ -230,7 +242,7 @@ __global__ void __maxnreg__(WsRegs<VT>::LAUNCH) blend_ws_kernel(const Params P)
                     for (int ps = 0; ps < C::NPASS; ++ps)
                         if (lane + 32 * ps < C::NC) rrow[32 * ps] = (float)pre[q * C::NPASS + ps];
                 }
-                if (c + 1 < nchunks) prefetch(ybase + (c + 1) * STEP);
+                if (!UNIFORM && c + 1 < nchunks) prefetch(ybase + (c + 1) * STEP);
                 mbar_wait(empty + slot, ((gc / WS_SLOTS) & 1) ^ 1);      // the V group is done with the slot's previous chunk
                 group_sync(2, WS_HTHREADS);                              // raw visible to the whole group
 #pragma unroll
@@ -243,7 +255,7 @@ __global__ void __maxnreg__(WsRegs<VT>::LAUNCH) blend_ws_kernel(const Params P)
     }
 
     // =============================== V group: vertical pass + combine, one step at a time ===============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WsRegs<VT>::V));
+    if (!UNIFORM) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WsRegs<VT>::V));
     const int vx = tid % SW, vch = (tid / SW) & 3, vg = tid / (4 * SW);
     const int po = tid / SW, px = tid % SW;
 #pragma unroll 1

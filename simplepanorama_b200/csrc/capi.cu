@@ -200,7 +200,12 @@ extern "C" int spano_create(spano_ctx **out, int device)
     ctx->device = device;
     int prev = -1;
     if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    const bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    // the context's own stream gets the highest priority: blends (main stream) must win the SMs against the warp / mask kernels
+    // of the next image (auxiliary stream, default priority) when both become runnable at once -- see composite_impl
+    int prio_lo = 0, prio_hi = 0;
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    if (ok) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    ok = ok && cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
     if (prev >= 0 && prev != device) cudaSetDevice(prev);
     if (!ok) {
         delete ctx;
@@ -274,7 +279,7 @@ extern "C" int spano_set_option(spano_ctx *ctx, int option, int value)
     case SPANO_OPT_FLAG_WAIT: ctx->opt_flag_wait = value != 0; return SPANO_OK;
     case SPANO_OPT_WARP_KERNEL: ctx->opt_warp_kernel = value != 0; return SPANO_OK;
     case SPANO_OPT_BLEND_KERNEL:
-        if (value < 0 || value > 3) return spano_fail(ctx, SPANO_E_INVALID, "SPANO_OPT_BLEND_KERNEL: value %d not in [0,3]", value);
+        if (value < 0 || value > 4) return spano_fail(ctx, SPANO_E_INVALID, "SPANO_OPT_BLEND_KERNEL: value %d not in [0,4]", value);
         ctx->opt_blend_kernel = value;
         return SPANO_OK;
     default: return spano_fail(ctx, SPANO_E_INVALID, "unknown option %d", option);
@@ -705,6 +710,9 @@ extern "C" int spano_multiblend(spano_ctx *ctx, int n, const uint8_t *const *til
 // ---------------------------------------------------------------------------------------------
 namespace {
 
+int stream_wait_flag(spano_ctx *ctx, const uint32_t *flag, uint32_t value);
+bool stream_wait_available();
+
 int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *im_in, int bands, double sigma,
                    int row0, int row1, uint8_t *canvas, size_t canvas_step, bool host, const spano_center_fix *fix = nullptr)
 {
@@ -863,6 +871,17 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         }
         SPANO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_start2, cudaEventDisableTiming));
     }
+    // The blend kernel is one large CTA per SM (all of the shared memory, 3/4 of the registers); the warp / mask kernels of
+    // the next image are thousands of small CTAs.  Both become runnable when the previous blend ends, and if the small CTAs
+    // get onto the SMs first the blend cannot be placed until they have drained: the two run one after the other.  Placed
+    // the other way round they share the SMs (one warp CTA fits next to a blend CTA).  So the blend publishes "all my CTAs
+    // are resident" and the auxiliary stream parks the next image's kernels behind that flag (a stream memory operation).
+    if (!ctx->blend_sync && stream_wait_available() && !ctx->opt_flag_wait) {
+        SPANO_CUDA(ctx, cudaMalloc((void **)&ctx->blend_sync, 2 * sizeof(unsigned int)));
+        SPANO_CUDA(ctx, cudaMemset(ctx->blend_sync, 0, 2 * sizeof(unsigned int)));
+        ctx->owned.push_back(ctx->blend_sync);
+        ctx->blend_seq = 0;
+    }
     cudaStream_t main_stream = ctx->stream, aux = ctx->aux_stream;
     SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_start2, main_stream));
     SPANO_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->ev_start2, 0));
@@ -908,6 +927,8 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         {   // ---- auxiliary stream: warp (+ mask) into tile buffer b ----
             StreamSwap sw(ctx, aux);
             if (idx >= 2) SPANO_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->ev_blended[b], 0));
+            if (idx >= 1 && ctx->blend_sync && ctx->blend_seq)   // the previous image's blend has all its CTAs on the SMs
+                if (int rc = stream_wait_flag(ctx, ctx->blend_sync + 1, ctx->blend_seq)) return rc;
             if (host) {
                 SPANO_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->ev_copied[b], 0));
                 src = d_srcbuf[b];  s_step = align_up((size_t)im[j].src_w * 3, 16);
@@ -1587,6 +1608,8 @@ stream_wait32_fn driver_stream_wait32()
     }();
     return fn;
 }
+
+bool stream_wait_available() { return driver_stream_wait32() != nullptr; }
 
 // the context's stream waits until *flag >= value (wrap-safe), without occupying an SM
 int stream_wait_flag(spano_ctx *ctx, const uint32_t *flag, uint32_t value)

@@ -226,7 +226,7 @@ def test_blend_kernels_agree(ctx, oracle, bands):
     cuts[3][:, 200:520] = 0                                   # a sparse tile: several pieces per CTA
     valids = [np.where(rng.random((h, w)) < 0.9, 255, 0).astype(np.uint8) for (w, h) in sizes]
     outs = []
-    for mode in (0, 2, 3, 1):
+    for mode in (0, 2, 3, 4, 1):
         ctx.set_option(ctx.OPT_BLEND_KERNEL, mode)
         try:
             outs.append(api.multi_blend(tiles, cuts, valids, corners, bands, 7.0, ctx))
@@ -234,7 +234,8 @@ def test_blend_kernels_agree(ctx, oracle, bands):
             ctx.set_option(ctx.OPT_BLEND_KERNEL, 0)
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
     assert np.array_equal(outs[0].view(np.uint32), outs[2].view(np.uint32))
-    _assert_float_close(outs[0], outs[3])
+    assert np.array_equal(outs[0].view(np.uint32), outs[3].view(np.uint32))
+    _assert_float_close(outs[0], outs[4])
     _assert_float_close(outs[0], oracle.multi_blend(tiles, cuts, valids, corners, bands, 7.0))
 
 
