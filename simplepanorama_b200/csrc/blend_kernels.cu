@@ -304,16 +304,9 @@ int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
         if (int rc = make_plan<SW>(ctx, Q, sms, plan)) return rc;
         P.plan = plan;
     }
-    P.start_count = P.start_flag = nullptr;
-    P.start_value = 0;
     if (mode == 2) {
         march::blend_march_kernel<B, SW><<<sms, march::THREADS, C::SMEM, ctx->stream>>>(P);
         return 0;
-    }
-    if (ctx->blend_sync) {   // (allocated by the fused path when it wants the signal)
-        P.start_count = ctx->blend_sync;
-        P.start_flag = ctx->blend_sync + 1;
-        P.start_value = ++ctx->blend_seq;
     }
     if constexpr (SW == 32) {
         if (mode == 3) return launch_ws<B, SW, 384, false>(ctx, P, sms);

@@ -62,11 +62,6 @@ struct Params {
     int canvas_w;
     int ax, ay;
     const int *plan;        // device plan of this launch (see Plan below)
-    // "every CTA of this launch is resident": the last CTA to start stores start_value to *start_flag (start_count is the
-    // arrival counter, left at 0 again).  The fused path parks the warp kernel of the NEXT image behind this flag, see
-    // composite_impl.  nullptr: no signal.
-    unsigned int *start_count, *start_flag;
-    unsigned int start_value;
 };
 
 // ---- sparsity plan -----------------------------------------------------------------------------------------

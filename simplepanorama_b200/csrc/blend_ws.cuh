@@ -28,9 +28,12 @@ constexpr int WS_HTHREADS = 128;
 // V group size: 8 warps (2 per scheduler) or 12 warps (3 per scheduler; strips of 32 columns only).  Registers per thread
 // after the role split: the launch allocates 128 x 384 = 49152 (8 V warps; then 256 x 96 + 128 x 192 = 49152) or
 // 128 x 512 = 65536 (12 V warps; then 384 x 96 + 128 x 224 = 65536).
-// With 8 V warps the launch is capped at 128 registers per thread (49152 per CTA) instead of the 168 it could take: the
-// remaining quarter of the register file lets the warp / mask kernels of the NEXT image (auxiliary stream of the fused
-// path) stay co-resident with the blend of the current one.
+// With 8 V warps the launch is capped at 128 registers per thread (49152 per CTA) instead of the 168 it could take; a
+// quarter of the register file and 1.4 KB of shared memory stay free.  That does NOT make the SM shareable: measured on
+// the fused path (profiles/r2_fused_step_timeline.txt), the warp / mask kernels of the next image (auxiliary stream) start
+// only when a launch of this kernel has ended, whereas they run next to the 8-warp marching kernel -- a CTA that
+// re-partitions its registers with setmaxnreg keeps its SM to itself.  (The variant without setmaxnreg, UNIFORM below,
+// would share, but starves its H group of prefetch registers and is 2x slower.)
 template <int VT> struct WsRegs { static constexpr int LAUNCH = 128, V = 96, H = (VT == 256) ? 192 : 224; };
 
 template <int B, int SW, int VT>
@@ -177,13 +180,6 @@ __global__ void __maxnreg__(WsRegs<VT>::LAUNCH) blend_ws_kernel(const Params P)
 #pragma unroll
         for (int i = 0; i < WS_SLOTS; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (P.start_flag) {   // the grid is one CTA per SM, all resident at once: the last one to arrive publishes it
-            if (atomicAdd(P.start_count, 1u) == gridDim.x - 1) {
-                *P.start_count = 0u;
-                __threadfence();
-                *reinterpret_cast<volatile unsigned int *>(P.start_flag) = P.start_value;
-            }
-        }
     }
     __syncthreads();
 

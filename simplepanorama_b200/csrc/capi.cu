@@ -710,9 +710,6 @@ extern "C" int spano_multiblend(spano_ctx *ctx, int n, const uint8_t *const *til
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-int stream_wait_flag(spano_ctx *ctx, const uint32_t *flag, uint32_t value);
-bool stream_wait_available();
-
 int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_image_desc *im_in, int bands, double sigma,
                    int row0, int row1, uint8_t *canvas, size_t canvas_step, bool host, const spano_center_fix *fix = nullptr)
 {
@@ -871,17 +868,6 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         }
         SPANO_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_start2, cudaEventDisableTiming));
     }
-    // The blend kernel is one large CTA per SM (all of the shared memory, 3/4 of the registers); the warp / mask kernels of
-    // the next image are thousands of small CTAs.  Both become runnable when the previous blend ends, and if the small CTAs
-    // get onto the SMs first the blend cannot be placed until they have drained: the two run one after the other.  Placed
-    // the other way round they share the SMs (one warp CTA fits next to a blend CTA).  So the blend publishes "all my CTAs
-    // are resident" and the auxiliary stream parks the next image's kernels behind that flag (a stream memory operation).
-    if (!ctx->blend_sync && stream_wait_available() && !ctx->opt_flag_wait) {
-        SPANO_CUDA(ctx, cudaMalloc((void **)&ctx->blend_sync, 2 * sizeof(unsigned int)));
-        SPANO_CUDA(ctx, cudaMemset(ctx->blend_sync, 0, 2 * sizeof(unsigned int)));
-        ctx->owned.push_back(ctx->blend_sync);
-        ctx->blend_seq = 0;
-    }
     cudaStream_t main_stream = ctx->stream, aux = ctx->aux_stream;
     SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_start2, main_stream));
     SPANO_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->ev_start2, 0));
@@ -927,8 +913,6 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         {   // ---- auxiliary stream: warp (+ mask) into tile buffer b ----
             StreamSwap sw(ctx, aux);
             if (idx >= 2) SPANO_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->ev_blended[b], 0));
-            if (idx >= 1 && ctx->blend_sync && ctx->blend_seq)   // the previous image's blend has all its CTAs on the SMs
-                if (int rc = stream_wait_flag(ctx, ctx->blend_sync + 1, ctx->blend_seq)) return rc;
             if (host) {
                 SPANO_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->ev_copied[b], 0));
                 src = d_srcbuf[b];  s_step = align_up((size_t)im[j].src_w * 3, 16);
@@ -1608,8 +1592,6 @@ stream_wait32_fn driver_stream_wait32()
     }();
     return fn;
 }
-
-bool stream_wait_available() { return driver_stream_wait32() != nullptr; }
 
 // the context's stream waits until *flag >= value (wrap-safe), without occupying an SM
 int stream_wait_flag(spano_ctx *ctx, const uint32_t *flag, uint32_t value)

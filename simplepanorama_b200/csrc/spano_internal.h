@@ -49,9 +49,6 @@ struct spano_ctx {
            BUF_CANVAS, BUF_MISC, BUF_SRC2, BUF_CUT2, BUF_RESIZE, BUF_CUTSMALL, BUF_CUTSMALL2, BUF_FIELD, BUF_FIELD2, BUF_BLENDPLAN, BUF_BLENDPLAN2, BUF_DT_TMP, BUF_DT_JOBS, BUF_DT_JOBS2, BUF_DT_ARENA, BUF_PREP_CUT, BUF_PREP_PLAN, BUF_RESIZE_AUX, BUF_TABLES_AUX, BUF_PRETILE, BUF_EQUALIZE, BUF_COUNT };
     DeviceBuffer buf[BUF_COUNT];
     std::vector<void *> owned; // extra allocations freed at destroy / end of call
-    // fused path: [0] arrival counter, [1] "all CTAs of blend launch #blend_seq are resident" (see march::Params::start_flag)
-    unsigned int *blend_sync = nullptr;
-    unsigned int blend_seq = 0;
     unsigned long long *blend_stats = nullptr; // device: [0] tile pixels the blend processed, [1] tile pixels offered
     // incremental band blend (spano_dev_blend_begin / add / finish)
     struct BlendSession {
