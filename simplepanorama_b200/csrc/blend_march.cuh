@@ -136,8 +136,10 @@ __global__ void plan_kernel(int *plan, int S, int max_cta, int ty_begin, int ty_
     constexpr int NB = (R + SW - 1) / SW;   // neighbour strips whose mask_cut reaches into this strip's window
     const PlanView V(S, max_cta);
     const int *ymin = plan + V.ymin(), *ymax = plan + V.ymax();
-    __shared__ int s_pref[2049];
-    __shared__ int s_cnt[1025];
+    // prefix sums live in the plan itself (scratch `prefix`, and `cta_start` which ends up holding them): no shared memory,
+    // so this one-CTA kernel fits on an SM next to a blend CTA of the previous image instead of waiting for it to end
+    int *s_pref = plan + V.prefix();
+    int *s_cnt = plan + V.cta_start();
     for (int s = threadIdx.x; s < S; s += blockDim.x) {
         int lo = 0x7fffffff, hi = -1;
         for (int t = max(0, s - NB); t <= min(S - 1, s + NB); ++t) { lo = min(lo, ymin[t]); hi = max(hi, ymax[t]); }
@@ -153,8 +155,9 @@ __global__ void plan_kernel(int *plan, int S, int max_cta, int ty_begin, int ty_
     __syncthreads();
     if (threadIdx.x == 0) {
         s_pref[0] = 0;
-        for (int s = 0; s < S; ++s) s_pref[s + 1] += s_pref[s];
-        const int total = s_pref[S];
+        int run = 0;
+        for (int s = 0; s < S; ++s) { run += s_pref[s + 1]; s_pref[s + 1] = run; }
+        const int total = run;
         // CTAs in use: all of them once every CTA gets at least 64 rows; rows per CTA rounded up to the step
         int ncta = min(max_cta, max(1, total / 64));
         int per = ((total + ncta - 1) / ncta + STEP - 1) / STEP * STEP;
@@ -195,12 +198,14 @@ __global__ void plan_kernel(int *plan, int S, int max_cta, int ty_begin, int ty_
         __syncthreads();
         if (!pass && threadIdx.x == 0) {
             s_cnt[0] = 0;
-            for (int i = 0; i < ncta; ++i) s_cnt[i + 1] += s_cnt[i];
-            plan[3] = s_cnt[ncta];
+            int run = 0;
+            for (int i = 0; i < ncta; ++i) { run += s_cnt[i + 1]; s_cnt[i + 1] = run; }
+            plan[3] = run;
         }
         __syncthreads();
     }
-    for (int i = threadIdx.x; i <= max_cta; i += blockDim.x) plan[V.cta_start() + i] = s_cnt[min(i, ncta)];
+    const int last = s_cnt[ncta];
+    for (int i = ncta + 1 + threadIdx.x; i <= max_cta; i += blockDim.x) s_cnt[i] = last;
 }
 
 // u8 global load that lands zero-extended in a 32-bit register: no dependent instruction (mask /

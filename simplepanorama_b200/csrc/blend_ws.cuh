@@ -29,11 +29,11 @@ constexpr int WS_HTHREADS = 128;
 // after the role split: the launch allocates 128 x 384 = 49152 (8 V warps; then 256 x 96 + 128 x 192 = 49152) or
 // 128 x 512 = 65536 (12 V warps; then 384 x 96 + 128 x 224 = 65536).
 // With 8 V warps the launch is capped at 128 registers per thread (49152 per CTA) instead of the 168 it could take; a
-// quarter of the register file and 1.4 KB of shared memory stay free.  That does NOT make the SM shareable: measured on
-// the fused path (profiles/r2_fused_step_timeline.txt), the warp / mask kernels of the next image (auxiliary stream) start
-// only when a launch of this kernel has ended, whereas they run next to the 8-warp marching kernel -- a CTA that
-// re-partitions its registers with setmaxnreg keeps its SM to itself.  (The variant without setmaxnreg, UNIFORM below,
-// would share, but starves its H group of prefetch registers and is 2x slower.)
+// quarter of the register file (16 K) and 1.4 KB of shared memory stay free, i.e. room for ONE small CTA per SM: in the
+// fused path the warp / mask kernels of the NEXT image (auxiliary stream) run next to the blend of the current one.  Every
+// kernel of that chain has to fit (<= 64 registers x 256 threads, no shared memory beyond the 1 KB system reserve): one
+// that does not waits for the blend to end and holds up the chain behind it (measured, profiles/r2_fused_step_timeline.txt;
+// see resize_linear_u8_kernel and plan_kernel).
 template <int VT> struct WsRegs { static constexpr int LAUNCH = 128, V = 96, H = (VT == 256) ? 192 : 224; };
 
 template <int B, int SW, int VT>
@@ -160,8 +160,8 @@ __device__ __forceinline__ void ws_row_item(const Params &P, const float *raw, f
 
 // UNIFORM = true: every thread keeps the 128 registers of the launch (no setmaxnreg) and the H group loads the bytes of a
 // chunk right before it stages them instead of one chunk ahead (no prefetch registers; the H group has the slack to sit out
-// the load latency).  A CTA that re-partitions its registers with setmaxnreg does not share its SM with CTAs of other
-// kernels (measured: the warp / mask kernels of the next image then only run between blend launches), a uniform one does.
+// the load latency).  Measured 2x slower (the H warps, one per scheduler, are the critical path and now wait for their
+// loads); kept as SPANO_OPT_BLEND_KERNEL = 4 for A/B runs.
 template <int B, int SW, int VT, bool UNIFORM>
 __global__ void __maxnreg__(WsRegs<VT>::LAUNCH) blend_ws_kernel(const Params P)
 {

@@ -55,7 +55,10 @@ __global__ void resize_tables_kernel(int sw, int sh, int dw, int dh, AxisEntry *
 // is 0 whatever the coefficients, so such groups skip the arithmetic.
 constexpr int RESIZE_ROWS = 16;
 
-__global__ void __launch_bounds__(256) resize_linear_u8_kernel(const uint8_t *src, int sw, int sh, size_t sstep, const AxisEntry *xt,
+// At most 56 registers (x 256 threads = 14 K): this is the first kernel of the auxiliary-stream work of an image in the fused
+// path, and an SM that runs a blend CTA of the previous image has 16 K registers left.  At 80 registers (what ptxas takes with
+// the row loop unrolled) the CTA does not fit, and the whole warp / mask chain behind it waits until the blend has ended.
+__global__ void __maxnreg__(56) resize_linear_u8_kernel(const uint8_t *src, int sw, int sh, size_t sstep, const AxisEntry *xt,
                                                                const AxisEntry *yt, uint8_t *dst, int dw, int dh, size_t dstep,
                                                                int row_begin, int row_end)
 {
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(256) resize_linear_u8_kernel(const uint8_t *sr
             return;
         }
     }
-#pragma unroll 4
+#pragma unroll 1
     for (int r = 0; r < RESIZE_ROWS; ++r) {
         const int dy = y_first + r;
         if (dy >= row_end) break;

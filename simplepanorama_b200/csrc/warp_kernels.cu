@@ -351,6 +351,8 @@ __device__ __forceinline__ void map_backward4(const WarpParams &P, int x0, int v
 }
 
 constexpr int WARP_PX_PER_THREAD = 4;
+// (block shape: 4, 8 and 12 warps per CTA measured the same, alone and next to a blend CTA of the fused path, where an SM has
+// room for ONE such CTA -- 16 K registers and ~1.4 KB of shared memory are free beside blend_ws_kernel)
 constexpr int WARP_BLOCK_X = 32, WARP_BLOCK_Y = 8;
 
 // 4 consecutive destination pixels x0..x0+3 of tile row v: coordinates, sampling (from the staged box when there is one),
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(WARP_BLOCK_X *WARP_BLOCK_Y) warp_kernel(const 
     __shared__ uint8_t s_gain[256];
     {
         const uint32_t t = threadIdx.y * WARP_BLOCK_X + threadIdx.x;
-        s_gain[t] = (uint8_t)(P.apply_gain ? gain_u8(t, P.inv_gain) : t);
+        if (t < 256) s_gain[t] = (uint8_t)(P.apply_gain ? gain_u8(t, P.inv_gain) : t);
     }
     __syncthreads();
     const int x0 = (blockIdx.x * WARP_BLOCK_X + threadIdx.x) * WARP_PX_PER_THREAD;
