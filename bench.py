@@ -175,10 +175,16 @@ def bind_to_gpu_numa_node(torch, index: int):
             if a.strip().isdigit():
                 cpus.update(range(int(a), int(b or a) + 1))
         return cpus
+    seen = {}
+    try:
+        seen["nodes_online"] = open("/sys/devices/system/node/online").read().strip()
+    except Exception:
+        seen["nodes_online"] = None
     try:
         p = torch.cuda.get_device_properties(index)
         bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        seen["sysfs_numa_node"] = node
         if node >= 0:
             cpus = parse_list(open(f"/sys/devices/system/node/node{node}/cpulist").read()) & os.sched_getaffinity(0)
             if cpus:
@@ -195,12 +201,14 @@ def bind_to_gpu_numa_node(torch, index: int):
             vals = [c for c in rows[0].split("\t") if c.strip()]
             k = cols.index([c for c in cols if "CPU Affinity" in c][0]) + 1    # the row has its own name in front
             cpus = parse_list(vals[k]) & os.sched_getaffinity(0)
+            seen["topo_cpu_affinity"] = vals[k].strip()
             if cpus and len(cpus) < len(os.sched_getaffinity(0)):
                 os.sched_setaffinity(0, cpus)
                 return {"numa_node": None, "source": "nvidia-smi topo", "cpus": len(cpus)}
     except Exception:
         pass
-    return None
+    # nothing to bind to: say what the host exposes (a single node / no PCI locality = nothing to fix by binding)
+    return {"numa_node": None, "source": "not bound", "cpus": len(os.sched_getaffinity(0)), **seen}
 
 
 class _Shape:

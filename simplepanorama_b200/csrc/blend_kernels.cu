@@ -276,8 +276,9 @@ int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
 {
     constexpr int SW = (B <= 6) ? 32 : 16;
     using C = march::Cfg<B, SW>;
-    const int mode = ctx->opt_blend_kernel;   // 0 default (warp-specialised, 8 V warps, uniform registers), 2 the 8-warp marching kernel, 3 warp-specialised with 12 V warps,
-    // 4 warp-specialised with the setmaxnreg register split
+    // 0 default (warp-specialised, 8 V warps; 12 for B >= 9), 2 the 8-warp marching kernel, 3 warp-specialised with 12 V warps,
+    // 4 warp-specialised without the setmaxnreg register split
+    const int mode = ctx->opt_blend_kernel;
     static bool configured[64] = {false};
     int dev = ctx->device & 63;
     if (mode == 2 && !configured[dev]) {
@@ -312,6 +313,7 @@ int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
         if (mode == 3) return launch_ws<B, SW, 384, false>(ctx, P, sms);
     }
     if (mode == 4) return launch_ws<B, SW, 256, true>(ctx, P, sms);   // no setmaxnreg: measured 2x slower, kept for A/B
+    if constexpr (B >= 9) return launch_ws<B, SW, 384, false>(ctx, P, sms);   // 6 sigma groups x 2 instead of 4 x 3
     return launch_ws<B, SW, 256, false>(ctx, P, sms);
 }
 

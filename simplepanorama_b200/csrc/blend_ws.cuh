@@ -34,7 +34,13 @@ constexpr int WS_HTHREADS = 128;
 // kernel of that chain has to fit (<= 64 registers x 256 threads, no shared memory beyond the 1 KB system reserve): one
 // that does not waits for the blend to end and holds up the chain behind it (measured, profiles/r2_fused_step_timeline.txt;
 // see resize_linear_u8_kernel and plan_kernel).
-template <int VT> struct WsRegs { static constexpr int LAUNCH = 128, V = 96, H = (VT == 256) ? 192 : 224; };
+// (setmaxnreg is a warpgroup-wide instruction: both groups must be whole warpgroups, so VT is a multiple of 128 -- a 10-warp V
+// group deadlocks.)  Strips of 16 columns with B = 9 or 10 use the 12-warp V group: six sigma groups of two sigmas instead of
+// four groups of three with one of them idle or short.
+template <int VT> struct WsRegs {
+    static_assert(VT % 128 == 0, "setmaxnreg needs whole warpgroups");
+    static constexpr int LAUNCH = 128, V = 96, H = (VT == 256) ? 192 : 224;
+};
 
 template <int B, int SW, int VT>
 struct WsCfg {
