@@ -533,7 +533,7 @@ def run_ours(args):
     n_blend = max(1, stage_n["blend"] // args.steps)
     n_warp = max(1, len(iso_tiles))   # one warp_kernel (+ one tiny table kernel) per tile
     roofline = {
-        "kernel": f"march::blend_ws_kernel<{cfg.bands},{32 if cfg.bands <= 6 else 16},256>", "bound": "fp32",
+        "kernel": f"march::blend_ws_kernel<{cfg.bands},{32 if cfg.bands <= 6 else 16},{256 if cfg.bands <= 8 else 384}>", "bound": "fp32",
         "achieved": blend_flops / blend_s / 1e12 if blend_s > 0 else None, "peak": fp32_peak, "unit": "TFLOP/s",
         "frac": (blend_flops / blend_s / 1e12 / fp32_peak) if blend_s > 0 else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture, scaled to this run
@@ -708,7 +708,7 @@ def run_band_sweep(args, rn, torch, fp32_peak):
         bs = stage_ms["blend"] * 1e-3 / 5
         out["per_band"].append({"bands": B, "value": rn.W * rn.H / 1e6 / (ms * 1e-3), "ms_per_step": ms, "blend_ms_per_step": bs * 1e3,
                                 "roofline_frac": (688.0 * B * done / bs / 1e12 / fp32_peak) if bs > 0 else None,
-                                "kernel": f"blend_ws_kernel<{B},{32 if B <= 6 else 16},256>", "active_fraction": done / offered if offered else None})
+                                "kernel": f"blend_ws_kernel<{B},{32 if B <= 6 else 16},{256 if B <= 8 else 384}>", "active_fraction": done / offered if offered else None})
     rn.cfg.bands = keep
     return out
 
