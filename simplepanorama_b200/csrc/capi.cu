@@ -852,11 +852,6 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], cs));
         return 0;
     };
-    {
-        StageTimer t(ctx, 2);
-        if (int rc = launch_blend_clear(ctx, acc, cw, rows)) return rc;
-        t.stop(0);
-    }
     // Warp + validity mask of image i+1 run on an auxiliary stream while image i is blended on the main
     // stream (two tile buffers): the blend CTAs leave issue slots and registers free, the small warp/mask
     // CTAs (no shared memory) co-reside on the same SMs and fill them.
@@ -871,6 +866,11 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
     cudaStream_t main_stream = ctx->stream, aux = ctx->aux_stream;
     SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_start2, main_stream));
     SPANO_CUDA(ctx, cudaStreamWaitEvent(aux, ctx->ev_start2, 0));
+    {   // the accumulator clear (pure HBM writes) runs while the auxiliary stream already warps the first image
+        StageTimer t(ctx, 2);
+        if (int rc = launch_blend_clear(ctx, acc, cw, rows)) return rc;
+        t.stop(0);
+    }
     struct StreamSwap {
         spano_ctx *c; cudaStream_t keep;
         StreamSwap(spano_ctx *ctx_, cudaStream_t s) : c(ctx_), keep(ctx_->stream) { c->stream = s; }
