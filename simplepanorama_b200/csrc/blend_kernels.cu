@@ -314,7 +314,7 @@ int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
     }
     if (mode == 4) return launch_ws<B, SW, 256, true>(ctx, P, sms);   // no setmaxnreg: measured 2x slower, kept for A/B
     if constexpr (B >= 9) return launch_ws<B, SW, 384, false>(ctx, P, sms);   // 6 sigma groups x 2 instead of 4 x 3
-    return launch_ws<B, SW, 256, false>(ctx, P, sms);
+    else return launch_ws<B, SW, 256, false>(ctx, P, sms);
 }
 
 template <int B>
