@@ -279,10 +279,9 @@ class Runner:
         self.ctx = api.Context(local)
         # a dedicated (non-default) stream shared by torch and the library, so that torch.cuda.Event brackets exactly the
         # kernels the library launches (the legacy default stream has handle 0 = "use the context's own stream")
-        # HIGH priority: when the blend of image i and the warp of image i+1 (the library's auxiliary stream, default priority)
-        # become runnable at the same moment, the blend's 148 large CTAs must be placed first -- otherwise the warp kernel's
-        # thousands of small CTAs fill every SM and the blend waits for them to drain (measured: the two then run one after
-        # the other instead of side by side)
+        # (high priority, so that the blend's 148 large CTAs are placed before the small CTAs of the next image's warp when both
+        # become runnable at once; measured to make no difference -- what decides whether the two share the SMs is whether every
+        # kernel of the warp / mask chain fits next to a blend CTA)
         self.stream = torch.cuda.Stream(device=dev, priority=-1)
         assert self.stream.cuda_stream != 0
         self.ctx.set_stream(self.stream.cuda_stream)

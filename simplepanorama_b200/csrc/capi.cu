@@ -200,8 +200,8 @@ extern "C" int spano_create(spano_ctx **out, int device)
     ctx->device = device;
     int prev = -1;
     if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    // the context's own stream gets the highest priority: blends (main stream) must win the SMs against the warp / mask kernels
-    // of the next image (auxiliary stream, default priority) when both become runnable at once -- see composite_impl
+    // the context's own stream gets the highest priority, so that a blend's large CTAs (main stream) are placed before the small
+    // CTAs of the next image's warp / mask kernels (auxiliary stream, default priority) when both become runnable at once
     int prio_lo = 0, prio_hi = 0;
     bool ok = cudaSetDevice(device) == cudaSuccess;
     if (ok) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
@@ -853,8 +853,9 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
         return 0;
     };
     // Warp + validity mask of image i+1 run on an auxiliary stream while image i is blended on the main
-    // stream (two tile buffers): the blend CTAs leave issue slots and registers free, the small warp/mask
-    // CTAs (no shared memory) co-reside on the same SMs and fill them.
+    // stream (two tile buffers): a blend CTA leaves 16 K registers and 1.4 KB of shared memory of its SM free, room
+    // for one small CTA, so every kernel of that chain is kept within 64 registers x 256 threads and without
+    // shared memory of its own (one that does not fit waits for the blend to end and stalls the chain behind it).
     if (!ctx->aux_stream) {
         SPANO_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
         for (int b = 0; b < 2; ++b) {
