@@ -562,11 +562,20 @@ def run_ours(args):
     if world == 1:
         ctx.set_option(ctx.OPT_BLEND_DENSE, 1)
         ms_d, _, _ = rn.timed(rn.step_dev, 2, 1)
+        cks_dense = rn.checksum()
         ctx.set_option(ctx.OPT_BLEND_DENSE, 0)
         dense = {"value": canvas_mpx / (ms_d * 1e-3), "unit": UNIT, "ms_per_step": ms_d,
                  "note": "blend sparsity disabled (SPANO_OPT_BLEND_DENSE): all tile pixels filtered"}
 
     checksum = rn.checksum()
+    # size-independent properties at the full bench size: the canvas with the sparsity switched off, and the canvas from the
+    # round-1 blend kernel (same arithmetic, different schedule), must be bit-identical to the default one
+    invariants = None
+    if world == 1:
+        ctx.set_option(ctx.OPT_BLEND_KERNEL, 2)
+        cks_march = rn.checksum()
+        ctx.set_option(ctx.OPT_BLEND_KERNEL, getattr(args, "blend_kernel", 0) or 0)
+        invariants = {"dense_canvas_identical": cks_dense == checksum, "march_kernel_canvas_identical": cks_march == checksum}
 
     e2e = None
     if not args.no_e2e:
@@ -667,7 +676,7 @@ def run_ours(args):
                 "clocks": clocks, "numa": numa,
                 "canvas_checksum": checksum, "cpu_enqueue_ms_per_step": enqueue,
                 "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu, "parity_at_bench_scale": parity,
-                "dense_masks": dense, "cfg1": cfg1, "cfg4": cfg4, "band_sweep": band_sweep,
+                "dense_masks": dense, "invariants_at_bench_scale": invariants, "cfg1": cfg1, "cfg4": cfg4, "band_sweep": band_sweep,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
                 "stage_note": "in-step warp/mask times overlap the blend (auxiliary stream); isolated: warp %.3f ms, mask %.3f ms per step" % (warp_s * 1e3, mask_iso_ms),
                 "tile_mpx_per_s": prim["T"] / 1e6 / (ms * 1e-3)}
