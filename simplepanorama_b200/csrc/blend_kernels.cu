@@ -48,6 +48,7 @@ struct BlendParams {
     const uint8_t *valid; size_t valid_step;
     int w, h;          // tile extent
     int ty_begin, ty_end; // tile rows to produce
+    int wx0, wx1;      // tile columns to produce: the part of the tile inside the accumulator's columns (reads go 21 px beyond)
     float4 *acc;       // canvas accumulator rows [row0, ...), pitch canvas_w
     int canvas_w;
     int ax, ay;        // tile corner relative to acc origin (canvas x, canvas y - row0)
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(GTHREADS) blend_generic_kernel(const __grid_co
     bool ok[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        ok[j] = (tx0 + cx < P.w) && (ty0 + cy + 8 * j < P.ty_end);
+        ok[j] = (tx0 + cx >= P.wx0) && (tx0 + cx < P.wx1) && (ty0 + cy + 8 * j < P.ty_end);
         wsum[j] = 0.f;
         cur[j] = 0.f;
         contrib[0][j] = contrib[1][j] = contrib[2][j] = 0.f;
@@ -250,7 +251,7 @@ int make_plan(spano_ctx *ctx, const BlendParams &Q, int sms, int *plan)
         dim3 ag((Q.w + 511) / 512, (rb - ra + 63) / 64);
         march::activity_kernel<SW><<<ag, 256, 0, ctx->stream>>>(Q.cut, Q.cut_step, Q.w, ra, rb, ymin, ymax);
     }
-    march::plan_kernel<SW><<<1, 256, 0, ctx->stream>>>(plan, strips, sms, Q.ty_begin, Q.ty_end, dense, ctx->blend_stats, Q.w);
+    march::plan_kernel<SW><<<1, 256, 0, ctx->stream>>>(plan, strips, sms, Q.ty_begin, Q.ty_end, dense, ctx->blend_stats, Q.wx0, Q.wx1);
     SPANO_CUDA(ctx, cudaGetLastError());
     ctx->launches += dense ? 2 : 3;
     return 0;
@@ -293,6 +294,7 @@ int launch_march(spano_ctx *ctx, const BlendParams &Q, int sms)
     P.valid = Q.valid;  P.valid_step = Q.valid_step;
     P.w = Q.w;  P.h = Q.h;
     P.ty_begin = Q.ty_begin;  P.ty_end = Q.ty_end;
+    P.wx0 = Q.wx0;  P.wx1 = Q.wx1;
     P.acc = Q.acc;  P.canvas_w = Q.canvas_w;  P.ax = Q.ax;  P.ay = Q.ay;
     // sparsity plan (activity of mask_cut per strip -> active output rows -> even split over the CTAs), unless the
     // caller already made it (fused path: on the auxiliary stream, one image ahead)
@@ -426,7 +428,7 @@ size_t blend_plan_bytes(spano_ctx *ctx, int w, int bands, int radius)
     return march::PlanView::ints((w + SW - 1) / SW, sms) * sizeof(int);
 }
 
-int launch_blend_plan(spano_ctx *ctx, const BlendTile &t, int bands, int radius, int row0, int row1, int *plan)
+int launch_blend_plan(spano_ctx *ctx, const BlendTile &t, int bands, int radius, int row0, int row1, int *plan, int canvas_w)
 {
     int ty_begin = row0 - t.cy, ty_end = row1 - t.cy;
     if (ty_begin < 0) ty_begin = 0;
@@ -436,6 +438,8 @@ int launch_blend_plan(spano_ctx *ctx, const BlendTile &t, int bands, int radius,
     P.cut = t.cut;  P.cut_step = t.cut_step;
     P.w = t.w;  P.h = t.h;
     P.ty_begin = ty_begin;  P.ty_end = ty_end;
+    P.wx0 = std::max(0, -t.cx);  P.wx1 = std::min(t.w, canvas_w - t.cx);
+    if (P.wx1 <= P.wx0) return 0;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     const int rc = bands <= 6 ? make_plan<32>(ctx, P, sms, plan) : make_plan<16>(ctx, P, sms, plan);
@@ -456,6 +460,9 @@ int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius,
     P.valid = t.valid;  P.valid_step = t.valid_step;
     P.w = t.w;  P.h = t.h;
     P.ty_begin = ty_begin;  P.ty_end = ty_end;
+    // a tile may stick out of the accumulator's columns (column bands: the accumulator is a column range of the canvas)
+    P.wx0 = std::max(0, -t.cx);  P.wx1 = std::min(t.w, canvas_w - t.cx);
+    if (P.wx1 <= P.wx0) return 0;
     P.acc = acc;  P.canvas_w = canvas_w;
     P.ax = t.cx;  P.ay = t.cy - row0;
     P.radius = radius;

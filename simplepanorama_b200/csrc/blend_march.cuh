@@ -62,6 +62,7 @@ struct Params {
     int canvas_w;
     int ax, ay;
     const int *plan;        // device plan of this launch (see Plan below)
+    int wx0, wx1;           // tile columns that are accumulated (the tile clipped to the accumulator's columns)
 };
 
 // ---- sparsity plan -----------------------------------------------------------------------------------------
@@ -131,7 +132,7 @@ __global__ void plan_init_kernel(int *ymin, int *ymax, int S)
 
 // one CTA; S <= 2048 strips, max_cta <= 1024
 template <int SW>
-__global__ void plan_kernel(int *plan, int S, int max_cta, int ty_begin, int ty_end, int dense, unsigned long long *stats, int w)
+__global__ void plan_kernel(int *plan, int S, int max_cta, int ty_begin, int ty_end, int dense, unsigned long long *stats, int wx0, int wx1)
 {
     constexpr int NB = (R + SW - 1) / SW;   // neighbour strips whose mask_cut reaches into this strip's window
     const PlanView V(S, max_cta);
@@ -148,6 +149,7 @@ __global__ void plan_kernel(int *plan, int S, int max_cta, int ty_begin, int ty_
             if (hi < 0) { a0 = a1 = ty_begin; }
             else { a0 = max(ty_begin, lo - R); a1 = min(ty_end, hi + R + 1); if (a1 < a0) a1 = a0; }
         }
+        if ((s + 1) * SW <= wx0 || s * SW >= wx1) a1 = a0;   // the strip lies outside the columns that are accumulated
         plan[V.a0() + s] = a0;
         plan[V.a1() + s] = a1;
         s_pref[s + 1] = (a1 - a0 + STEP - 1) / STEP * STEP;
@@ -166,7 +168,7 @@ __global__ void plan_kernel(int *plan, int S, int max_cta, int ty_begin, int ty_
         plan[0] = total;  plan[1] = per;  plan[2] = ncta;
         if (stats) {
             atomicAdd(stats, (unsigned long long)total * SW);                       // tile pixels processed (incl. rounding)
-            atomicAdd(stats + 1, (unsigned long long)(ty_end - ty_begin) * w);      // tile pixels of the launch
+            atomicAdd(stats + 1, (unsigned long long)(ty_end - ty_begin) * (wx1 - wx0));      // tile pixels of the launch
         }
     }
     __syncthreads();
@@ -485,7 +487,7 @@ __global__ void __launch_bounds__(THREADS, 1) blend_march_kernel(const Params P)
         // issue the global loads of the combine of step s (consumed after the next barrier A)
         {
             const int cty = y0 + s * STEP + po, ctx_ = tx0 + px;
-            cdo = vdo && (tid < C::NPX) && (ctx_ < P.w) && (cty < y1);
+            cdo = vdo && (tid < C::NPX) && (ctx_ >= P.wx0) && (ctx_ < P.wx1) && (cty < y1);
             if (cdo) {
                 vraw = ldg_u8(P.valid + (size_t)cty * P.valid_step + ctx_);
                 const uint8_t *pp = P.tile + (size_t)cty * P.tile_step + (size_t)ctx_ * 3;

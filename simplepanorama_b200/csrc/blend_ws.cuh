@@ -272,7 +272,7 @@ __global__ void __maxnreg__(WsRegs<VT>::LAUNCH) blend_ws_kernel(const Params P)
             float4 accv = make_float4(0.f, 0.f, 0.f, 0.f);
             float4 *accp = nullptr;
             const int cty = y0 + s * STEP + po, ctx_ = tx0 + px;
-            const bool cdo = (tid < C::NPX) && (ctx_ < P.w) && (cty < y1);
+            const bool cdo = (tid < C::NPX) && (ctx_ >= P.wx0) && (ctx_ < P.wx1) && (cty < y1);
             if (cdo) {
                 vraw = ldg_u8(P.valid + (size_t)cty * P.valid_step + ctx_);
                 const uint8_t *pp = P.tile + (size_t)cty * P.tile_step + (size_t)ctx_ * 3;

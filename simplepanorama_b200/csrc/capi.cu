@@ -985,7 +985,7 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
                 // the blend's sparsity plan (activity of mask_cut -> pieces) is made here, one image ahead, so that
                 // the blends follow each other back to back on the main stream
                 const BlendTile pt{tile_b, t_step, cut, c_step, valid, v_step, im[j].w, im[j].h, im[j].tl_x - mx, im[j].tl_y - my};
-                int kk = launch_blend_plan(ctx, pt, bands, radius, row0, row1, d_plan[b]);
+                int kk = launch_blend_plan(ctx, pt, bands, radius, row0, row1, d_plan[b], cw);
                 if (kk < 0) return kk;
             }
             SPANO_CUDA(ctx, cudaEventRecord(ctx->ev_warped[b], aux));
@@ -1308,7 +1308,7 @@ int blend_prepare_impl(spano_ctx *ctx, int n, const spano_image_desc *images, co
         if (blend_plan_bytes(ctx, im->w, S.bands, S.radius)) {
             plan = reinterpret_cast<int *>(plan_arena + off_p[j]);
             const BlendTile pt{nullptr, 0, cut_v, c_step, nullptr, 0, im->w, im->h, im->tl_x - S.mx, im->tl_y - S.my};
-            int k = launch_blend_plan(ctx, pt, S.bands, S.radius, S.row0, S.row1, plan);
+            int k = launch_blend_plan(ctx, pt, S.bands, S.radius, S.row0, S.row1, plan, S.cw);
             if (k < 0) return k;
         }
         if (ev_used == ctx->event_pool.size()) {

@@ -145,7 +145,9 @@ int launch_blend_clear(spano_ctx *ctx, float4 *acc, int canvas_w, int rows);
 int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius, float4 *acc, int canvas_w, int row0,
                       int row1, const int *plan = nullptr);
 size_t blend_plan_bytes(spano_ctx *ctx, int w, int bands, int radius);
-int launch_blend_plan(spano_ctx *ctx, const BlendTile &t, int bands, int radius, int row0, int row1, int *plan);
+// canvas_w: width of the accumulator the tile will be blended into (tile columns outside [0, canvas_w) - cx are clipped, as
+// launch_blend_tile clips them: the plan must be made for the same window)
+int launch_blend_plan(spano_ctx *ctx, const BlendTile &t, int bands, int radius, int row0, int row1, int *plan, int canvas_w);
 int launch_normalise(spano_ctx *ctx, const float4 *acc, int canvas_w, int rows, int bands, int out_kind, void *out,
                      size_t out_step, int col0 = 0, int col1 = -1);
 int launch_fp32_peak(spano_ctx *ctx, int variant, double *tflops);

@@ -300,3 +300,52 @@ def test_shard_step_two_processes_ipc():
         p.join(timeout=300)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert q.get(timeout=5) is True
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# column ranges: the accumulator of a blend session may be a COLUMN range of the canvas (spano_dev_blend_begin with
+# canvas_w = the range's width and min_x shifted): tiles that stick out of it are clipped, the result is those
+# columns of the full canvas bit for bit
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("name,scale,coarse", [("cfg2", 0.04, True), ("cfg1", 0.2, False), ("cfg4", 0.03, True)])
+@pytest.mark.parametrize("kernel", [0, 2, 1])
+def test_column_range_of_the_canvas(ctx, name, scale, coarse, kernel):
+    import torch
+    from simplepanorama_b200 import api
+    from simplepanorama_b200._lib import Slice, ImageDesc
+    cfg, K, R, gains, images, plan, cuts = _case(name, scale, coarse)
+    full = api.return_full(images, R, K, cfg.kind, cfg.focal, gains, cuts, cfg.bands, cfg.sigma, ctx=ctx)
+    dev = torch.device("cuda", 0)
+    corners, sizes = [p[2] for p in plan], [p[3] for p in plan]
+    W, H, min_x, min_y = api.pan_dimension(corners, sizes)
+    imgs = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in images]
+    cts = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in cuts]
+    descs = api.make_descs(imgs, plan, gains, cts, lambda t: t.data_ptr(), lambda t: t.stride(0))
+    al16 = lambda v: (v + 15) // 16 * 16
+    tiles, valids = [], []
+    for j in range(cfg.n):   # whole tiles, warped once
+        w, h = sizes[j]
+        t = torch.zeros((h, al16(3 * w)), dtype=torch.uint8, device=dev)
+        m = torch.zeros((h, al16(w)), dtype=torch.uint8, device=dev)
+        d = descs[j]
+        ctx.check(ctx.lib.spano_dev_warp(ctx.h, cfg.kind, C.c_float(cfg.focal), d.K, d.R, d.src_bgr, d.src_w, d.src_h, d.src_step, C.c_double(d.gain),
+                                         d.tl_x, d.tl_y, d.w, d.h, t.data_ptr(), t.stride(0), m.data_ptr(), m.stride(0)))
+        tiles.append(t); valids.append(m)
+    ctx.set_option(ctx.OPT_BLEND_KERNEL, kernel)
+    try:
+        rng = np.random.default_rng(7)
+        cuts_at = sorted(set([0, W] + [int(v) for v in rng.integers(1, W, 3)] + [W // 2, W // 2 + 1]))
+        for c0, c1 in zip(cuts_at, cuts_at[1:]):
+            ctx.check(ctx.lib.spano_dev_blend_begin(ctx.h, c1 - c0, min_x + c0, min_y, 0, H, cfg.bands, C.c_double(cfg.sigma)))
+            for j in range(cfg.n):
+                s = Slice(0, sizes[j][1], tiles[j].data_ptr(), tiles[j].stride(0), valids[j].data_ptr(), valids[j].stride(0))
+                pj = C.cast(C.addressof(descs) + j * C.sizeof(ImageDesc), C.POINTER(ImageDesc))
+                ctx.check(ctx.lib.spano_dev_blend_add(ctx.h, pj, C.byref(s)))
+            out = torch.zeros((H, 3 * (c1 - c0)), dtype=torch.uint8, device=dev)
+            ctx.check(ctx.lib.spano_dev_blend_finish(ctx.h, C.c_void_p(out.data_ptr()), out.stride(0)))
+            ctx.sync()
+            got = out.cpu().numpy().reshape(H, c1 - c0, 3)
+            assert np.array_equal(got, full[:, c0:c1]), f"columns [{c0},{c1}) of {W}"
+    finally:
+        ctx.set_option(ctx.OPT_BLEND_KERNEL, 0)
