@@ -308,14 +308,20 @@ int spano_dev_multiblend(spano_ctx *ctx, int n, const uint8_t *const *tiles, con
  * over NVLink / NVSwitch through pointers opened with spano_peer_open); no staging copy, no collective
  * on the data path -- the caller only needs a barrier between "all owners have written" and "blend".
  *
- * A slice = rows [row0,row1) of one warped tile as stored at its band owner: `tile` / `valid` point at the
- * storage of tile row `row0` (8UC3 / 8UC1, steps in bytes; 16-byte aligned rows recommended).           */
+ * A slice = rows [row0,row1) (and, optionally, columns [col0,col1)) of one warped tile as stored at its band owner:
+ * `tile` / `valid` point at the storage of tile pixel (row0, col0) (8UC3 / 8UC1, steps in bytes; 16-byte aligned rows
+ * recommended).  col1 <= col0 (e.g. both 0): all columns.  A column range starts on a multiple of 32 and ends on one
+ * or at the tile's right edge.  Column ranges serve bands that are COLUMN ranges of the canvas: open the band's blend
+ * session with canvas_w = the width of the range and min_x = the panorama's min_x + its first column (the blend
+ * clips every tile to the session's columns); such a band reads the 32-column strips of a tile that intersect its
+ * columns, plus the blur radius on either side.                                                          */
 typedef struct spano_slice {
     int row0, row1;
     uint8_t *tile;
     size_t tile_step;
     uint8_t *valid;
     size_t valid_step;
+    int col0, col1;
 } spano_slice;
 
 /* Peer memory: cudaMalloc + cudaIpcGetMemHandle on the owner, cudaIpcOpenMemHandle on the peers

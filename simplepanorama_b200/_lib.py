@@ -34,9 +34,9 @@ class ImageDesc(C.Structure):
 
 
 class Slice(C.Structure):
-    """struct spano_slice: rows [row0,row1) of one warped tile as stored at its band owner"""
+    """struct spano_slice: rows [row0,row1) (columns [col0,col1); col1 <= col0: all) of one warped tile as stored at its band owner"""
     _fields_ = [("row0", C.c_int), ("row1", C.c_int), ("tile", C.c_void_p), ("tile_step", C.c_size_t),
-                ("valid", C.c_void_p), ("valid_step", C.c_size_t)]
+                ("valid", C.c_void_p), ("valid_step", C.c_size_t), ("col0", C.c_int), ("col1", C.c_int)]
 
 
 class ShardPlanC(C.Structure):

@@ -1151,12 +1151,20 @@ int warp_scatter_impl(spano_ctx *ctx, int proj, float scale, const spano_image_d
     for (int d = 0; d < n_slices; ++d) {
         const spano_slice &s = slices[d];
         if (s.row0 < 0 || s.row1 > im->h || s.row1 <= s.row0) return spano_fail(ctx, SPANO_E_INVALID, "slice %d: rows [%d,%d) outside the tile (h=%d)", d, s.row0, s.row1, im->h);
-        if (!s.tile || !s.valid || s.tile_step < (size_t)im->w * 3 || s.valid_step < (size_t)im->w)
+        int c0 = 0, c1 = im->w;
+        if (s.col1 > s.col0) {   // the slice holds a column range of the tile (32-pixel granularity: one word of the mask kernel)
+            c0 = s.col0;  c1 = s.col1;
+            if (c0 < 0 || c1 > im->w || (c0 & 31) || ((c1 & 31) && c1 != im->w))
+                return spano_fail(ctx, SPANO_E_INVALID, "slice %d: columns [%d,%d) must lie inside the tile (w=%d) on multiples of 32", d, c0, c1, im->w);
+        }
+        if (!s.tile || !s.valid || s.tile_step < (size_t)(c1 - c0) * 3 || s.valid_step < (size_t)(c1 - c0))
             return spano_fail(ctx, SPANO_E_INVALID, "slice %d: null pointer or step too small", d);
         st.row0[d] = sm.row0[d] = s.row0;
         st.row1[d] = sm.row1[d] = s.row1;
-        st.base[d] = s.tile - (size_t)s.row0 * s.tile_step;   st.step[d] = s.tile_step;
-        sm.base[d] = s.valid - (size_t)s.row0 * s.valid_step; sm.step[d] = s.valid_step;
+        st.col0[d] = sm.col0[d] = c0;
+        st.col1[d] = sm.col1[d] = c1;
+        st.base[d] = s.tile - (size_t)s.row0 * s.tile_step - (size_t)c0 * 3;   st.step[d] = s.tile_step;
+        sm.base[d] = s.valid - (size_t)s.row0 * s.valid_step - (size_t)c0;     sm.step[d] = s.valid_step;
     }
     st.n = sm.n = n_slices;
     if (n_slices == 0) return SPANO_OK;
@@ -1359,7 +1367,19 @@ int blend_add_impl(spano_ctx *ctx, const spano_image_desc *im, const spano_slice
     const int need0 = (im->h < 4 * R) ? 0 : std::max(0, first - R), need1 = (im->h < 4 * R) ? im->h : std::min(im->h, last + R);
     if (slice->row0 > need0 || slice->row1 < need1)
         return spano_fail(ctx, SPANO_E_INVALID, "slice rows [%d,%d) do not cover the rows the band reads [%d,%d)", slice->row0, slice->row1, need0, need1);
-    if (!slice->tile || !slice->valid || slice->tile_step < (size_t)im->w * 3 || slice->valid_step < (size_t)im->w)
+    // columns: the slice may hold a column range of the tile; the band reads the strips (32 columns) that intersect its own
+    // columns, plus the blur radius (BORDER_REFLECT stays inside the tile, as for the rows)
+    int sc0 = 0, sc1 = im->w;
+    if (slice->col1 > slice->col0) { sc0 = slice->col0;  sc1 = slice->col1; }
+    {
+        const int cx = im->tl_x - S.mx;
+        const int wx0 = std::max(0, -cx), wx1 = std::min(im->w, S.cw - cx);
+        if (wx1 <= wx0) return SPANO_OK;   // the tile does not touch this band's columns
+        const int needc0 = (im->w < 4 * R) ? 0 : std::max(0, (wx0 & ~31) - R), needc1 = (im->w < 4 * R) ? im->w : std::min(im->w, ((wx1 + 31) & ~31) + R);
+        if (sc0 > needc0 || sc1 < needc1)
+            return spano_fail(ctx, SPANO_E_INVALID, "slice columns [%d,%d) do not cover the columns the band reads [%d,%d)", sc0, sc1, needc0, needc1);
+    }
+    if (!slice->tile || !slice->valid || slice->tile_step < (size_t)(sc1 - sc0) * 3 || slice->valid_step < (size_t)(sc1 - sc0))
         return spano_fail(ctx, SPANO_E_INVALID, "slice: null pointer or step too small");
     const uint8_t *cut_v = nullptr;   // virtual address of mask_cut row 0 at tile size
     size_t c_step = 0;
@@ -1374,8 +1394,8 @@ int blend_add_impl(spano_ctx *ctx, const spano_image_desc *im, const spano_slice
         if (int rc = blend_resolve_cut(ctx, im, need0, need1, host, spano_ctx::BUF_CUTMASK, 0, &cut_v, &c_step)) return rc;
     }
     StageTimer t2(ctx, 2);
-    const BlendTile bt{slice->tile - (size_t)slice->row0 * slice->tile_step, slice->tile_step, cut_v, c_step,
-                       slice->valid - (size_t)slice->row0 * slice->valid_step, slice->valid_step, im->w, im->h, im->tl_x - S.mx, cy};
+    const BlendTile bt{slice->tile - (size_t)slice->row0 * slice->tile_step - (size_t)sc0 * 3, slice->tile_step, cut_v, c_step,
+                       slice->valid - (size_t)slice->row0 * slice->valid_step - (size_t)sc0, slice->valid_step, im->w, im->h, im->tl_x - S.mx, cy};
     int k = launch_blend_tile(ctx, bt, S.bands, S.radius, S.acc, S.cw, S.row0, S.row1, plan);
     if (k < 0) return k;
     t2.stop(k);

@@ -215,7 +215,8 @@ __global__ void erode_bits_kernel(const uint32_t *bits, int words_per_row, int w
     if (sc.n > 0) {
         // tile-sharded multi-GPU path: row y goes to every band slice that reads it (possibly peer-GPU memory)
         for (int d = 0; d < sc.n; ++d)
-            if (y >= sc.row0[d] && y < sc.row1[d]) store_mask_word(sc.base[d] + (size_t)y * sc.step[d] + x0, o, x0, w);
+            if (y >= sc.row0[d] && y < sc.row1[d] && x0 >= sc.col0[d] && x0 < sc.col1[d])
+                store_mask_word(sc.base[d] + (size_t)y * sc.step[d] + x0, o, x0, w);
     } else {
         store_mask_word(mask + (size_t)y * mask_step + x0, o, x0, w);
     }

@@ -113,7 +113,8 @@ int spano_reserve(spano_ctx *ctx, int which, size_t bytes, void **out);
 struct SpanoScatter {
     int n = 0;
     int row0[SPANO_MAX_SLICES], row1[SPANO_MAX_SLICES];
-    uint8_t *base[SPANO_MAX_SLICES];
+    int col0[SPANO_MAX_SLICES], col1[SPANO_MAX_SLICES];   // tile columns the slice holds (multiples of 32, or the tile width)
+    uint8_t *base[SPANO_MAX_SLICES];                       // VIRTUAL address of tile pixel (0, 0) in the slice's storage
     size_t step[SPANO_MAX_SLICES];
 };
 

@@ -396,7 +396,8 @@ __device__ __forceinline__ void warp_four_pixels(const WarpParams &P, const uint
         // tile-sharded multi-GPU path: the row goes to every band slice that reads it (its band plus the blur
         // halo of the neighbours), straight into the owning GPU's memory; the row index is warp-uniform
         for (int d = 0; d < P.sc.n; ++d)
-            if (v >= P.sc.row0[d] && v < P.sc.row1[d]) store_row(P.sc.base[d] + (size_t)v * P.sc.step[d] + (size_t)x0 * 3);
+            if (v >= P.sc.row0[d] && v < P.sc.row1[d] && x0 >= P.sc.col0[d] && x0 < P.sc.col1[d])
+                store_row(P.sc.base[d] + (size_t)v * P.sc.step[d] + (size_t)x0 * 3);
     } else if (P.dst) {
         store_row(P.dst + (size_t)v * P.dst_step + (size_t)x0 * 3);
     }   // else: flags-only pass (validity masks computed on another rank's behalf), no tile store

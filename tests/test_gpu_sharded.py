@@ -22,11 +22,21 @@ def _case(name, scale, coarse):
     return cfg, K, R, gains, images, plan, cuts
 
 
-def _run_sharded(ctx, cfg, gains, images, plan, cuts, world, host):
+def _band_shape(sp, k):
+    """(rows, columns) of rank k's band"""
+    cw, _, r0, r1 = sp.band_geometry(k)
+    return max(0, r1 - r0), cw
+
+
+def _join(sp, parts):
+    return np.concatenate(parts, axis=1 if sp.orient == "cols" else 0)
+
+
+def _run_sharded(ctx, cfg, gains, images, plan, cuts, world, host, orient="rows"):
     import torch
     from simplepanorama_b200 import api, dist
     dev = torch.device("cuda", 0)
-    sp = dist.plan_tile_shards([p[2] for p in plan], [p[3] for p in plan], world, cfg.sigma)
+    sp = dist.plan_tile_shards([p[2] for p in plan], [p[3] for p in plan], world, cfg.sigma, orient=orient)
     arenas = [torch.zeros(sp.arena_bytes[k], dtype=torch.uint8, device=dev) for k in range(world)]
     ptrs = [a.data_ptr() for a in arenas]
     if host:
@@ -41,12 +51,12 @@ def _run_sharded(ctx, cfg, gains, images, plan, cuts, world, host):
         dist.scatter_tile(ctx, sp, j, descs[j], ptrs, cfg.kind, cfg.focal, host=host)
     parts = []
     for k in range(world):                       # band side
-        r0, r1 = sp.bands[k]
-        if r1 <= r0:
+        rows, bw = _band_shape(sp, k)
+        if rows <= 0 or bw <= 0:
             continue
         # host variant: announce the images (and the canvas, for the early column download) for even bands only, so
         # both the staged / early-flush and the on-demand paths run
-        out = torch.zeros((r1 - r0, sp.canvas_w, 3), dtype=torch.uint8).pin_memory() if host else None
+        out = torch.zeros((rows, bw, 3), dtype=torch.uint8).pin_memory() if host else None
         announce = host and k % 2 == 0
         dist.blend_begin(ctx, sp, k, cfg.bands, cfg.sigma, host_descs=descs if announce else None,
                          host_canvas=(out.data_ptr(), out.stride(0)) if announce else (0, 0))
@@ -58,12 +68,12 @@ def _run_sharded(ctx, cfg, gains, images, plan, cuts, world, host):
             dist.blend_finish(ctx, out.data_ptr(), out.stride(0), host=True)
             parts.append(out.numpy().copy())
         else:
-            out = torch.empty((r1 - r0, sp.canvas_w, 3), dtype=torch.uint8, device=dev)
+            out = torch.empty((rows, bw, 3), dtype=torch.uint8, device=dev)
             dist.blend_finish(ctx, out.data_ptr(), out.stride(0))
             ctx.sync()
             parts.append(out.cpu().numpy())
     ctx.sync()
-    return np.concatenate(parts, axis=0), sp
+    return _join(sp, parts), sp
 
 
 @pytest.mark.parametrize("name,scale,coarse", [("cfg1", 0.2, False), ("cfg2", 0.04, True), ("cfg3", 0.06, True)])
@@ -123,7 +133,7 @@ def test_sharded_errors(ctx):
 # ---------------------------------------------------------------------------------------------------------------
 # spano_shard_step_owner / spano_shard_step_band: the library-driven step, ordered by readiness flags
 # ---------------------------------------------------------------------------------------------------------------
-def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=3, poll_kernel=False, two_arenas=False):
+def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=3, poll_kernel=False, two_arenas=False, orient="rows"):
     """`world` ranks emulated on one device: per rank one band context + one owner context (their own streams), arenas and
     flag blocks are plain device buffers.  From the second step on (scratch buffers have their final size: nothing calls
     cudaFree, which would wait for the blocked streams) the band phases are enqueued BEFORE the owner phases, so the band
@@ -134,7 +144,7 @@ def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=3, poll_
     import torch
     from simplepanorama_b200 import api, dist
     dev = torch.device("cuda", 0)
-    sp = dist.plan_tile_shards([p[2] for p in plan], [p[3] for p in plan], world, cfg.sigma)
+    sp = dist.plan_tile_shards([p[2] for p in plan], [p[3] for p in plan], world, cfg.sigma, orient=orient)
     n = cfg.n
     arenas = [torch.full((sp.arena_bytes[k],), 0xAB, dtype=torch.uint8, device=dev) for k in range(world)]
     arenas_b = [torch.full((sp.arena_bytes[k],), 0xCD, dtype=torch.uint8, device=dev) for k in range(world)] if two_arenas else None
@@ -143,7 +153,7 @@ def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=3, poll_
     if host:
         imgs = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in images]
         cts = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in cuts]
-        hcv = [torch.zeros((max(1, b1 - b0), sp.canvas_w, 3), dtype=torch.uint8).pin_memory() for (b0, b1) in sp.bands]
+        hcv = [torch.zeros((max(1, _band_shape(sp, k)[0]), max(1, _band_shape(sp, k)[1]), 3), dtype=torch.uint8).pin_memory() for k in range(world)]
     else:
         imgs = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in images]
         cts = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in cuts]
@@ -153,9 +163,8 @@ def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=3, poll_
     own_ctx = [api.Context(0) for _ in range(world)]
     sessions = []
     for k in range(world):
-        r0, _ = sp.bands[k]
         sessions.append(dist.ShardSession(sp, k, cfg.kind, cfg.focal, cfg.bands, cfg.sigma, [a.data_ptr() for a in arenas],
-                                          [f.data_ptr() for f in flags], canvas.data_ptr() + r0 * canvas.stride(0), canvas.stride(0),
+                                          [f.data_ptr() for f in flags], canvas.data_ptr() + sp.band_origin(k, canvas.stride(0)), canvas.stride(0),
                                           arena_ptrs2=[a.data_ptr() for a in arenas_b] if two_arenas else None))
         if poll_kernel:
             band_ctx[k].set_option(3, 1)   # SPANO_OPT_FLAG_WAIT
@@ -187,7 +196,7 @@ def _run_shard_steps(cfg, gains, images, plan, cuts, world, host, steps=3, poll_
         for c in band_ctx + own_ctx:
             c.sync()
         if host:
-            results.append(np.concatenate([hcv[k].numpy()[: b1 - b0] for k, (b0, b1) in enumerate(sp.bands) if b1 > b0], axis=0).copy())
+            results.append(_join(sp, [hcv[k].numpy()[: _band_shape(sp, k)[0], : _band_shape(sp, k)[1]] for k, (b0, b1) in enumerate(sp.bands) if b1 > b0]).copy())
         else:
             results.append(canvas.cpu().numpy())
     for c in band_ctx + own_ctx:
@@ -349,3 +358,42 @@ def test_column_range_of_the_canvas(ctx, name, scale, coarse, kernel):
             assert np.array_equal(got, full[:, c0:c1]), f"columns [{c0},{c1}) of {W}"
     finally:
         ctx.set_option(ctx.OPT_BLEND_KERNEL, 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# column bands (dist.plan_tile_shards(orient="cols")): slices are column ranges of the tiles, the owners scatter by
+# column, every band blends a column range of the canvas -- same bar: the bands join to the single-GPU canvas bit for bit
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("name,scale,coarse", [("cfg1", 0.2, False), ("cfg2", 0.04, True), ("cfg3", 0.06, True), ("cfg4", 0.03, True)])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_column_bands_equal_single_gpu(ctx, name, scale, coarse, world):
+    from simplepanorama_b200 import api
+    cfg, K, R, gains, images, plan, cuts = _case(name, scale, coarse)
+    full = api.return_full(images, R, K, cfg.kind, cfg.focal, gains, cuts, cfg.bands, cfg.sigma, ctx=ctx)
+    got, sp = _run_sharded(ctx, cfg, gains, images, plan, cuts, world, host=False, orient="cols")
+    assert sp.orient == "cols" and got.shape == full.shape and np.array_equal(got, full)
+
+
+@pytest.mark.timeout(120)
+def test_column_bands_host_buffers(ctx):
+    from simplepanorama_b200 import api
+    cfg, K, R, gains, images, plan, cuts = _case("cfg2", 0.04, True)
+    full = api.return_full(images, R, K, cfg.kind, cfg.focal, gains, cuts, cfg.bands, cfg.sigma, ctx=ctx)
+    got, _ = _run_sharded(ctx, cfg, gains, images, plan, cuts, 3, host=True, orient="cols")
+    assert np.array_equal(got, full)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("name,scale,coarse,world", [("cfg2", 0.04, True, 4), ("cfg4", 0.03, True, 3), ("cfg1", 0.2, False, 2)])
+def test_shard_step_column_bands(ctx, name, scale, coarse, world):
+    from simplepanorama_b200 import api
+    cfg, K, R, gains, images, plan, cuts = _case(name, scale, coarse)
+    full = api.return_full(images, R, K, cfg.kind, cfg.focal, gains, cuts, cfg.bands, cfg.sigma, ctx=ctx)
+    res, sp = _run_shard_steps(cfg, gains, images, plan, cuts, world, host=False, steps=4, two_arenas=True, orient="cols")
+    assert sp.orient == "cols"
+    for got in res:
+        assert got.shape == full.shape and np.array_equal(got, full)
+    res, _ = _run_shard_steps(cfg, gains, images, plan, cuts, world, host=True, orient="cols")
+    for got in res:
+        assert np.array_equal(got, full)

@@ -186,7 +186,7 @@ def test_ctypes_structs_match_the_header(tmp_path):
     fields = {"spano_image_desc": (L.ImageDesc, ["src_bgr", "src_w", "src_h", "src_step", "K", "R", "gain", "mask_cut", "mask_cut_step",
                                                  "tl_x", "tl_y", "w", "h", "valid_mask", "valid_mask_step", "mask_cut_w", "mask_cut_h",
                                                  "intensity", "intensity_w", "intensity_h", "intensity_step"]),
-              "spano_slice": (L.Slice, ["row0", "row1", "tile", "tile_step", "valid", "valid_step"]),
+              "spano_slice": (L.Slice, ["row0", "row1", "tile", "tile_step", "valid", "valid_step", "col0", "col1"]),
               "spano_overlap_info": (L.OverlapInfo, ["i", "j", "area", "I_i", "I_j"])}
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "spano.h"', 'int main(void) {']
     for name, (_, fs) in fields.items():
