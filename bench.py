@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--no-cfg1", action="store_true")
     ap.add_argument("--no-cfg4", action="store_true")
     ap.add_argument("--no-center-fix", action="store_true", help="cfg3 without sten_proj::disk_reproj")
+    ap.add_argument("--band-orient", default="auto", choices=["auto", "rows", "cols"],
+                    help="N > 1: canvas row bands or column bands (auto: whichever leaves the bands closer to square)")
     ap.add_argument("--blend-kernel", type=int, default=0, help="SPANO_OPT_BLEND_KERNEL (0 default; 2 = the 8-warp marching kernel of round 1)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU time budget of the cpu_baseline sample")
     return ap.parse_args()
@@ -112,11 +114,11 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # workload description shared by both arms
 # ----------------------------------------------------------------------------------------------
-def config_json(cfg, W, H, T, args, world, note=None):
+def config_json(cfg, W, H, T, args, world, note=None, orient="rows"):
     d = {"workload": f"{cfg.name}: {cfg.description}", "images": cfg.n, "image_size": [cfg.width, cfg.height],
          "projection": ["spherical", "cylindrical", "stereographic"][cfg.kind], "focal": cfg.focal, "bands": cfg.bands,
          "sigma": cfg.sigma, "canvas": [W, H], "tile_mpx": round(T / 1e6, 1),
-         "sharding": (f"tile-sharded warp+mask (owner by band locality) -> NVLink peer stores -> row-band blend x{world}, ordered by "
+         "sharding": (f"tile-sharded warp+mask (owner by band locality) -> NVLink peer stores -> {'column' if orient == 'cols' else 'row'}-band blend x{world}, ordered by "
                       f"readiness flags (cuStreamWaitValue32); two alternating sets of slice arenas, so the owners' warps of step s+1 overlap the blends of step s" if world > 1 else "single GPU"),
          "mask_cut": "preview scale (1/8), resized to tile size on the device inside the step",
          "l2": "inputs larger than L2 (sources 1.7 GB vs 126 MB)", "scale": args.scale}
@@ -264,8 +266,8 @@ class Runner:
                                                                 self.fix.radius, bool(self.fix.quadratic))
         self.W, self.H, _, self.min_y = api.pan_dimension(self.corners, self.sizes)
         self.T = sum(w * h for w, h in self.sizes)
-        self.sp = sdist.plan_tile_shards(self.corners, self.sizes, world, cfg.sigma)
-        self.row0, self.row1 = self.sp.bands[rank]
+        self.sp = sdist.plan_tile_shards(self.corners, self.sizes, world, cfg.sigma, orient=getattr(args, "band_orient", "auto") if world > 1 else "rows")
+        self.band_w, _, self.row0, self.row1 = self.sp.band_geometry(rank)   # this rank's band: band_w columns x rows [row0, row1)
         self.mine = set(j for j in range(cfg.n) if self.sp.owner[j] == rank) if world > 1 else set(range(cfg.n))
         workers = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
         with ThreadPoolExecutor(max_workers=workers) as ex:   # numpy releases the GIL
@@ -299,7 +301,7 @@ class Runner:
         self.d_cut = [t.to(dev, non_blocking=True) for t in self.h_cut]
         rows = max(1, self.row1 - self.row0)
         self.d_canvas = torch.empty((rows, self.W, 3), dtype=torch.uint8, device=dev) if world == 1 else None
-        self.h_canvas = torch.empty((rows, self.W, 3), dtype=torch.uint8).pin_memory() if (want_host and self.h_img is not None) else None
+        self.h_canvas = torch.empty((rows, max(1, self.band_w), 3), dtype=torch.uint8).pin_memory() if (want_host and self.h_img is not None) else None
         torch.cuda.synchronize()
 
         class _Absent:   # placeholder for a source this rank does not own (never dereferenced)
@@ -323,7 +325,7 @@ class Runner:
             self.flags = sdist.PeerFlags(self.ctx, self.sp, rank)
             self.peer_canvas = sdist.PeerCanvas(self.ctx, self.sp, rank)   # the canvas lives on rank 0
             self.session = sdist.ShardSession(self.sp, rank, cfg.kind, cfg.focal, cfg.bands, cfg.sigma, self.arenas.ptrs, self.flags.ptrs,
-                                              self.peer_canvas.band_ptr(self.row0), self.peer_canvas.step, arena_ptrs2=self.arenas2.ptrs)
+                                              self.peer_canvas.origin(self.sp, rank), self.peer_canvas.step, arena_ptrs2=self.arenas2.ptrs)
         self.enqueue_ms = []
 
     def _estimate_circle(self, api, synth, name, scale):
@@ -581,7 +583,7 @@ def run_ours(args):
     if not args.no_e2e:
         ms_e, _, _ = rn.timed(rn.step_host, max(1, min(args.steps, 3)), 1)
         h2d = sum(a.numel() for a in rn.h_img if a is not None) + sum(a.numel() for a in rn.h_cut)
-        d2h = (rn.row1 - rn.row0) * rn.W * 3
+        d2h = (rn.row1 - rn.row0) * rn.band_w * 3
         # what the host link delivers on its own: the same pinned sources copied H2D back to back (all ranks at once)
         link = None
         try:
@@ -624,7 +626,7 @@ def run_ours(args):
         parity = {"max_abs_diff_lsb": int(d.max()), "differing_bytes": int((d > 0).sum()), "bytes": int(d.size), "shape_equal": got.shape == r["canvas"].shape,
                   "sample": f"images {s['idx']}, {s['rows']}-row strips, canvas {got.shape[1]}x{got.shape[0]}: the cpu_baseline sample's own inputs "
                             f"through spano_composite vs the cv2 result", "bar": "<= 1 LSB per channel"}
-    prim = {"W": rn.W, "H": rn.H, "T": rn.T, "note": ("centre fix: " + rn.fix_note) if name == "cfg3" and world == 1 and hasattr(rn, "fix_note") else None}
+    prim = {"W": rn.W, "H": rn.H, "T": rn.T, "orient": rn.sp.orient, "note": ("centre fix: " + rn.fix_note) if name == "cfg3" and world == 1 and hasattr(rn, "fix_note") else None}
     enqueue = float(np.median(rn.enqueue_ms)) if rn.enqueue_ms else None
     rn.close()
     del rn
@@ -660,7 +662,7 @@ def run_ours(args):
             m4, l4, st4 = r4.timed(r4.step_dev, 3, 2, with_timers=True)
             c4 = r4.W * r4.H / 1e6
             cfg4 = {"workload": f"cfg4: {r4.cfg.description}", "canvas": [r4.W, r4.H], "tile_mpx": round(r4.T / 1e6, 1), "n_gpus": world,
-                    "value": c4 / (m4 * 1e-3), "ms_per_step": m4, "unit": UNIT, "steps": 3, "warmup": 2, "gpu_launches": int(l4),
+                    "bands": ("column" if r4.sp.orient == "cols" else "row") if world > 1 else None, "value": c4 / (m4 * 1e-3), "ms_per_step": m4, "unit": UNIT, "steps": 3, "warmup": 2, "gpu_launches": int(l4),
                     "canvas_checksum": r4.checksum(), "data": "synthetic, generated on the device",
                     "stage_ms_per_step_rank0": {k: v / 3 for k, v in st4[0].items()},
                     "cpu_enqueue_ms_per_step": (float(np.median(r4.enqueue_ms)) if r4.enqueue_ms else None)}
@@ -672,7 +674,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": config_json(cfg, prim["W"], prim["H"], prim["T"], args, world, prim.get("note")), "e2e": e2e, "gpu_launches": int(launches),
+                "data": "synthetic", "config": config_json(cfg, prim["W"], prim["H"], prim["T"], args, world, prim.get("note"), prim.get("orient", "rows")), "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "numa": numa,
                 "canvas_checksum": checksum, "cpu_enqueue_ms_per_step": enqueue,
                 "roofline": roofline, "roofline_warp": roofline_warp, "cpu_baseline": cpu, "parity_at_bench_scale": parity,

@@ -300,9 +300,10 @@ int spano_dev_multiblend(spano_ctx *ctx, int n, const uint8_t *const *tiles, con
  * loop over images inside blnd::multi_blend).  Across G GPUs the two loops shard differently:
  *   - warp + validity mask (src/math/_projection.cpp:422-454) are per-IMAGE work and the mask's flood
  *     fill is a whole-tile property: image j is uploaded, warped and masked ONCE, by its owner rank;
- *   - the blend (src/math/_blending.cpp:186-252) shards by canvas ROW BAND: rank k accumulates and
- *     normalises the canvas rows [row0,row1) from the rows of every tile that its band reads (its rows
- *     plus the blur radius; BORDER_REFLECT is resolved inside the tile, so nothing else is needed).
+ *   - the blend (src/math/_blending.cpp:186-252) shards by canvas BAND -- row bands, or column bands where that
+ *     leaves the bands closer to square (a wide one-row panorama): rank k accumulates and normalises its rows
+ *     [row0,row1) (or columns) from the part of every tile that its band reads (its rows / columns plus the blur
+ *     radius; BORDER_REFLECT is resolved inside the tile, so nothing else is needed).
  * The exchange between the two is fused into the producing kernels: the warp kernel and the mask kernel
  * store every tile row straight into the memory of the GPU(s) whose band reads it (peer-to-peer stores
  * over NVLink / NVSwitch through pointers opened with spano_peer_open); no staging copy, no collective
@@ -405,14 +406,15 @@ typedef struct spano_shard_plan {
     float scale;
     int bands;
     double sigma;
-    int canvas_w, min_x, min_y; /* spano_pan_dimension of the whole panorama */
-    int row0, row1;             /* this rank's canvas row band */
+    int canvas_w, min_x, min_y; /* row bands: spano_pan_dimension of the whole panorama.  Column band [c0,c1): canvas_w = c1 - c0,
+                                   min_x = the panorama's min_x + c0 (the band's blend session covers just those columns) */
+    int row0, row1;             /* this rank's canvas rows (a column band: 0 and the canvas height) */
     const spano_image_desc *images;
     const int *owner;           /* [n] */
     const int *order;           /* [n] permutation: the order in which owners process images */
     const spano_slice *slices;  /* [world * n]; row1 <= row0: image j does not touch band k */
     uint32_t *const *flags;     /* [world] */
-    uint8_t *canvas;            /* row 0 of this band in the destination canvas (device pointer; NULL with host != 0) */
+    uint8_t *canvas;            /* first pixel of this band in the destination canvas (device pointer; NULL with host != 0) */
     size_t canvas_step;
     /* 1 (or 0): the owners of step s wait until every band has finished step s - 1 (one set of slice arenas).
      * 2: the caller alternates between TWO sets of arenas (`slices` of even / odd steps point into different memory), so the

@@ -172,14 +172,16 @@ def owner_order(n: int, slices):
     return order
 
 
-def band_orientation(canvas_w: int, canvas_h: int, world: int) -> str:
-    """Row bands or column bands: whichever leaves the bands closer to square.  A thin band gets a thin slice of EVERY
-    tile stacked across it -- many small blend launches whose pipeline fill and 42-row halo are not amortised (measured
-    on the 37000 x 4004 panorama at 8 ranks: 24 launches of 60 us of work taking 107 us each) -- a squarish band gets few,
-    large pieces."""
-    def aspect(w, h):
-        return max(w, h) / max(1, min(w, h))
-    return "cols" if aspect(canvas_w / world, canvas_h) < aspect(canvas_w, canvas_h / world) else "rows"
+def band_orientation(rows_plan: "ShardPlan", cols_plan: "ShardPlan") -> str:
+    """Row bands or column bands, from the two candidate plans.  What a band costs beyond its share of the pixels is the
+    number of tiles it touches: every (band, tile) pair is a slice, a flag, a mask up-scaling, a sparsity plan and a blend
+    launch whose pipeline fill and 42-row halo are amortised over fewer rows the thinner the slice is.  Measured at 8
+    ranks: the 36999 x 4004 one-row panorama (24 tiles under every row band, at most 8 under a column band) 3.26 ms with
+    row bands, 2.58 ms with column bands; the 54360 x 17451 sphere (80 against 63) 23.9 against 25.1 ms.  Column bands are
+    taken when they cut the busiest band's tile count to 60 % or less."""
+    def busiest(p):
+        return max(sum(1 for s in p.slices[k] if s is not None) for k in range(p.world))
+    return "cols" if busiest(cols_plan) <= 0.6 * busiest(rows_plan) else "rows"
 
 
 def plan_tile_shards(corners, sizes, world: int, sigma: float = 7.0, balance: str = "area", owners: str = "locality",
@@ -187,7 +189,7 @@ def plan_tile_shards(corners, sizes, world: int, sigma: float = 7.0, balance: st
     """corners[j] = (tl_x, tl_y), sizes[j] = (w, h) of every warped tile (spano_warp_roi).
     balance: "area" (equal band heights, see plan_area_bands) or "tile_pixels" (plan_row_bands).
     owners: "locality" (assign_owners) or "round_robin" (j % world).
-    orient: "rows" (canvas row bands), "cols" (canvas column bands) or "auto" (band_orientation)."""
+    orient: "rows" (canvas row bands), "cols" (canvas column bands) or "auto" (both are planned, band_orientation picks)."""
     import math
     n = len(sizes)
     radius = int(math.ceil(3 * sigma))
@@ -195,7 +197,11 @@ def plan_tile_shards(corners, sizes, world: int, sigma: float = 7.0, balance: st
     xs1 = max(c[0] + s[0] for c, s in zip(corners, sizes)); ys1 = max(c[1] + s[1] for c, s in zip(corners, sizes))
     W, H = xs1 - xs0, ys1 - ys0           # == util::get_pan_dimension
     if orient == "auto":
-        orient = band_orientation(W, H, world)
+        r = plan_tile_shards(corners, sizes, world, sigma, balance, owners, "rows")
+        if world == 1:
+            return r
+        c = _plan_column_shards(corners, sizes, world, radius, W, H, xs0, ys0, owners)
+        return c if band_orientation(r, c) == "cols" else r
     if orient == "cols":
         return _plan_column_shards(corners, sizes, world, radius, W, H, xs0, ys0, owners)
     bands = plan_area_bands(world, H) if balance == "area" else plan_row_bands(list(zip(corners, sizes)), world, ys0, H)

@@ -203,3 +203,58 @@ def test_ctypes_structs_match_the_header(tmp_path):
         assert int(out[name]) == C.sizeof(cls), name
         for f in fs:
             assert int(out[f"{name}.{f}"]) == getattr(cls, f).offset, f"{name}.{f}"
+
+
+def test_column_shard_plan_covers_every_band():
+    """plan_tile_shards(orient="cols"): the column bands partition the canvas, every tile column a band reads (the 32-column
+    strips that intersect its columns, +- the blur radius, inside the tile) is in that band's slice, slices start on
+    multiples of 32, arena slots do not overlap; orient="auto" takes column bands when they cut the busiest band's tile count."""
+    from simplepanorama_b200 import dist
+    # a one-row strip of 24 wide tiles: every row band sees all 24, a column band a handful -> columns; stacked the other way: rows
+    strip_c, strip_s = [(1540 * j, 0) for j in range(24)], [(5591, 4004)] * 24
+    assert dist.plan_tile_shards(strip_c, strip_s, 8, 7.0, orient="auto").orient == "cols"
+    assert dist.plan_tile_shards([(y, x) for (x, y) in strip_c], [(h, w) for (w, h) in strip_s], 8, 7.0, orient="auto").orient == "rows"
+    assert dist.plan_tile_shards(strip_c, strip_s, 1, 7.0, orient="auto").orient == "rows"
+    rng = np.random.default_rng(11)
+    for world in (1, 2, 3, 4, 8):
+        n = int(rng.integers(1, 30))
+        sizes = [(int(rng.integers(1, 900)), int(rng.integers(1, 500))) for _ in range(n)]
+        corners = [(int(rng.integers(-300, 4000)), int(rng.integers(-200, 400))) for _ in range(n)]
+        sp = dist.plan_tile_shards(corners, sizes, world, 7.0, orient="cols")
+        assert sp.orient == "cols" and sp.radius == 21
+        assert sp.bands[0][0] == 0 and sp.bands[-1][1] == sp.canvas_w
+        assert all(sp.bands[k][1] == sp.bands[k + 1][0] for k in range(world - 1))
+        assert max(sp.owner.count(k) for k in range(world)) <= -(-n // world)
+        assert all(0 <= o < world for o in sp.owner) and sorted(sp.order) == list(range(n))
+        for k in range(world):
+            b0, b1 = sp.bands[k]
+            cw, mx, r0, r1 = sp.band_geometry(k)
+            assert (cw, mx, r0, r1) == (b1 - b0, sp.min_x + b0, 0, sp.canvas_h) and sp.band_origin(k, 12345) == 3 * b0
+            spans = []
+            for j in range(n):
+                (w, h), cx = sizes[j], corners[j][0] - sp.min_x
+                wx0, wx1 = max(0, b0 - cx), min(w, b1 - cx)
+                if wx1 <= wx0:
+                    assert sp.slices[k][j] is None
+                    continue
+                assert sp.slices[k][j] == (0, h)
+                c0, c1 = sp.cols[k][j]
+                ts, vs = sp.steps[k][j]
+                assert c0 % 32 == 0 and (c1 % 32 == 0 or c1 == w) and 0 <= c0 < c1 <= w
+                if w < 84:
+                    assert (c0, c1) == (0, w)
+                else:   # what spano_dev_blend_add asks of a slice
+                    assert c0 <= max(0, (wx0 & ~31) - 21) and c1 >= min(w, ((wx1 + 31) & ~31) + 21)
+                assert ts >= 3 * (c1 - c0) and vs >= c1 - c0 and ts % 16 == 0 and vs % 16 == 0
+                t_off, v_off = sp.offsets[k][j]
+                assert t_off % 256 == 0 and v_off % 256 == 0
+                spans += [(t_off, t_off + ts * h), (v_off, v_off + vs * h)]
+            spans.sort()
+            assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
+            assert not spans or spans[-1][1] <= sp.arena_bytes[k]
+        for j in range(n):   # every tile column is stored somewhere
+            covered = np.zeros(sizes[j][0], bool)
+            for k in range(world):
+                if sp.slices[k][j] is not None:
+                    covered[sp.cols[k][j][0]:sp.cols[k][j][1]] = True
+            assert covered.all()
