@@ -175,3 +175,83 @@ def test_tile_sharded_exchange_world2(tmp_path):
     mp.spawn(_sharded_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     got, ref = np.load(out), np.load(out + ".ref.npy")
     assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# the same with COLUMN bands (dist.plan_tile_shards(orient="cols")): a band receives a column range of every tile
+# it touches (all rows), everything else is poisoned, and keeps its canvas columns
+# ---------------------------------------------------------------------------------------------
+def _sharded_cols_worker(rank, world, port, out_path):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    tdist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from simplepanorama_b200 import dist as sdist, synth
+    cfg = synth.config("cfg1", 0.12)
+    K, R, gains = synth.cameras(cfg)
+    bands_n, sigma = 2, 7.0
+    geo = []
+    for j in range(cfg.n):
+        K32, R32 = orc.adjusted_camera(K[j], R[j], cfg.width, cfg.height)
+        geo.append((K32, R32) + tuple(orc.warp_roi(cfg.kind, cfg.focal, K32, R32, cfg.width, cfg.height)))
+    corners = [(g[2][0], g[2][1]) for g in geo]
+    sizes = [(g[3][0], g[3][1]) for g in geo]
+    sp = sdist.plan_tile_shards(corners, sizes, world, sigma, orient="cols")
+    assert sp.orient == "cols"
+    cuts = synth.seam_masks(corners, sizes)
+    true = {}
+    for j in range(cfg.n):
+        if sp.owner[j] != rank and rank != 0:
+            continue
+        img = synth.make_image(cfg, j, gains[j])
+        _, tile = orc.warp(cfg.kind, cfg.focal, geo[j][0], geo[j][1], img)
+        true[j] = (orc.apply_gain(tile, gains[j]), orc.surrounding_mask(tile, 3))
+    rng = np.random.default_rng(200 + rank)
+    tiles, valids = [], []
+    for j in range(cfg.n):
+        w, h = sizes[j]
+        for k in range(world):
+            if sp.slices[k][j] is None or not (sp.owner[j] == rank and k != rank):
+                continue
+            c0, c1 = sp.cols[k][j]
+            tdist.send(torch.from_numpy(np.ascontiguousarray(true[j][0][:, c0:c1])), dst=k)
+            tdist.send(torch.from_numpy(np.ascontiguousarray(true[j][1][:, c0:c1])), dst=k)
+        t = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)      # poison: columns this band was never sent
+        v = rng.integers(0, 2, (h, w), dtype=np.uint8) * 255
+        if sp.slices[rank][j] is not None:
+            c0, c1 = sp.cols[rank][j]
+            if sp.owner[j] == rank:
+                t[:, c0:c1], v[:, c0:c1] = true[j][0][:, c0:c1], true[j][1][:, c0:c1]
+            else:
+                bt = torch.empty((h, c1 - c0, 3), dtype=torch.uint8); bv = torch.empty((h, c1 - c0), dtype=torch.uint8)
+                tdist.recv(bt, src=sp.owner[j]); tdist.recv(bv, src=sp.owner[j])
+                t[:, c0:c1], v[:, c0:c1] = bt.numpy(), bv.numpy()
+        tiles.append(t); valids.append(v)
+    b0, b1 = sp.bands[rank]
+    full = orc.blend_to_u8(orc.multi_blend(tiles, cuts, valids, corners, bands_n, sigma))
+    band = torch.from_numpy(np.ascontiguousarray(full[:, b0:b1]))
+    if rank == 0:
+        canvas = np.zeros_like(full)
+        canvas[:, b0:b1] = band.numpy()
+        for k in range(1, world):
+            k0, k1 = sp.bands[k]
+            buf = torch.empty((sp.canvas_h, k1 - k0, 3), dtype=torch.uint8)
+            tdist.recv(buf, src=k)
+            canvas[:, k0:k1] = buf.numpy()
+        np.save(out_path, canvas)
+        tt = [true[j][0] for j in range(cfg.n)]; tv = [true[j][1] for j in range(cfg.n)]
+        np.save(out_path + ".ref.npy", orc.blend_to_u8(orc.multi_blend(tt, cuts, tv, corners, bands_n, sigma)))
+    else:
+        tdist.send(band, dst=0)
+    tdist.barrier()
+    tdist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_tile_sharded_exchange_column_bands_world2(tmp_path):
+    world = 2
+    out = str(tmp_path / "sharded_cols.npy")
+    mp.spawn(_sharded_cols_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got, ref = np.load(out), np.load(out + ".ref.npy")
+    assert got.shape == ref.shape and np.array_equal(got, ref)
