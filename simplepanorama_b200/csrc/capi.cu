@@ -1709,7 +1709,7 @@ extern "C" int spano_shard_step_band(spano_ctx *ctx, const spano_shard_plan *P, 
     const int n = P->n, W = P->world;
     std::vector<uint32_t *> done_targets;
     for (int r = 0; r < W; ++r) done_targets.push_back(P->flags[r] + n + P->rank);
-    if (P->row1 <= P->row0) {   // an empty band still tells the owners that it is "done"
+    if (P->row1 <= P->row0 || P->canvas_w <= 0) {   // an empty band still tells the owners that it is "done"
         const int k = launch_flag_signal(ctx, done_targets.data(), W, step);
         return k < 0 ? k : SPANO_OK;
     }
