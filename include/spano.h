@@ -37,7 +37,9 @@
 extern "C" {
 #endif
 
-#define SPANO_VERSION 100
+/* 100: round 1.  200: spano_slice grew by col0/col1 (column bands); spano_set_option, spano_*_composite_fixed, spano_shard_step_*,
+ * spano_equalize_intensities added.  A host compiled against another major (hundreds) must not load this library. */
+#define SPANO_VERSION 200
 
 /* projection kinds == pan::Projection order used by the reference's projector classes */
 #define SPANO_SPHERICAL 0     /* proj::spherical_proj   -> cv::detail::SphericalWarper    */

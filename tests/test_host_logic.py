@@ -24,7 +24,7 @@ def test_header_symbols_exported(spano_lib):
     for n in names:
         assert hasattr(spano_lib, n), f"libspano.so does not export {n}"
         assert n in L.SYMBOLS, f"ctypes binding misses {n}"
-    assert spano_lib.spano_version() == 100
+    assert spano_lib.spano_version() == 200
 
 
 def test_no_cpu_fallback(spano_lib):
