@@ -231,9 +231,15 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *sink, int iters, 
     if (s == 123.456f) sink[0] = s;
 }
 
+struct PreviewCut {   // mask_cut at preview scale, to be up-scaled into Q.cut where the plan reads it
+    const uint8_t *small;
+    int sw, sh;
+    size_t sstep;
+};
+
 // activity + plan kernels of one tile launch into `plan` (device, march::PlanView::ints(strips, sms) ints)
 template <int SW>
-int make_plan(spano_ctx *ctx, const BlendParams &Q, int sms, int *plan)
+int make_plan(spano_ctx *ctx, const BlendParams &Q, int sms, int *plan, const PreviewCut *pv = nullptr)
 {
     const int strips = (Q.w + SW - 1) / SW;
     if (strips > 2048 || sms > 1024) return spano_fail(ctx, SPANO_E_LIMIT, "tile wider than %d px", 2048 * SW);
@@ -246,14 +252,26 @@ int make_plan(spano_ctx *ctx, const BlendParams &Q, int sms, int *plan)
     int *ymin = plan + V.ymin(), *ymax = plan + V.ymax();
     march::plan_init_kernel<<<(strips + 255) / 256, 256, 0, ctx->stream>>>(ymin, ymax, strips);
     const int dense = ctx->opt_blend_dense;
+    const int ra = std::max(0, Q.ty_begin - march::R), rb = std::min(Q.h, Q.ty_end + march::R);
+    int extra = 0;
     if (!dense) {
-        const int ra = std::max(0, Q.ty_begin - march::R), rb = std::min(Q.h, Q.ty_end + march::R);
-        dim3 ag((Q.w + 511) / 512, (rb - ra + 63) / 64);
-        march::activity_kernel<SW><<<ag, 256, 0, ctx->stream>>>(Q.cut, Q.cut_step, Q.w, ra, rb, ymin, ymax);
+        if (pv) {
+            const int k = launch_resize_activity(ctx, pv->small, pv->sw, pv->sh, pv->sstep, Q.w, Q.h, SW, ra, rb, ymin, ymax);
+            if (k < 0) return k;
+            extra += k - 1;
+        } else {
+            dim3 ag((Q.w + 511) / 512, (rb - ra + 63) / 64);
+            march::activity_kernel<SW><<<ag, 256, 0, ctx->stream>>>(Q.cut, Q.cut_step, Q.w, ra, rb, ymin, ymax);
+        }
     }
-    march::plan_kernel<SW><<<1, 256, 0, ctx->stream>>>(plan, strips, sms, Q.ty_begin, Q.ty_end, dense, ctx->blend_stats, Q.wx0, Q.wx1);
+    march::plan_kernel<SW><<<1, 256, 0, ctx->stream>>>(plan, strips, sms, Q.ty_begin, Q.ty_end, dense, ctx->blend_stats, Q.wx0, Q.wx1, pv ? Q.h : 0);
     SPANO_CUDA(ctx, cudaGetLastError());
-    ctx->launches += dense ? 2 : 3;
+    if (pv) {
+        const int k = launch_resize_mask_rows(ctx, pv->small, pv->sw, pv->sh, pv->sstep, const_cast<uint8_t *>(Q.cut), Q.w, Q.h, Q.cut_step, SW, ymin, ymax);
+        if (k < 0) return k;
+        extra += k;
+    }
+    ctx->launches += (dense ? 2 : 3) + extra;
     return 0;
 }
 
@@ -444,6 +462,26 @@ int launch_blend_plan(spano_ctx *ctx, const BlendTile &t, int bands, int radius,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     const int rc = bands <= 6 ? make_plan<32>(ctx, P, sms, plan) : make_plan<16>(ctx, P, sms, plan);
     return rc ? rc : 3;
+}
+
+int launch_blend_plan_preview(spano_ctx *ctx, const BlendTile &t, const uint8_t *small, int sw, int sh, size_t sstep, int bands, int radius,
+                              int row0, int row1, int *plan, int canvas_w)
+{
+    int ty_begin = row0 - t.cy, ty_end = row1 - t.cy;
+    if (ty_begin < 0) ty_begin = 0;
+    if (ty_end > t.h) ty_end = t.h;
+    if (ty_end <= ty_begin || t.w <= 0 || !plan || !march_path(ctx, radius)) return 0;
+    BlendParams P;
+    P.cut = t.cut;  P.cut_step = t.cut_step;
+    P.w = t.w;  P.h = t.h;
+    P.ty_begin = ty_begin;  P.ty_end = ty_end;
+    P.wx0 = std::max(0, -t.cx);  P.wx1 = std::min(t.w, canvas_w - t.cx);
+    if (P.wx1 <= P.wx0) return 0;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const PreviewCut pv{small, sw, sh, sstep};
+    const int rc = bands <= 6 ? make_plan<32>(ctx, P, sms, plan, &pv) : make_plan<16>(ctx, P, sms, plan, &pv);
+    return rc ? rc : 5;
 }
 
 int launch_blend_tile(spano_ctx *ctx, const BlendTile &t, int bands, int radius, float4 *acc, int canvas_w, int row0,

@@ -132,7 +132,11 @@ __global__ void plan_init_kernel(int *ymin, int *ymax, int S)
 
 // one CTA; S <= 2048 strips, max_cta <= 1024
 template <int SW>
-__global__ void plan_kernel(int *plan, int S, int max_cta, int ty_begin, int ty_end, int dense, unsigned long long *stats, int wx0, int wx1)
+// need_rows != 0: ymin / ymax are overwritten with, per strip, the tile rows [need0, need1) at which ANY launch piece reads
+// mask_cut in that strip's columns (the strip itself and the neighbours whose windows reach into it, +-R rows, clipped to the
+// tile of height need_rows; need1 <= need0: none) -- what an up-scaling of a preview-scale mask has to produce.
+__global__ void plan_kernel(int *plan, int S, int max_cta, int ty_begin, int ty_end, int dense, unsigned long long *stats, int wx0, int wx1,
+                            int need_rows)
 {
     constexpr int NB = (R + SW - 1) / SW;   // neighbour strips whose mask_cut reaches into this strip's window
     const PlanView V(S, max_cta);
@@ -155,6 +159,18 @@ __global__ void plan_kernel(int *plan, int S, int max_cta, int ty_begin, int ty_
         s_pref[s + 1] = (a1 - a0 + STEP - 1) / STEP * STEP;
     }
     __syncthreads();
+    if (need_rows > 0) {
+        int *need0 = plan + V.ymin(), *need1 = plan + V.ymax();   // (activity no longer needed: every a0 / a1 is final)
+        for (int s = threadIdx.x; s < S; s += blockDim.x) {
+            int lo = 0x7fffffff, hi = -1;
+            for (int t = max(0, s - NB); t <= min(S - 1, s + NB); ++t) {
+                const int b0 = plan[V.a0() + t], b1 = plan[V.a1() + t];
+                if (b1 > b0) { lo = min(lo, b0 - R); hi = max(hi, b1 + R); }
+            }
+            need0[s] = hi < 0 ? 0 : max(0, lo);
+            need1[s] = hi < 0 ? 0 : min(need_rows, hi);
+        }
+    }
     if (threadIdx.x == 0) {
         s_pref[0] = 0;
         int run = 0;

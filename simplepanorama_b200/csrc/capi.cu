@@ -919,12 +919,24 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
                 src = d_srcbuf[b];  s_step = align_up((size_t)im[j].src_w * 3, 16);
                 cut = d_cutbuf[b];  c_step = m_step;
             }
+            bool planned = false;
             if (im[j].mask_cut_w > 0 || im[j].mask_cut_h > 0) {
-                // mask_cut is at preview scale: cv::resize(.., tile size) with the 8-bit INTER_LINEAR arithmetic
+                // mask_cut is at preview scale: cv::resize(.., tile size) with the 8-bit INTER_LINEAR arithmetic.  With a
+                // sparsity plan the plan comes FIRST, from the preview mask, and only the rows of the tile-size mask that
+                // the plan's pieces read are produced (most of a seam mask is zero and never looked at).
                 const uint8_t *small = host ? d_cutsmall[b] : im[j].mask_cut;
                 const size_t small_step = host ? align_up((size_t)im[j].mask_cut_w, 16) : im[j].mask_cut_step;
-                int kk = launch_resize_mask(ctx, small, im[j].mask_cut_w, im[j].mask_cut_h, small_step, d_cutbuf[b], im[j].w, im[j].h, m_step);
-                if (kk < 0) return kk;
+                if (d_plan[b]) {
+                    const BlendTile pt{nullptr, 0, d_cutbuf[b], m_step, nullptr, 0, im[j].w, im[j].h, im[j].tl_x - mx, im[j].tl_y - my};
+                    int kk = launch_blend_plan_preview(ctx, pt, small, im[j].mask_cut_w, im[j].mask_cut_h, small_step, bands, radius, row0, row1,
+                                                       d_plan[b], cw);
+                    if (kk < 0) return kk;
+                    planned = kk > 0;
+                }
+                if (!planned) {
+                    int kk = launch_resize_mask(ctx, small, im[j].mask_cut_w, im[j].mask_cut_h, small_step, d_cutbuf[b], im[j].w, im[j].h, m_step);
+                    if (kk < 0) return kk;
+                }
                 cut = d_cutbuf[b];  c_step = m_step;
             }
             if (!host && im[j].valid_mask) {
@@ -981,7 +993,7 @@ int composite_impl(spano_ctx *ctx, int proj, float scale, int n, const spano_ima
                 int kk = launch_adjust_intensity(ctx, tile_b, im[j].w, im[j].h, t_step, fld, im[j].intensity_w, im[j].intensity_h, fpitch);
                 if (kk < 0) return kk;
             }
-            if (d_plan[b]) {
+            if (d_plan[b] && !planned) {
                 // the blend's sparsity plan (activity of mask_cut -> pieces) is made here, one image ahead, so that
                 // the blends follow each other back to back on the main stream
                 const BlendTile pt{tile_b, t_step, cut, c_step, valid, v_step, im[j].w, im[j].h, im[j].tl_x - mx, im[j].tl_y - my};
@@ -1198,8 +1210,11 @@ int warp_scatter_impl(spano_ctx *ctx, int proj, float scale, const spano_image_d
 // step.  Preview-scale masks are up-scaled (host ones are first looked up among those staged at begin, else uploaded),
 // tile-sized host masks are uploaded, tile-sized device masks are used in place.  Work goes to ctx->stream; the
 // resized rows land in buffer `buf` at byte offset `buf_off`.
+// `defer` (optional): when the mask is at preview scale it is NOT up-scaled here; *defer receives the (device) preview mask
+// and the caller up-scales what it needs (launch_blend_plan_preview, or launch_resize_mask for the rows [need0, need1)).
+struct PreviewRef { const uint8_t *small = nullptr; int sw = 0, sh = 0; size_t sstep = 0; };
 int blend_resolve_cut(spano_ctx *ctx, const spano_image_desc *im, int need0, int need1, bool host, int buf, size_t buf_off,
-                      const uint8_t **cut_v, size_t *cut_step)
+                      const uint8_t **cut_v, size_t *cut_step, PreviewRef *defer = nullptr)
 {
     spano_ctx::BlendSession &S = ctx->bs;
     const bool small = im->mask_cut_w > 0 || im->mask_cut_h > 0;
@@ -1235,8 +1250,12 @@ int blend_resolve_cut(spano_ctx *ctx, const spano_image_desc *im, int need0, int
                                               cudaMemcpyHostToDevice, ctx->stream));
             sm = stage;
         }
-        int k = launch_resize_mask(ctx, sm, im->mask_cut_w, im->mask_cut_h, sm_step, cut_base, im->w, im->h, m_step, need0, need1);
-        if (k < 0) return k;
+        if (defer) {
+            defer->small = sm;  defer->sw = im->mask_cut_w;  defer->sh = im->mask_cut_h;  defer->sstep = sm_step;
+        } else {
+            int k = launch_resize_mask(ctx, sm, im->mask_cut_w, im->mask_cut_h, sm_step, cut_base, im->w, im->h, m_step, need0, need1);
+            if (k < 0) return k;
+        }
     } else {
         SPANO_CUDA(ctx, cudaMemcpy2DAsync(cutbuf, m_step, im->mask_cut + (size_t)need0 * im->mask_cut_step, im->mask_cut_step, (size_t)im->w,
                                           need1 - need0, cudaMemcpyHostToDevice, ctx->stream));
@@ -1311,11 +1330,23 @@ int blend_prepare_impl(spano_ctx *ctx, int n, const spano_image_desc *images, co
         blend_rows(S, im, &first, &last, &need0, &need1);
         const uint8_t *cut_v = nullptr;
         size_t c_step = 0;
-        if (int rc = blend_resolve_cut(ctx, im, need0, need1, host, spano_ctx::BUF_PREP_CUT, off_c[j], &cut_v, &c_step)) return rc;
+        PreviewRef pv;
+        if (int rc = blend_resolve_cut(ctx, im, need0, need1, host, spano_ctx::BUF_PREP_CUT, off_c[j], &cut_v, &c_step, &pv)) return rc;
         int *plan = nullptr;
-        if (blend_plan_bytes(ctx, im->w, S.bands, S.radius)) {
-            plan = reinterpret_cast<int *>(plan_arena + off_p[j]);
-            const BlendTile pt{nullptr, 0, cut_v, c_step, nullptr, 0, im->w, im->h, im->tl_x - S.mx, im->tl_y - S.my};
+        const bool want_plan = blend_plan_bytes(ctx, im->w, S.bands, S.radius) != 0;
+        if (want_plan) plan = reinterpret_cast<int *>(plan_arena + off_p[j]);
+        const BlendTile pt{nullptr, 0, cut_v, c_step, nullptr, 0, im->w, im->h, im->tl_x - S.mx, im->tl_y - S.my};
+        bool planned = false;
+        if (pv.small && want_plan) {   // plan from the preview mask; only the rows / strips the plan reads are up-scaled
+            int k = launch_blend_plan_preview(ctx, pt, pv.small, pv.sw, pv.sh, pv.sstep, S.bands, S.radius, S.row0, S.row1, plan, S.cw);
+            if (k < 0) return k;
+            planned = k > 0;
+        }
+        if (pv.small && !planned) {    // no plan applies: all the rows the band reads
+            int k = launch_resize_mask(ctx, pv.small, pv.sw, pv.sh, pv.sstep, const_cast<uint8_t *>(cut_v), im->w, im->h, c_step, need0, need1);
+            if (k < 0) return k;
+        }
+        if (want_plan && !planned) {
             int k = launch_blend_plan(ctx, pt, S.bands, S.radius, S.row0, S.row1, plan, S.cw);
             if (k < 0) return k;
         }

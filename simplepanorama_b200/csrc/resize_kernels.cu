@@ -48,6 +48,34 @@ __global__ void resize_tables_kernel(int sw, int sh, int dw, int dh, AxisEntry *
     }
 }
 
+// First / last result row in [ra, rb) that has a non-zero source tap, per strip of strip_w result columns: block =
+// (strip, 1024 rows), thread = 4 rows.  The source taps of a strip are the columns xt[first].ofs .. xt[last].ofs + 1 of the
+// two source rows of the result row.  atomicMin / atomicMax into ymin / ymax (one per warp that found something).
+__global__ void resize_activity_kernel(const uint8_t *src, int sw, int sh, size_t sstep, const AxisEntry *xt, const AxisEntry *yt, int dw,
+                                       int strip_w, int ra, int rb, int *ymin, int *ymax)
+{
+    const int s = blockIdx.x;
+    const int c0 = s * strip_w, c1 = min(dw, c0 + strip_w) - 1;
+    const int sx0 = xt[c0].ofs, sx1 = min(xt[c1].ofs + 1, sw - 1);
+    int lo = 0x7fffffff, hi = -1;
+    for (int k = 0; k < 4; ++k) {
+        const int dy = ra + blockIdx.y * 1024 + k * 256 + threadIdx.x;
+        if (dy >= rb) break;
+        const int o = yt[dy].ofs;
+        const int y0 = min(max(o, 0), sh - 1), y1 = min(max(o + 1, 0), sh - 1);
+        const uint8_t *r0 = src + (size_t)y0 * sstep, *r1 = src + (size_t)y1 * sstep;
+        uint32_t any = 0;
+        for (int x = sx0; x <= sx1; ++x) any |= (uint32_t)__ldg(r0 + x) | (uint32_t)__ldg(r1 + x);
+        if (any) { lo = min(lo, dy); hi = max(hi, dy); }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d));
+    }
+    if ((threadIdx.x & 31) == 0 && hi >= 0) { atomicMin(ymin + s, lo); atomicMax(ymax + s, hi); }
+}
+
 // One thread = 4 consecutive destination pixels (one 32-bit store) of RESIZE_ROWS consecutive rows: the x-table
 // entries are loaded once and stay in registers, the rows are independent of each other (their loads overlap), and
 // the y-table entry of a row is the same for the whole block.  Seam masks are mostly 0 (SURVEY.md appendix A:
@@ -58,12 +86,22 @@ constexpr int RESIZE_ROWS = 16;
 // At most 56 registers (x 256 threads = 14 K): this is the first kernel of the auxiliary-stream work of an image in the fused
 // path, and an SM that runs a blend CTA of the previous image has 16 K registers left.  At 80 registers (what ptxas takes with
 // the row loop unrolled) the CTA does not fit, and the whole warp / mask chain behind it waits until the blend has ended.
+// need0 / need1 (optional): per strip of strip_w result columns the result rows [need0[s], need1[s]) that anybody will read;
+// the rest is not produced (a thread's 4 columns lie in one strip: strip_w is a multiple of 4).
 __global__ void __maxnreg__(56) resize_linear_u8_kernel(const uint8_t *src, int sw, int sh, size_t sstep, const AxisEntry *xt,
                                                                const AxisEntry *yt, uint8_t *dst, int dw, int dh, size_t dstep,
-                                                               int row_begin, int row_end)
+                                                               int row_begin, int row_end, int strip_w, const int *need0, const int *need1)
 {
     const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (dx0 >= dw) return;
+    // this thread's rows: the block's RESIZE_ROWS rows of the launch's range, cut down to what the strip needs
+    int y_first = row_begin + blockIdx.y * RESIZE_ROWS, y_end = min(y_first + RESIZE_ROWS, row_end);
+    if (need0) {
+        const int s = dx0 / strip_w;
+        y_first = max(y_first, __ldg(need0 + s));
+        y_end = min(y_end, __ldg(need1 + s));
+    }
+    if (y_end <= y_first) return;
     AxisEntry ex[4];
     int x1[4];
 #pragma unroll
@@ -71,13 +109,11 @@ __global__ void __maxnreg__(56) resize_linear_u8_kernel(const uint8_t *src, int 
         ex[i] = xt[min(dx0 + i, dw - 1)];
         x1[i] = min(ex[i].ofs + 1, sw - 1);
     }
-    const int y_first = row_begin + blockIdx.y * RESIZE_ROWS;
     const bool vec = dx0 + 4 <= dw && ((((uintptr_t)dst) | dstep) & 3) == 0;
     {
         // whole-thread early out: the source taps of all RESIZE_ROWS x 4 pixels lie in a small rectangle (both tables
         // are monotonic); if every byte of it is 0 -- most of a seam mask -- the pixels are 0
-        const int y_last = min(y_first + RESIZE_ROWS, row_end) - 1;
-        if (y_last < y_first) return;
+        const int y_last = y_end - 1;
         const int sy0 = min(max(yt[y_first].ofs, 0), sh - 1), sy1 = min(max(yt[y_last].ofs + 1, 0), sh - 1);
         const int sx0 = ex[0].ofs, sx1 = x1[3];
         uint32_t any = 1;
@@ -99,9 +135,7 @@ __global__ void __maxnreg__(56) resize_linear_u8_kernel(const uint8_t *src, int 
         }
     }
 #pragma unroll 1
-    for (int r = 0; r < RESIZE_ROWS; ++r) {
-        const int dy = y_first + r;
-        if (dy >= row_end) break;
+    for (int dy = y_first; dy < y_end; ++dy) {
         const AxisEntry ey = yt[dy];
         const int y0 = min(max(ey.ofs, 0), sh - 1), y1 = min(max(ey.ofs + 1, 0), sh - 1);
         const uint8_t *r0p = src + (size_t)y0 * sstep, *r1p = src + (size_t)y1 * sstep;
@@ -215,7 +249,47 @@ int launch_resize_mask(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_
     const int n = dw > dh ? dw : dh;
     resize_tables_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sw, sh, dw, dh, tab, tab + dw);
     dim3 block(256), grid((dw + 1023) / 1024, (row_end - row_begin + RESIZE_ROWS - 1) / RESIZE_ROWS);
-    resize_linear_u8_kernel<<<grid, block, 0, ctx->stream>>>(src, sw, sh, sstep, tab, tab + dw, dst, dw, dh, dstep, row_begin, row_end);
+    resize_linear_u8_kernel<<<grid, block, 0, ctx->stream>>>(src, sw, sh, sstep, tab, tab + dw, dst, dw, dh, dstep, row_begin, row_end, 4, nullptr, nullptr);
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return 2;
+}
+
+int launch_resize_activity(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_t sstep, int dw, int dh, int strip_w, int ra, int rb,
+                           int *ymin, int *ymax)
+{
+    if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0 || strip_w <= 0) return spano_fail(ctx, SPANO_E_INVALID, "resize: empty image");
+    ra = std::max(ra, 0);
+    rb = std::min(rb, dh);
+    AxisEntry *tab = nullptr;
+    int rc = spano_reserve(ctx, spano_table_buffer(ctx, spano_ctx::BUF_RESIZE, spano_ctx::BUF_RESIZE_AUX), (size_t)(dw + dh) * sizeof(AxisEntry), (void **)&tab);
+    if (rc) return rc;
+    const int n = dw > dh ? dw : dh;
+    resize_tables_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sw, sh, dw, dh, tab, tab + dw);
+    if (rb > ra) {
+        const int strips = (dw + strip_w - 1) / strip_w;
+        dim3 grid(strips, (rb - ra + 1023) / 1024);
+        resize_activity_kernel<<<grid, 256, 0, ctx->stream>>>(src, sw, sh, sstep, tab, tab + dw, dw, strip_w, ra, rb, ymin, ymax);
+    }
+    SPANO_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    return 2;
+}
+
+// (the tables of launch_resize_activity for the same geometry are still in the table buffer of this stream: the two calls are
+// made back to back by make_plan; they are rebuilt here all the same -- 2.5 us -- so that the call stands on its own)
+int launch_resize_mask_rows(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_t sstep, uint8_t *dst, int dw, int dh, size_t dstep,
+                            int strip_w, const int *need0, const int *need1)
+{
+    if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return spano_fail(ctx, SPANO_E_INVALID, "resize: empty image");
+    if (strip_w <= 0 || (strip_w & 3) || !need0 || !need1) return spano_fail(ctx, SPANO_E_INVALID, "resize: bad strip description");
+    AxisEntry *tab = nullptr;
+    int rc = spano_reserve(ctx, spano_table_buffer(ctx, spano_ctx::BUF_RESIZE, spano_ctx::BUF_RESIZE_AUX), (size_t)(dw + dh) * sizeof(AxisEntry), (void **)&tab);
+    if (rc) return rc;
+    const int n = dw > dh ? dw : dh;
+    resize_tables_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(sw, sh, dw, dh, tab, tab + dw);
+    dim3 block(256), grid((dw + 1023) / 1024, (dh + RESIZE_ROWS - 1) / RESIZE_ROWS);
+    resize_linear_u8_kernel<<<grid, block, 0, ctx->stream>>>(src, sw, sh, sstep, tab, tab + dw, dst, dw, dh, dstep, 0, dh, strip_w, need0, need1);
     SPANO_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
     return 2;

@@ -149,6 +149,12 @@ size_t blend_plan_bytes(spano_ctx *ctx, int w, int bands, int radius);
 // canvas_w: width of the accumulator the tile will be blended into (tile columns outside [0, canvas_w) - cx are clipped, as
 // launch_blend_tile clips them: the plan must be made for the same window)
 int launch_blend_plan(spano_ctx *ctx, const BlendTile &t, int bands, int radius, int row0, int row1, int *plan, int canvas_w);
+// mask_cut still at preview scale (small: sw x sh, device): the plan is made from the preview mask and only the rows of the
+// tile-size mask that the plan's pieces read are up-scaled, into t.cut (pitch t.cut_step; the rest of that buffer is left
+// untouched and is never read by a blend launched with this plan).  Returns 0 when no plan applies (the caller then
+// up-scales the whole mask with launch_resize_mask).
+int launch_blend_plan_preview(spano_ctx *ctx, const BlendTile &t, const uint8_t *small, int sw, int sh, size_t sstep, int bands, int radius,
+                              int row0, int row1, int *plan, int canvas_w);
 int launch_normalise(spano_ctx *ctx, const float4 *acc, int canvas_w, int rows, int bands, int out_kind, void *out,
                      size_t out_step, int col0 = 0, int col1 = -1);
 int launch_fp32_peak(spano_ctx *ctx, int variant, double *tflops);
@@ -158,6 +164,16 @@ int launch_resize_mask(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_
                        size_t dstep, int row_begin = 0, int row_end = -1);
 int launch_adjust_intensity(spano_ctx *ctx, uint8_t *bgr, int w, int h, size_t step, const float *field, int fw, int fh,
                             size_t fpitch_elems);
+// The same up-scaling split in two, for the blend's sparsity plan (launch_blend_plan_preview):
+// (a) per strip of strip_w result columns the first / last result row in [ra, rb) that has a non-zero source tap -- a superset
+//     of the rows where the up-scaled mask is non-zero (its coefficients are >= 0) -- merged into ymin / ymax (device, one int
+//     per strip, initialised to INT_MAX / -1 by the caller);
+// (b) the up-scaling itself, restricted per strip to the result rows [need0[s], need1[s]) (device arrays): nothing else is
+//     written.
+int launch_resize_activity(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_t sstep, int dw, int dh, int strip_w, int ra, int rb,
+                           int *ymin, int *ymax);
+int launch_resize_mask_rows(spano_ctx *ctx, const uint8_t *src, int sw, int sh, size_t sstep, uint8_t *dst, int dw, int dh, size_t dstep,
+                            int strip_w, const int *need0, const int *need1);
 // dist_kernels.cu: 5x5 chamfer distance transform (cv::distanceTransform DIST_L2 / DIST_MASK_5) and dcut::dist_cut
 int launch_distance_transform(spano_ctx *ctx, int n, const uint8_t *const *masks, const size_t *msteps, const int *w, const int *h,
                               float *const *dist, const size_t *dsteps);

@@ -10,7 +10,7 @@ import pytest
 
 from simplepanorama_b200 import _lib as L
 
-CHAIN = ["resize_tables_kernel", "resize_linear_u8_kernel", "warp_tables_kernelILi0E", "warp_tables_kernelILi1E", "warp_kernelILi0E",
+CHAIN = ["resize_tables_kernel", "resize_activity_kernel", "resize_linear_u8_kernel", "warp_tables_kernelILi0E", "warp_tables_kernelILi1E", "warp_kernelILi0E",
          "warp_kernelILi1E", "ccl_init_kernel", "ccl_merge_kernel", "resolve_bits_kernel", "erode_bits_kernel", "plan_init_kernel",
          "activity_kernelILi32E", "activity_kernelILi16E", "plan_kernelILi32E", "plan_kernelILi16E", "normalise_kernel"]
 THREADS = 256                      # largest CTA any of them is launched with
