@@ -1,4 +1,4 @@
-"""What does ONE rank of an N-GPU run cost when nothing else interferes?  python tools/shard_probe.py [world] [rank] [cfg]
+"""What does ONE rank of an N-GPU run cost when nothing else interferes?  python tools/shard_probe.py [world] [rank] [cfg] [rows|cols|auto]
 All `world` ranks of the tile-sharded path are emulated on one device (plain device buffers as arenas / flag blocks, as in
 tests/test_gpu_sharded.py); only rank r's work is timed: its band phase of step s next to its owner phase of step s+1 (what
 overlaps in a real run with two arena sets), the band phase alone, and the owner phase alone.  The other ranks' owners run
@@ -15,12 +15,13 @@ from simplepanorama_b200 import api, synth, dist
 world = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 r = int(sys.argv[2]) if len(sys.argv) > 2 else world // 2
 name = sys.argv[3] if len(sys.argv) > 3 else "cfg2"
+orient = sys.argv[4] if len(sys.argv) > 4 else "rows"
 dev = torch.device("cuda", 0)
 cfg = synth.config(name, 1.0)
 K, R, gains = synth.cameras(cfg)
 plan = api.plan_tiles([bench._Shape(cfg.height, cfg.width)] * cfg.n, R, K, cfg.kind, cfg.focal)
 corners, sizes = [p[2] for p in plan], [p[3] for p in plan]
-sp = dist.plan_tile_shards(corners, sizes, world, cfg.sigma)
+sp = dist.plan_tile_shards(corners, sizes, world, cfg.sigma, orient=orient)
 n = cfg.n
 cuts = [synth.seam_masks(corners, sizes, only=j, coarse=True) for j in range(n)]
 imgs = [bench.make_image_torch(torch, cfg, j, gains[j], dev) for j in range(n)]
@@ -32,9 +33,8 @@ canvas = torch.zeros((sp.canvas_h, sp.canvas_w, 3), dtype=torch.uint8, device=de
 
 
 def session(k):
-    r0, _ = sp.bands[k]
     return dist.ShardSession(sp, k, cfg.kind, cfg.focal, cfg.bands, cfg.sigma, [a.data_ptr() for a in arenas[0]], [f.data_ptr() for f in flags],
-                             canvas.data_ptr() + r0 * canvas.stride(0), canvas.stride(0), arena_ptrs2=[a.data_ptr() for a in arenas[1]])
+                             canvas.data_ptr() + sp.band_origin(k, canvas.stride(0)), canvas.stride(0), arena_ptrs2=[a.data_ptr() for a in arenas[1]])
 
 
 own_ctx = [api.Context(0) for _ in range(world)]
@@ -97,7 +97,7 @@ for s in range(1, K_STEPS + 1):
         res[mode].append(t)
     fake_done(s)
 b0, b1 = sp.bands[r]
-print(f"{name} world {world} rank {r}: band rows {b0}..{b1} of {sp.canvas_h}, owns {sp.owner.count(r)} of {n} images, "
+print(f"{name} world {world} rank {r}: band {'columns' if sp.orient == 'cols' else 'rows'} {b0}..{b1} of {sp.canvas_w if sp.orient == 'cols' else sp.canvas_h}, owns {sp.owner.count(r)} of {n} images, "
       f"{sum(1 for j in range(n) if sp.slices[r][j] is not None)} tiles touch the band")
 for k, v in res.items():
     if v:
